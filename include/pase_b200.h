@@ -1,0 +1,207 @@
+/*
+ * pase_b200 -- C-ABI of the B200-native PASE/PASE+ hot path (sm_100a).
+ *
+ * The reference (santi-pdp/pase) is pure Python/PyTorch and has no FFI; the
+ * boundary a maintainer binds is therefore this library, loaded with ctypes
+ * from the Python shim (pase_b200/_lib.py) that mirrors
+ * pase.models.frontend.wf_builder / pase.models.pase.pase.  Every entry point
+ * below replaces one library call (cuDNN / cuBLAS / ATen / torchqrnn) that the
+ * reference issues on this path; the reference call site is cited per entry
+ * as /root/reference/<file>:<line>.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers into buffers owned by the caller
+ *     (PyTorch caching allocator); the library allocates nothing persistent;
+ *   - activations are channel-last: (sample, time, channel), fp32;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = ok, otherwise a negative pase error code or a positive
+ *     cudaError_t; pase_last_error() returns a thread-local message.
+ */
+#ifndef PASE_B200_H
+#define PASE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PASE_OK 0
+#define PASE_ERR_ARG (-1)
+#define PASE_ERR_UNSUPPORTED (-2)
+
+const char* pase_last_error(void);
+int pase_version(void);
+/* Device properties the host side sizes grids with: out[0]=SM count,
+ * out[1]=cc major, out[2]=cc minor, out[3]=max opt-in smem per block. */
+int pase_device_info(int* out4);
+
+/* ---- GEMM family (replaces F.conv1d / nn.Conv1d / nn.Linear /
+ * nn.ConvTranspose1d and their backward: modules.py:932,1072,
+ * frontend.py:195,244-262, minions.py:494-524, torchqrnn linear) -----------
+ *
+ * pase_gemm_nt:  C[map(m), n] (+)= alpha * sum_k A[m*lda + k] * B[n*ldb + k] + bias[n]
+ *   A may be an OVERLAPPING-row view (lda < K): row m of a strided 1-D
+ *   convolution's implicit im2col matrix is K contiguous floats of the padded
+ *   channel-last activation starting at m*lda.
+ *   Row map: g = m / rows_in, u = m % rows_in.  Element (u, n) is valid iff
+ *   u*fold + n/(N/fold) < t_valid; it is stored at row g*rows_out + u.
+ *   colsum/colsumsq (double[N], may be NULL) accumulate the per-column sum and
+ *   sum of squares of the valid outputs (BatchNorm batch statistics).
+ *   prec: 0 = fp32 FFMA, (tensor-core modes added by later entry points).
+ */
+int pase_gemm_nt(const float* A, long lda, const float* B, long ldb,
+                 float* C, long ldc, int M, int N, int K,
+                 float alpha, const float* bias,
+                 int rows_in, int t_valid, int rows_out, int fold,
+                 double* colsum, double* colsumsq, int accumulate,
+                 void* stream);
+
+/* pase_gemm_tn:  C[i, j] (+)= alpha * sum_r A[rowA(r)*lda + i] * B[rowB(r)*ldb + j]
+ *   r in [0, groups*rows_per_group): g = r / rows_per_group, u = r % rows_per_group,
+ *   rowA = g*pitchA + offA + u, rowB = g*pitchB + offB + u.
+ *   (weight gradients: reduction over samples x time.) */
+int pase_gemm_tn(const float* A, long lda, int pitchA, int offA,
+                 const float* B, long ldb, int pitchB, int offB,
+                 float* C, long ldc, int I, int J,
+                 int groups, int rows_per_group,
+                 float alpha, int accumulate, void* stream);
+
+/* ---- weight re-layout (implicit-GEMM operand preparation) ---------------- */
+/* (Cout,Cin,k) -> Wt[co, j*Cin+ci]                      (forward operand)   */
+int pase_conv_w_to_fwd(const float* W, float* Wt, int Cout, int Cin, int k, void* stream);
+/* (Cout,Cin,k) -> Wd[p*Cin+ci, v*Cout+co] = W[co,ci,s*(taps-1-v)+p] or 0    */
+int pase_conv_w_to_dgrad(const float* W, float* Wd, int Cout, int Cin, int k,
+                         int s, int taps, void* stream);
+/* dWt[co, j*Cin+ci] -> dW (Cout,Cin,k)                                      */
+int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, void* stream);
+/* ConvTranspose1d weight (Cin,Cout,k) -> Wu[p*Cout+co, v*Cin+ci] =
+ * W[ci,co,s*(taps-1-v)+p] or 0 (forward operand of the transposed conv)     */
+int pase_deconv_w_to_fwd(const float* W, float* Wu, int Cin, int Cout, int k,
+                         int s, int taps, void* stream);
+/* dWu -> dW (Cin,Cout,k) (inverse gather of the above)                      */
+int pase_deconv_w_from_fwd(const float* dWu, float* dW, int Cin, int Cout, int k,
+                           int s, int taps, void* stream);
+/* dst (cols x ldd) = src(rows x cols)^T, zero-padding columns rows..ldd-1 */
+int pase_transpose_pad(const float* src, long lds, float* dst, long ldd, int rows, int cols,
+                       void* stream);
+/* ConvTranspose1d weight -> backward-data operand Wb[ci, j*Cout+co]=W[ci,co,j] */
+int pase_deconv_w_to_bwd(const float* W, float* Wb, int Cin, int Cout, int k, void* stream);
+
+/* ---- SincConv_fast band-pass generator (modules.py:868-918) -------------- */
+/* low_hz_,band_hz_ (C) + host-precomputed n_ and window_ (k/2 each) ->
+ * polyphase forward operand Wp[(p*C+co), kk] = filt[co][kk-p] (0 outside),
+ * p < fold, kk < Kv; also writes filt (C,k) if non-NULL. */
+int pase_sinc_make(const float* low_hz, const float* band_hz,
+                   const float* n_, const float* window_,
+                   float* filt, float* Wp, int C, int k, int fold, int Kv,
+                   float min_low, float min_band, float sr, void* stream);
+/* dWp -> d low_hz_, d band_hz_ (through abs / clamp / sin) */
+int pase_sinc_grad(const float* dWp, const float* low_hz, const float* band_hz,
+                   const float* n_, const float* window_,
+                   float* dlow, float* dband, int C, int k, int fold, int Kv,
+                   float min_low, float min_band, float sr, void* stream);
+
+/* ---- padding / BatchNorm / PReLU (F.pad reflect, nn.BatchNorm1d, nn.PReLU:
+ * modules.py:924-928,1071-1075,79,111-113) --------------------------------- */
+/* (N,T) waveform -> reflect-padded rows of pitch `pitch` floats */
+int pase_reflect_pad_wave(const float* x, float* dst, int N, int T, int padL, int padR,
+                          long pitch, void* stream);
+/* batch statistics -> per-channel affine; updates running stats (training) */
+int pase_bn_finalize(const double* colsum, const double* colsumsq, int C, int fold,
+                     double count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream);
+int pase_bn_eval_affine(const float* running_mean, const float* running_var,
+                        const float* gamma, const float* beta, int C, float eps,
+                        float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* a = PReLU(y*scale+shift) written with reflect halo into the next layer's
+ * padded buffer, plus mean-pooled dense-skip accumulation (frontend.py:213-232) */
+int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, int C,
+                          const float* scale, const float* shift, const float* alpha,
+                          float* dst, long dst_sample_stride, long dst_row_stride,
+                          int padL, int padR,
+                          float* pool, long pool_sample_stride, long pool_row_stride,
+                          int pool_d, int pool_T, void* stream);
+/* backward, pass 1: g = sum of gradient sources; du = PReLU'(u) g written to
+ * dst; accumulates S1=sum du, S2=sum du*xhat, dalpha (double[C] each). */
+int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T, int C,
+                             const float* mean, const float* invstd,
+                             const float* scale, const float* shift, const float* alpha,
+                             const float* srcA, long a_sample_stride, long a_row_stride,
+                             int padL, int padR,
+                             const float* srcB, long b_sample_stride, long b_row_stride,
+                             int b_shift,
+                             const float* pool, long pool_sample_stride, long pool_row_stride,
+                             int pool_d, int pool_T,
+                             float* dst, long dst_sample_stride,
+                             double* S1, double* S2, double* dalpha, void* stream);
+/* backward, pass 2 (in place on dst): dy = gamma*invstd*(du - S1/M - xhat*S2/M);
+ * also finalises dgamma=S2, dbeta=S1, dalpha and db = sum dy.  */
+int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, int C,
+                            const float* mean, const float* invstd, const float* gamma,
+                            const double* S1, const double* S2, double count,
+                            float* dst, long dst_sample_stride,
+                            double* dbias_acc, void* stream);
+/* plain per-channel PReLU on (rows,C) (MLPBlock / GDeconv1DBlock act) */
+int pase_prelu_fwd(const float* u, float* h, const float* alpha, long rows, int C,
+                   long ldu, long ldh, void* stream);
+int pase_prelu_bwd(const float* u, const float* dh, const float* alpha, float* du,
+                   double* dalpha, long rows, int C, long ldu, long lddh, long lddu,
+                   void* stream);
+/* acc[c] += sum_r X[r*ld+c]  (bias gradients) */
+int pase_colsum(const float* X, long ld, long rows, int C, double* acc, void* stream);
+int pase_cast_d2f(const double* src, float* dst, int n, float scale, void* stream);
+
+/* ---- output BatchNorm(affine=False) + layout change (frontend.py:206-208,
+ * 266-268): (N*T,C) channel-last -> (N,C,T) ------------------------------- */
+/* out (N,C,T) = y*scale+shift; optionally also the channel-last copy out_ntc */
+int pase_out_affine_nct(const float* y, const float* scale, const float* shift,
+                        float* out, float* out_ntc, int N, int T, int C, void* stream);
+/* g_ntc = dout(N,C,T)^T + dout_ntc; S1 += g, S2 += g*xhat (double[C]) */
+int pase_out_bwd_reduce(const float* dout, const float* dout_ntc, const float* y,
+                        const float* mean, const float* invstd, int N, int T, int C,
+                        float* g_ntc, double* S1, double* S2, void* stream);
+/* in place: g = scale*(g - use_stats*(S1/M + xhat*S2/M)) */
+int pase_out_bwd_apply(float* g, const float* y, const float* mean, const float* invstd,
+                       const float* scale, const double* S1, const double* S2,
+                       double count, int use_stats, long rows, int C, void* stream);
+/* generic (N,C,T) <-> (N,T,C) */
+int pase_nct_to_ntc(const float* src, float* dst, int N, int C, int T, long dst_row_stride,
+                    void* stream);
+int pase_ntc_to_nct(const float* src, long src_row_stride, float* dst, int N, int C, int T,
+                    void* stream);
+
+/* ---- QRNN (torchqrnn.QRNN window=2 as called at modules.py:52) ----------- */
+/* Y (rows=N*T, 3H) pre-activations -> h (row stride ldh), cell state Cst (rows,H) */
+int pase_qrnn_scan_fwd(const float* Y, float* h, long ldh, float* Cst,
+                       int N, int T, int H, void* stream);
+int pase_qrnn_scan_bwd(const float* Y, const float* Cst, const float* dh, long lddh,
+                       float* dY, int N, int T, int H, void* stream);
+
+/* ---- worker losses (losses.py:6-37, utils.py:63-68) ----------------------- */
+/* pred (B*T, F*r) channel-last, label (B,F,T): sum (pred - ctx(label))^2 -> acc */
+int pase_ctx_mse_fwd(const float* pred, long ldp, const float* label,
+                     int B, int F, int T, int r, double* acc, void* stream);
+/* dpred = coef * gscale[0] * (pred - ctx(label)) */
+int pase_ctx_mse_bwd(const float* pred, long ldp, const float* label,
+                     int B, int F, int T, int r, float coef, const float* gscale,
+                     float* dpred, long lddp, void* stream);
+int pase_l1_fwd(const float* pred, const float* target, long n, double* acc, void* stream);
+int pase_l1_bwd(const float* pred, const float* target, long n, float coef,
+                const float* gscale, float* dpred, void* stream);
+/* BCEWithLogits against labels 1 for rows < half_rows, else 0 */
+int pase_bce_pairs_fwd(const float* logit, long n, long n_pos, double* acc, void* stream);
+int pase_bce_pairs_bwd(const float* logit, long n, long n_pos, float coef,
+                       const float* gscale, float* dlogit, void* stream);
+/* time-mean over (B,T,C) channel-last -> (B,C) and its backward (GIM) */
+int pase_time_mean_fwd(const float* x, long ldx, float* out, long ldo, int B, int T, int C,
+                       void* stream);
+int pase_time_mean_bwd(const float* dout, long ldo, float* dx, long ldx, int B, int T, int C,
+                       int accumulate, void* stream);
+/* misc fused vector helpers */
+int pase_axpy(const float* x, float* y, long n, float a, void* stream);
+int pase_scale_dev(float* x, long n, const float* dev_scalar, float host_coef, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,692 @@
+// Padding, BatchNorm (batch statistics), PReLU and dense-skip pooling kernels.
+// All HBM-bound: channel-last float4 accesses, one pass per tensor.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RUN = 8;      // consecutive time steps handled by one thread
+constexpr int THREADS = 256;
+
+__global__ void reflect_pad_wave_kernel(const float* __restrict__ x, float* __restrict__ dst,
+                                        int T, int padL, int Tp, long pitch) {
+  const int n = blockIdx.y;
+  for (int tau = blockIdx.x * blockDim.x + threadIdx.x; tau < Tp; tau += gridDim.x * blockDim.x)
+    dst[(long)n * pitch + tau] = x[(long)n * T + reflect_idx(tau - padL, T)];
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ colsum,
+                                   const double* __restrict__ colsumsq, int C, int fold,
+                                   double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean,
+                                   float* running_var, float momentum, float eps, float* mean,
+                                   float* invstd, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < fold; ++p) {
+    s += colsum[p * C + c];
+    q += colsumsq[p * C + c];
+  }
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const double is = 1.0 / sqrt(var + (double)eps);
+  if (running_mean != nullptr) {
+    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+  }
+  const double g = gamma ? (double)gamma[c] : 1.0;
+  const double b = beta ? (double)beta[c] : 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)is;
+  scale[c] = (float)(g * is);
+  shift[c] = (float)(b - m * g * is);
+}
+
+__global__ void bn_eval_affine_kernel(const float* __restrict__ rm, const float* __restrict__ rv,
+                                      const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int C, float eps,
+                                      float* mean, float* invstd, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double is = 1.0 / sqrt((double)rv[c] + (double)eps);
+  const double g = gamma ? (double)gamma[c] : 1.0;
+  const double b = beta ? (double)beta[c] : 0.0;
+  mean[c] = rm[c];
+  invstd[c] = (float)is;
+  scale[c] = (float)(g * is);
+  shift[c] = (float)(b - (double)rm[c] * g * is);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float prelu1(float u, float a) { return u > 0.f ? u : a * u; }
+
+__global__ void __launch_bounds__(THREADS)
+bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ alpha, float* __restrict__ dst, long d_ss,
+                        long d_rs, int padL, int Tp, float* __restrict__ pool, long p_ss,
+                        long p_rs, int pool_d, int pool_T) {
+  const int C4 = C >> 2;
+  const int n = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (int)(idx % C4);
+  const long run = idx / C4;
+  const long tau0 = run * RUN;
+  if (tau0 >= Tp) return;
+  const int c = q * 4;
+  const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
+  const float* yn = y + (long)n * y_ss;
+  float* dn = dst + (long)n * d_ss;
+  const int pool_len = pool_d > 0 ? pool_T * pool_d : 0;
+  const float inv_d = pool_d > 0 ? 1.f / (float)pool_d : 0.f;
+  float4 pacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int pw = -1;
+  auto flush = [&]() {
+    if (pw >= 0) {
+      float* pp = pool + (long)n * p_ss + (long)pw * p_rs + c;
+      atomicAdd(pp + 0, pacc.x * inv_d);
+      atomicAdd(pp + 1, pacc.y * inv_d);
+      atomicAdd(pp + 2, pacc.z * inv_d);
+      atomicAdd(pp + 3, pacc.w * inv_d);
+    }
+    pacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+#pragma unroll 1
+  for (int i = 0; i < RUN; ++i) {
+    const long tau = tau0 + i;
+    if (tau >= Tp) break;
+    const int tr = (int)tau - padL;
+    const int t = reflect_idx(tr, T);
+    const float4 v = ld4(yn + (long)t * C + c);
+    float4 a;
+    a.x = prelu1(fmaf(v.x, sc.x, sh.x), al.x);
+    a.y = prelu1(fmaf(v.y, sc.y, sh.y), al.y);
+    a.z = prelu1(fmaf(v.z, sc.z, sh.z), al.z);
+    a.w = prelu1(fmaf(v.w, sc.w, sh.w), al.w);
+    st4(dn + tau * d_rs + c, a);
+    if (tr >= 0 && tr < pool_len) {
+      const int w = tr / pool_d;
+      if (w != pw) {
+        flush();
+        pw = w;
+      }
+      pacc.x += a.x; pacc.y += a.y; pacc.z += a.z; pacc.w += a.w;
+    }
+  }
+  flush();
+}
+
+// ---- backward pass 1: du + reductions ----
+struct BwdSrc {
+  const float* A; long a_ss, a_rs; int padL, padR;
+  const float* B; long b_ss, b_rs; int b_shift;
+  const float* P; long p_ss, p_rs; int pool_d, pool_T;
+};
+
+__global__ void __launch_bounds__(THREADS)
+bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
+                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                           const float* __restrict__ scale, const float* __restrict__ shift,
+                           const float* __restrict__ alpha, BwdSrc s, float* __restrict__ dst,
+                           long d_ss, double* __restrict__ S1, double* __restrict__ S2,
+                           double* __restrict__ dalpha) {
+  extern __shared__ float red[];      // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int n = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (int)(idx % C4);
+  const long run = idx / C4;
+  const long t0 = run * RUN;
+  if (t0 < T) {
+    const int c = q * 4;
+    const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
+    const float4 mu = ld4(mean + c), is = ld4(invstd + c);
+    const float* yn = y + (long)n * y_ss;
+    float* dn = dst + (long)n * d_ss;
+    const int pool_len = s.pool_d > 0 ? s.pool_T * s.pool_d : 0;
+    const float inv_d = s.pool_d > 0 ? 1.f / (float)s.pool_d : 0.f;
+    float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, a3[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int i = 0; i < RUN; ++i) {
+      const int t = (int)t0 + i;
+      if (t >= T) break;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto add4 = [&](const float* p, float w) {
+        const float4 v = ld4(p);
+        g.x += v.x * w; g.y += v.y * w; g.z += v.z * w; g.w += v.w * w;
+      };
+      if (s.A) {
+        const float* an = s.A + (long)n * s.a_ss + c;
+        add4(an + (long)(t + s.padL) * s.a_rs, 1.f);
+        if (s.padL > 0 && t >= 1 && t <= s.padL) add4(an + (long)(s.padL - t) * s.a_rs, 1.f);
+        if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
+          add4(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs, 1.f);
+      }
+      if (s.B) {
+        const int tb = t + s.b_shift;
+        if (tb >= 0 && tb < T) add4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c, 1.f);
+      }
+      if (s.P && t < pool_len)
+        add4(s.P + (long)n * s.p_ss + (long)(t / s.pool_d) * s.p_rs + c, inv_d);
+      const float4 v = ld4(yn + (long)t * C + c);
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+      const float alv[4] = {al.x, al.y, al.z, al.w};
+      const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+      float du[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float u = fmaf(vv[k], scv[k], shv[k]);
+        const bool pos = u > 0.f;
+        du[k] = pos ? gg[k] : alv[k] * gg[k];
+        a3[k] += pos ? 0.f : u * gg[k];
+        const float xh = (vv[k] - muv[k]) * isv[k];
+        a1[k] += du[k];
+        a2[k] += du[k] * xh;
+      }
+      st4(dn + (long)t * C + c, make_float4(du[0], du[1], du[2], du[3]));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&red[0 * C + c + k], a1[k]);
+      atomicAdd(&red[1 * C + c + k], a2[k]);
+      atomicAdd(&red[2 * C + c + k], a3[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(S1 + i, (double)red[0 * C + i]);
+    atomicAdd(S2 + i, (double)red[1 * C + i]);
+    atomicAdd(dalpha + i, (double)red[2 * C + i]);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS)
+bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const float* __restrict__ gamma, const double* __restrict__ S1,
+                          const double* __restrict__ S2, double inv_count,
+                          float* __restrict__ dst, long d_ss, double* __restrict__ dbias) {
+  extern __shared__ float red[];      // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int n = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (int)(idx % C4);
+  const long run = idx / C4;
+  const long t0 = run * RUN;
+  if (t0 < T) {
+    const int c = q * 4;
+    float m1[4], m2[4], gi[4], muv[4], isv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      m1[k] = (float)(S1[c + k] * inv_count);
+      m2[k] = (float)(S2[c + k] * inv_count);
+      muv[k] = mean[c + k];
+      isv[k] = invstd[c + k];
+      gi[k] = (gamma ? gamma[c + k] : 1.f) * isv[k];
+    }
+    const float* yn = y + (long)n * y_ss;
+    float* dn = dst + (long)n * d_ss;
+    float acc[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int i = 0; i < RUN; ++i) {
+      const int t = (int)t0 + i;
+      if (t >= T) break;
+      const float4 v = ld4(yn + (long)t * C + c);
+      const float4 d = ld4(dn + (long)t * C + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xh = (vv[k] - muv[k]) * isv[k];
+        o[k] = gi[k] * (dd[k] - m1[k] - xh * m2[k]);
+        acc[k] += o[k];
+      }
+      st4(dn + (long)t * C + c, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    if (dbias) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&red[c + k], acc[k]);
+    }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, (double)red[i]);
+  }
+}
+
+// ---- plain PReLU on (rows, C) ----
+__global__ void prelu_fwd_kernel(const float* __restrict__ u, float* __restrict__ h,
+                                 const float* __restrict__ alpha, long rows, int C, long ldu,
+                                 long ldh) {
+  const long total = rows * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const long r = i / C;
+    const int c = (int)(i - r * C);
+    h[r * ldh + c] = prelu1(u[r * ldu + c], alpha[c]);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS)
+prelu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dh,
+                 const float* __restrict__ alpha, float* __restrict__ du,
+                 double* __restrict__ dalpha, long rows, int C, long ldu, long lddh, long lddu) {
+  extern __shared__ float red[];      // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  // thread owns one channel of a strip of rows: coalesced over c
+  const int cpb = min(C, (int)blockDim.x);         // channels covered per row pass
+  const int rows_per_pass = blockDim.x / cpb;
+  const int lc = threadIdx.x % cpb, lr = threadIdx.x / cpb;
+  for (int c0 = 0; c0 < C; c0 += cpb) {
+    const int c = c0 + lc;
+    if (c >= C || lr >= rows_per_pass) continue;
+    const float a = alpha[c];
+    float acc = 0.f;
+    for (long r = (long)blockIdx.x * rows_per_pass + lr; r < rows;
+         r += (long)gridDim.x * rows_per_pass) {
+      const float uu = u[r * ldu + c], g = dh[r * lddh + c];
+      const bool pos = uu > 0.f;
+      du[r * lddu + c] = pos ? g : a * g;
+      acc += pos ? 0.f : uu * g;
+    }
+    atomicAdd(&red[c], acc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dalpha + i, (double)red[i]);
+}
+
+
+// out[c] (+)= sum_r X[r*ld + c]
+__global__ void __launch_bounds__(THREADS)
+colsum_kernel(const float* __restrict__ X, long ld, long rows, int C, double* __restrict__ acc) {
+  extern __shared__ float red[];      // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int cpb = min(C, (int)blockDim.x);
+  const int rows_per_pass = blockDim.x / cpb;
+  const int lc = threadIdx.x % cpb, lr = threadIdx.x / cpb;
+  for (int c0 = 0; c0 < C; c0 += cpb) {
+    const int c = c0 + lc;
+    if (c >= C || lr >= rows_per_pass) continue;
+    float a = 0.f;
+    for (long r = (long)blockIdx.x * rows_per_pass + lr; r < rows;
+         r += (long)gridDim.x * rows_per_pass)
+      a += X[r * ld + c];
+    atomicAdd(&red[c], a);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(acc + i, (double)red[i]);
+}
+
+__global__ void cast_d2f_kernel(const double* __restrict__ src, float* __restrict__ dst, int n,
+                                float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)(src[i] * (double)scale);
+}
+
+// ---- output affine + (N*T,C) -> (N,C,T) ----
+__global__ void out_affine_nct_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, float* __restrict__ out,
+                                      float* __restrict__ out_ntc, int T, int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) {
+      const float v = fmaf(y[((long)n * T + t) * C + c], scale[c], shift[c]);
+      tile[i][threadIdx.x] = v;
+      if (out_ntc) out_ntc[((long)n * T + t) * C + c] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (t < T && c < C) out[((long)n * C + c) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
+// g[n,t,c] = dout_nct[n,c,t] (+ dout_ntc[n,t,c]); S1 += g, S2 += g*xhat
+__global__ void out_bwd_reduce_kernel(const float* __restrict__ dout,
+                                      const float* __restrict__ dout_ntc,
+                                      const float* __restrict__ y, const float* __restrict__ mean,
+                                      const float* __restrict__ invstd, int T, int C,
+                                      float* __restrict__ g_ntc, double* __restrict__ S1,
+                                      double* __restrict__ S2) {
+  __shared__ float tile[32][33];
+  __shared__ float r1[32], r2[32];
+  const int n = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (threadIdx.y == 0) { r1[threadIdx.x] = 0.f; r2[threadIdx.x] = 0.f; }
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (dout && t < T && c < C) ? dout[((long)n * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  float a1 = 0.f, a2 = 0.f;
+  const int c = c0 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i;
+    if (t < T && c < C) {
+      const long o = ((long)n * T + t) * C + c;
+      float g = tile[threadIdx.x][i];
+      if (dout_ntc) g += dout_ntc[o];
+      g_ntc[o] = g;
+      const float xh = (y[o] - mean[c]) * invstd[c];
+      a1 += g;
+      a2 += g * xh;
+    }
+  }
+  atomicAdd(&r1[threadIdx.x], a1);
+  atomicAdd(&r2[threadIdx.x], a2);
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    atomicAdd(S1 + c, (double)r1[threadIdx.x]);
+    atomicAdd(S2 + c, (double)r2[threadIdx.x]);
+  }
+}
+
+// in place on g (N*T,C): dy = scale_c*(g - use*(S1/M + xhat*S2/M))
+__global__ void out_bwd_apply_kernel(float* __restrict__ g, const float* __restrict__ y,
+                                     const float* __restrict__ mean,
+                                     const float* __restrict__ invstd,
+                                     const float* __restrict__ scale,
+                                     const double* __restrict__ S1, const double* __restrict__ S2,
+                                     double inv_count, int use_stats, long rows, int C) {
+  const long total = rows * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float v = g[i];
+    if (use_stats) {
+      const float xh = (y[i] - mean[c]) * invstd[c];
+      v = v - (float)(S1[c] * inv_count) - xh * (float)(S2[c] * inv_count);
+    }
+    g[i] = v * scale[c];
+  }
+}
+
+__global__ void nct_to_ntc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
+                                  int T, long d_rs) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (t < T && c < C) tile[i][threadIdx.x] = src[((long)n * C + c) * T + t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) dst[((long)n * T + t) * d_rs + c] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void ntc_to_nct_kernel(const float* __restrict__ src, long s_rs,
+                                  float* __restrict__ dst, int C, int T) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) tile[i][threadIdx.x] = src[((long)n * T + t) * s_rs + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (t < T && c < C) dst[((long)n * C + c) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float a) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+
+__global__ void scale_dev_kernel(float* __restrict__ x, long n, const float* __restrict__ s,
+                                 float coef) {
+  const float f = (s ? s[0] : 1.f) * coef;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x)
+    x[i] *= f;
+}
+
+inline unsigned blocks_for(long total, int threads, int cap_mult = 8) {
+  long b = (total + threads - 1) / threads;
+  long cap = (long)pase_num_sms() * cap_mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pase_reflect_pad_wave(const float* x, float* dst, int N, int T, int padL, int padR,
+                          long pitch, void* stream) {
+  PASE_CHECK_ARG(x && dst && N > 0 && T > 0, "pase_reflect_pad_wave: bad args");
+  PASE_CHECK_ARG(padL < T && padR < T, "pase_reflect_pad_wave: reflect pad (%d,%d) >= T=%d", padL,
+                 padR, T);
+  const int Tp = T + padL + padR;
+  PASE_CHECK_ARG(pitch >= Tp, "pase_reflect_pad_wave: pitch %ld < padded length %d", pitch, Tp);
+  dim3 grid(blocks_for(Tp, 256, 4), N);
+  reflect_pad_wave_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dst, T, padL, Tp, pitch);
+  PASE_LAUNCH_CHECK("pase_reflect_pad_wave");
+  return PASE_OK;
+}
+
+int pase_bn_finalize(const double* colsum, const double* colsumsq, int C, int fold, double count,
+                     const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, float* mean, float* invstd,
+                     float* scale, float* shift, void* stream) {
+  PASE_CHECK_ARG(colsum && colsumsq && mean && invstd && scale && shift && C > 0 && fold > 0,
+                 "pase_bn_finalize: bad args");
+  PASE_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr),
+                 "pase_bn_finalize: running stats must be given together");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      colsum, colsumsq, C, fold, count, gamma, beta, running_mean, running_var, momentum, eps,
+      mean, invstd, scale, shift);
+  PASE_LAUNCH_CHECK("pase_bn_finalize");
+  return PASE_OK;
+}
+
+int pase_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma,
+                        const float* beta, int C, float eps, float* mean, float* invstd,
+                        float* scale, float* shift, void* stream) {
+  PASE_CHECK_ARG(running_mean && running_var && C > 0, "pase_bn_eval_affine: bad args");
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      running_mean, running_var, gamma, beta, C, eps, mean, invstd, scale, shift);
+  PASE_LAUNCH_CHECK("pase_bn_eval_affine");
+  return PASE_OK;
+}
+
+int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, int C,
+                          const float* scale, const float* shift, const float* alpha, float* dst,
+                          long dst_sample_stride, long dst_row_stride, int padL, int padR,
+                          float* pool, long pool_sample_stride, long pool_row_stride, int pool_d,
+                          int pool_T, void* stream) {
+  PASE_CHECK_ARG(y && dst && scale && shift && alpha, "pase_bn_prelu_pad_fwd: null pointer");
+  PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0,
+                 "pase_bn_prelu_pad_fwd: C=%d must be a positive multiple of 4", C);
+  PASE_CHECK_ARG((padL == 0 && padR == 0) || (padL < T && padR < T),
+                 "pase_bn_prelu_pad_fwd: reflect pad (%d,%d) >= T=%d", padL, padR, T);
+  PASE_CHECK_ARG((dst_row_stride % 4) == 0 && (dst_sample_stride % 4) == 0 &&
+                     (y_sample_stride % 4) == 0 && aligned16(y) && aligned16(dst),
+                 "pase_bn_prelu_pad_fwd: strides/pointers must be float4 aligned");
+  if (pool_d <= 1 && pool == nullptr) pool_d = 0;
+  if (pool == nullptr) pool_d = 0;
+  const int Tp = T + padL + padR;
+  const long threads = (long)(C / 4) * ((Tp + RUN - 1) / RUN);
+  dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
+  bn_prelu_pad_fwd_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(
+      y, y_sample_stride, T, C, scale, shift, alpha, dst, dst_sample_stride, dst_row_stride, padL,
+      Tp, pool, pool_sample_stride, pool_row_stride, pool_d, pool_T);
+  PASE_LAUNCH_CHECK("pase_bn_prelu_pad_fwd");
+  return PASE_OK;
+}
+
+int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T, int C,
+                             const float* mean, const float* invstd, const float* scale,
+                             const float* shift, const float* alpha, const float* srcA,
+                             long a_sample_stride, long a_row_stride, int padL, int padR,
+                             const float* srcB, long b_sample_stride, long b_row_stride,
+                             int b_shift, const float* pool, long pool_sample_stride,
+                             long pool_row_stride, int pool_d, int pool_T, float* dst,
+                             long dst_sample_stride, double* S1, double* S2, double* dalpha,
+                             void* stream) {
+  PASE_CHECK_ARG(y && mean && invstd && scale && shift && alpha && dst && S1 && S2 && dalpha,
+                 "pase_bn_prelu_bwd_reduce: null pointer");
+  PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 4096,
+                 "pase_bn_prelu_bwd_reduce: C=%d must be a multiple of 4, <= 4096", C);
+  BwdSrc s{srcA, a_sample_stride, a_row_stride, padL, padR, srcB, b_sample_stride, b_row_stride,
+           b_shift, pool, pool_sample_stride, pool_row_stride, pool ? pool_d : 0, pool_T};
+  const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
+  dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
+  bn_prelu_bwd_reduce_kernel<<<grid, THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
+      y, y_sample_stride, T, C, mean, invstd, scale, shift, alpha, s, dst, dst_sample_stride, S1,
+      S2, dalpha);
+  PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_reduce");
+  return PASE_OK;
+}
+
+int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, int C,
+                            const float* mean, const float* invstd, const float* gamma,
+                            const double* S1, const double* S2, double count, float* dst,
+                            long dst_sample_stride, double* dbias_acc, void* stream) {
+  PASE_CHECK_ARG(y && mean && invstd && S1 && S2 && dst, "pase_bn_prelu_bwd_apply: null pointer");
+  PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 8192,
+                 "pase_bn_prelu_bwd_apply: bad C=%d", C);
+  const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
+  dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
+  bn_prelu_bwd_apply_kernel<<<grid, THREADS, C * sizeof(float), (cudaStream_t)stream>>>(
+      y, y_sample_stride, T, C, mean, invstd, gamma, S1, S2, 1.0 / count, dst, dst_sample_stride,
+      dbias_acc);
+  PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_apply");
+  return PASE_OK;
+}
+
+int pase_prelu_fwd(const float* u, float* h, const float* alpha, long rows, int C, long ldu,
+                   long ldh, void* stream) {
+  PASE_CHECK_ARG(u && h && alpha && rows > 0 && C > 0, "pase_prelu_fwd: bad args");
+  prelu_fwd_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(u, h, alpha, rows,
+                                                                                C, ldu, ldh);
+  PASE_LAUNCH_CHECK("pase_prelu_fwd");
+  return PASE_OK;
+}
+
+int pase_prelu_bwd(const float* u, const float* dh, const float* alpha, float* du, double* dalpha,
+                   long rows, int C, long ldu, long lddh, long lddu, void* stream) {
+  PASE_CHECK_ARG(u && dh && alpha && du && dalpha && rows > 0 && C > 0 && C <= 8192,
+                 "pase_prelu_bwd: bad args");
+  const int cpb = C < THREADS ? C : THREADS;
+  const int rpp = THREADS / cpb;
+  long nb = (rows + rpp - 1) / rpp;
+  long cap = (long)pase_num_sms() * 4;
+  if (nb > cap) nb = cap;
+  prelu_bwd_kernel<<<(unsigned)nb, THREADS, C * sizeof(float), (cudaStream_t)stream>>>(
+      u, dh, alpha, du, dalpha, rows, C, ldu, lddh, lddu);
+  PASE_LAUNCH_CHECK("pase_prelu_bwd");
+  return PASE_OK;
+}
+
+int pase_colsum(const float* X, long ld, long rows, int C, double* acc, void* stream) {
+  PASE_CHECK_ARG(X && acc && rows > 0 && C > 0 && C <= 8192, "pase_colsum: bad args");
+  const int cpb = C < THREADS ? C : THREADS;
+  const int rpp = THREADS / cpb;
+  long nb = (rows + rpp * 8 - 1) / (rpp * 8);
+  long cap = (long)pase_num_sms() * 4;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  colsum_kernel<<<(unsigned)nb, THREADS, C * sizeof(float), (cudaStream_t)stream>>>(X, ld, rows, C,
+                                                                                   acc);
+  PASE_LAUNCH_CHECK("pase_colsum");
+  return PASE_OK;
+}
+
+int pase_cast_d2f(const double* src, float* dst, int n, float scale, void* stream) {
+  PASE_CHECK_ARG(src && dst && n > 0, "pase_cast_d2f: bad args");
+  cast_d2f_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, dst, n, scale);
+  PASE_LAUNCH_CHECK("pase_cast_d2f");
+  return PASE_OK;
+}
+
+int pase_out_affine_nct(const float* y, const float* scale, const float* shift, float* out,
+                        float* out_ntc, int N, int T, int C, void* stream) {
+  PASE_CHECK_ARG(y && scale && shift && out && N > 0 && T > 0 && C > 0,
+                 "pase_out_affine_nct: bad args");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  out_affine_nct_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(y, scale, shift, out, out_ntc, T,
+                                                                  C);
+  PASE_LAUNCH_CHECK("pase_out_affine_nct");
+  return PASE_OK;
+}
+
+int pase_out_bwd_reduce(const float* dout, const float* dout_ntc, const float* y,
+                        const float* mean, const float* invstd, int N, int T, int C, float* g_ntc,
+                        double* S1, double* S2, void* stream) {
+  PASE_CHECK_ARG((dout || dout_ntc) && y && mean && invstd && g_ntc && S1 && S2,
+                 "pase_out_bwd_reduce: null pointer");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  out_bwd_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dout, dout_ntc, y, mean, invstd,
+                                                                  T, C, g_ntc, S1, S2);
+  PASE_LAUNCH_CHECK("pase_out_bwd_reduce");
+  return PASE_OK;
+}
+
+int pase_out_bwd_apply(float* g, const float* y, const float* mean, const float* invstd,
+                       const float* scale, const double* S1, const double* S2, double count,
+                       int use_stats, long rows, int C, void* stream) {
+  PASE_CHECK_ARG(g && y && mean && invstd && scale && S1 && S2 && rows > 0 && C > 0,
+                 "pase_out_bwd_apply: bad args");
+  out_bwd_apply_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
+      g, y, mean, invstd, scale, S1, S2, 1.0 / count, use_stats, rows, C);
+  PASE_LAUNCH_CHECK("pase_out_bwd_apply");
+  return PASE_OK;
+}
+
+int pase_nct_to_ntc(const float* src, float* dst, int N, int C, int T, long dst_row_stride,
+                    void* stream) {
+  PASE_CHECK_ARG(src && dst && N > 0 && C > 0 && T > 0, "pase_nct_to_ntc: bad args");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nct_to_ntc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, T, dst_row_stride);
+  PASE_LAUNCH_CHECK("pase_nct_to_ntc");
+  return PASE_OK;
+}
+
+int pase_ntc_to_nct(const float* src, long src_row_stride, float* dst, int N, int C, int T,
+                    void* stream) {
+  PASE_CHECK_ARG(src && dst && N > 0 && C > 0 && T > 0, "pase_ntc_to_nct: bad args");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  ntc_to_nct_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_row_stride, dst, C, T);
+  PASE_LAUNCH_CHECK("pase_ntc_to_nct");
+  return PASE_OK;
+}
+
+int pase_axpy(const float* x, float* y, long n, float a, void* stream) {
+  PASE_CHECK_ARG(x && y && n > 0, "pase_axpy: bad args");
+  axpy_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, a);
+  PASE_LAUNCH_CHECK("pase_axpy");
+  return PASE_OK;
+}
+
+int pase_scale_dev(float* x, long n, const float* dev_scalar, float host_coef, void* stream) {
+  PASE_CHECK_ARG(x && n > 0, "pase_scale_dev: bad args");
+  scale_dev_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, dev_scalar,
+                                                                        host_coef);
+  PASE_LAUNCH_CHECK("pase_scale_dev");
+  return PASE_OK;
+}
+
+}  // extern "C"

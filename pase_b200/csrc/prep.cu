@@ -1,0 +1,300 @@
+// Operand preparation for the implicit-GEMM formulation: weight re-layouts and the
+// SincConv band-pass generator (forward + gradient).  All tiny, launched once per
+// step per layer.
+#include "common.cuh"
+
+namespace {
+
+__global__ void conv_w_to_fwd_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Cout,
+                                     int Cin, int k) {
+  const long total = (long)Cout * Cin * k;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    // i indexes Wt: [co][j][ci]
+    const int ci = (int)(i % Cin);
+    const long r = i / Cin;
+    const int j = (int)(r % k);
+    const int co = (int)(r / k);
+    Wt[i] = W[((long)co * Cin + ci) * k + j];
+  }
+}
+
+__global__ void conv_w_from_fwd_kernel(const float* __restrict__ dWt, float* __restrict__ dW,
+                                       int Cout, int Cin, int k) {
+  const long total = (long)Cout * Cin * k;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    // i indexes dW: [co][ci][j]
+    const int j = (int)(i % k);
+    const long r = i / k;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    dW[i] = dWt[((long)co * k + j) * Cin + ci];
+  }
+}
+
+// Wd[(p*Cin+ci), (v*Cout+co)] = W[co,ci, s*(taps-1-v)+p]  (0 when tap >= k)
+__global__ void conv_w_to_dgrad_kernel(const float* __restrict__ W, float* __restrict__ Wd,
+                                       int Cout, int Cin, int k, int s, int taps) {
+  const long total = (long)s * Cin * taps * Cout;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long r = i / Cout;
+    const int v = (int)(r % taps);
+    r /= taps;
+    const int ci = (int)(r % Cin);
+    const int p = (int)(r / Cin);
+    const int j = s * (taps - 1 - v) + p;
+    Wd[i] = (j < k) ? W[((long)co * Cin + ci) * k + j] : 0.f;
+  }
+}
+
+// ConvTranspose1d weight W (Cin,Cout,k): forward operand
+// Wu[(p*Cout+co), (v*Cin+ci)] = W[ci,co, s*(taps-1-v)+p]  (0 when tap >= k)
+__global__ void deconv_w_to_fwd_kernel(const float* __restrict__ W, float* __restrict__ Wu, int Cin,
+                                       int Cout, int k, int s, int taps) {
+  const long total = (long)s * Cout * taps * Cin;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    long r = i / Cin;
+    const int v = (int)(r % taps);
+    r /= taps;
+    const int co = (int)(r % Cout);
+    const int p = (int)(r / Cout);
+    const int j = s * (taps - 1 - v) + p;
+    Wu[i] = (j < k) ? W[((long)ci * Cout + co) * k + j] : 0.f;
+  }
+}
+
+__global__ void deconv_w_from_fwd_kernel(const float* __restrict__ dWu, float* __restrict__ dW,
+                                         int Cin, int Cout, int k, int s, int taps) {
+  const long total = (long)Cin * Cout * k;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % k);
+    long r = i / k;
+    const int co = (int)(r % Cout);
+    const int ci = (int)(r / Cout);
+    const int p = j % s;
+    const int v = taps - 1 - j / s;
+    dW[i] = dWu[(((long)p * Cout + co) * taps + v) * Cin + ci];
+  }
+}
+
+// Wb[ci, j*Cout+co] = W[ci,co,j]
+__global__ void deconv_w_to_bwd_kernel(const float* __restrict__ W, float* __restrict__ Wb, int Cin,
+                                       int Cout, int k) {
+  const long total = (long)Cin * Cout * k;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long r = i / Cout;
+    const int j = (int)(r % k);
+    const int ci = (int)(r / k);
+    Wb[i] = W[((long)ci * Cout + co) * k + j];
+  }
+}
+
+// dst (cols x ldd) = src^T, src (rows x cols, ld lds); pads columns [rows, ldd) with 0
+__global__ void transpose_pad_kernel(const float* __restrict__ src, long lds,
+                                     float* __restrict__ dst, long ldd, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(long)r * lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < ldd) dst[(long)c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ---- sinc filters ----
+__device__ __forceinline__ void sinc_edges(float l, float b, float min_low, float min_band,
+                                           float sr, float& low, float& high, bool& clamped) {
+  low = min_low + fabsf(l);
+  const float h = low + min_band + fabsf(b);
+  const float hi = sr * 0.5f;
+  clamped = (h < min_low) || (h > hi);
+  high = fminf(fmaxf(h, min_low), hi);
+}
+
+// one block per output channel
+__global__ void sinc_make_kernel(const float* __restrict__ low_hz, const float* __restrict__ band_hz,
+                                 const float* __restrict__ n_, const float* __restrict__ win,
+                                 float* __restrict__ filt, float* __restrict__ Wp, int C, int k,
+                                 int fold, int Kv, float min_low, float min_band, float sr) {
+  extern __shared__ float f[];       // [k]
+  const int co = blockIdx.x;
+  const int half = k / 2;
+  float low, high;
+  bool cl;
+  sinc_edges(low_hz[co], band_hz[co], min_low, min_band, sr, low, high, cl);
+  const float band = high - low;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float n = n_[i];
+    const float left = ((sinf(high * n) - sinf(low * n)) / (n / 2.f)) * win[i];
+    const float v = left / (2.f * band);
+    f[i] = v;
+    f[k - 1 - i] = v;
+  }
+  if (threadIdx.x == 0) f[half] = (2.f * band) / (2.f * band);
+  __syncthreads();
+  if (filt)
+    for (int i = threadIdx.x; i < k; i += blockDim.x) filt[(long)co * k + i] = f[i];
+  for (int p = 0; p < fold; ++p)
+    for (int kk = threadIdx.x; kk < Kv; kk += blockDim.x) {
+      const int j = kk - p;
+      Wp[((long)p * C + co) * Kv + kk] = (j >= 0 && j < k) ? f[j] : 0.f;
+    }
+}
+
+__global__ void sinc_grad_kernel(const float* __restrict__ dWp, const float* __restrict__ low_hz,
+                                 const float* __restrict__ band_hz, const float* __restrict__ n_,
+                                 const float* __restrict__ win, float* __restrict__ dlow,
+                                 float* __restrict__ dband, int C, int k, int fold, int Kv,
+                                 float min_low, float min_band, float sr) {
+  __shared__ double r_hi[32], r_lo[32];
+  const int co = blockIdx.x;
+  const int half = k / 2;
+  float low, high;
+  bool cl;
+  const float l = low_hz[co], b = band_hz[co];
+  sinc_edges(l, b, min_low, min_band, sr, low, high, cl);
+  const float band = high - low;
+  double ghi = 0.0, glo = 0.0;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    // gradient of the two symmetric taps i and k-1-i
+    float g = 0.f;
+    for (int p = 0; p < fold; ++p) {
+      g += dWp[((long)p * C + co) * Kv + i + p];
+      g += dWp[((long)p * C + co) * Kv + (k - 1 - i) + p];
+    }
+    const float n = n_[i];
+    const double A = (double)win[i] / ((double)n / 2.0);
+    const double S = (double)sinf(high * n) - (double)sinf(low * n);
+    const double b2 = 2.0 * (double)band;
+    const double dS = S / (b2 * (double)band);        // S / (2 band^2)
+    ghi += (double)g * A * ((double)cosf(high * n) * (double)n / b2 - dS);
+    glo += (double)g * A * (-(double)cosf(low * n) * (double)n / b2 + dS);
+  }
+  ghi = warp_sum_d(ghi);
+  glo = warp_sum_d(glo);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { r_hi[w] = ghi; r_lo[w] = glo; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double H = 0.0, L = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { H += r_hi[i]; L += r_lo[i]; }
+    if (cl) H = 0.0;                                   // clamp blocks the gradient
+    const double sl = (l > 0.f) ? 1.0 : ((l < 0.f) ? -1.0 : 0.0);
+    const double sb = (b > 0.f) ? 1.0 : ((b < 0.f) ? -1.0 : 0.0);
+    dlow[co] = (float)((L + H) * sl);
+    dband[co] = (float)(H * sb);
+  }
+}
+
+inline unsigned nblk(long total) {
+  long b = (total + 255) / 256;
+  long cap = (long)pase_num_sms() * 8;
+  return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+
+extern "C" {
+
+int pase_conv_w_to_fwd(const float* W, float* Wt, int Cout, int Cin, int k, void* stream) {
+  PASE_CHECK_ARG(W && Wt && Cout > 0 && Cin > 0 && k > 0, "pase_conv_w_to_fwd: bad args");
+  conv_w_to_fwd_kernel<<<nblk((long)Cout * Cin * k), 256, 0, (cudaStream_t)stream>>>(W, Wt, Cout,
+                                                                                    Cin, k);
+  PASE_LAUNCH_CHECK("pase_conv_w_to_fwd");
+  return PASE_OK;
+}
+
+int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, void* stream) {
+  PASE_CHECK_ARG(dWt && dW && Cout > 0 && Cin > 0 && k > 0, "pase_conv_w_from_fwd: bad args");
+  conv_w_from_fwd_kernel<<<nblk((long)Cout * Cin * k), 256, 0, (cudaStream_t)stream>>>(
+      dWt, dW, Cout, Cin, k);
+  PASE_LAUNCH_CHECK("pase_conv_w_from_fwd");
+  return PASE_OK;
+}
+
+int pase_conv_w_to_dgrad(const float* W, float* Wd, int Cout, int Cin, int k, int s, int taps,
+                         void* stream) {
+  PASE_CHECK_ARG(W && Wd && Cout > 0 && Cin > 0 && k > 0 && s > 0 && taps * s >= k,
+                 "pase_conv_w_to_dgrad: bad args (k=%d s=%d taps=%d)", k, s, taps);
+  conv_w_to_dgrad_kernel<<<nblk((long)s * Cin * taps * Cout), 256, 0, (cudaStream_t)stream>>>(
+      W, Wd, Cout, Cin, k, s, taps);
+  PASE_LAUNCH_CHECK("pase_conv_w_to_dgrad");
+  return PASE_OK;
+}
+
+int pase_deconv_w_to_fwd(const float* W, float* Wu, int Cin, int Cout, int k, int s, int taps,
+                         void* stream) {
+  PASE_CHECK_ARG(W && Wu && Cout > 0 && Cin > 0 && k > 0 && s > 0 && taps * s >= k,
+                 "pase_deconv_w_to_fwd: bad args");
+  deconv_w_to_fwd_kernel<<<nblk((long)s * Cout * taps * Cin), 256, 0, (cudaStream_t)stream>>>(
+      W, Wu, Cin, Cout, k, s, taps);
+  PASE_LAUNCH_CHECK("pase_deconv_w_to_fwd");
+  return PASE_OK;
+}
+
+int pase_deconv_w_from_fwd(const float* dWu, float* dW, int Cin, int Cout, int k, int s, int taps,
+                           void* stream) {
+  PASE_CHECK_ARG(dWu && dW && Cout > 0 && Cin > 0 && k > 0 && s > 0 && taps * s >= k,
+                 "pase_deconv_w_from_fwd: bad args");
+  deconv_w_from_fwd_kernel<<<nblk((long)Cin * Cout * k), 256, 0, (cudaStream_t)stream>>>(
+      dWu, dW, Cin, Cout, k, s, taps);
+  PASE_LAUNCH_CHECK("pase_deconv_w_from_fwd");
+  return PASE_OK;
+}
+
+int pase_deconv_w_to_bwd(const float* W, float* Wb, int Cin, int Cout, int k, void* stream) {
+  PASE_CHECK_ARG(W && Wb && Cout > 0 && Cin > 0 && k > 0, "pase_deconv_w_to_bwd: bad args");
+  deconv_w_to_bwd_kernel<<<nblk((long)Cin * Cout * k), 256, 0, (cudaStream_t)stream>>>(W, Wb, Cin,
+                                                                                      Cout, k);
+  PASE_LAUNCH_CHECK("pase_deconv_w_to_bwd");
+  return PASE_OK;
+}
+
+int pase_transpose_pad(const float* src, long lds, float* dst, long ldd, int rows, int cols,
+                       void* stream) {
+  PASE_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ldd >= rows && lds >= cols,
+                 "pase_transpose_pad: bad args");
+  dim3 grid((unsigned)((ldd + 31) / 32), (cols + 31) / 32), block(32, 8);
+  transpose_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols);
+  PASE_LAUNCH_CHECK("pase_transpose_pad");
+  return PASE_OK;
+}
+
+int pase_sinc_make(const float* low_hz, const float* band_hz, const float* n_, const float* window_,
+                   float* filt, float* Wp, int C, int k, int fold, int Kv, float min_low,
+                   float min_band, float sr, void* stream) {
+  PASE_CHECK_ARG(low_hz && band_hz && n_ && window_ && Wp, "pase_sinc_make: null pointer");
+  PASE_CHECK_ARG(C > 0 && (k & 1) && fold >= 1 && Kv >= k + fold - 1,
+                 "pase_sinc_make: need odd k and Kv >= k+fold-1 (k=%d fold=%d Kv=%d)", k, fold, Kv);
+  sinc_make_kernel<<<C, 128, k * sizeof(float), (cudaStream_t)stream>>>(
+      low_hz, band_hz, n_, window_, filt, Wp, C, k, fold, Kv, min_low, min_band, sr);
+  PASE_LAUNCH_CHECK("pase_sinc_make");
+  return PASE_OK;
+}
+
+int pase_sinc_grad(const float* dWp, const float* low_hz, const float* band_hz, const float* n_,
+                   const float* window_, float* dlow, float* dband, int C, int k, int fold, int Kv,
+                   float min_low, float min_band, float sr, void* stream) {
+  PASE_CHECK_ARG(dWp && low_hz && band_hz && n_ && window_ && dlow && dband,
+                 "pase_sinc_grad: null pointer");
+  PASE_CHECK_ARG(C > 0 && (k & 1) && fold >= 1 && Kv >= k + fold - 1, "pase_sinc_grad: bad shape");
+  sinc_grad_kernel<<<C, 128, 0, (cudaStream_t)stream>>>(dWp, low_hz, band_hz, n_, window_, dlow,
+                                                        dband, C, k, fold, Kv, min_low, min_band,
+                                                        sr);
+  PASE_LAUNCH_CHECK("pase_sinc_grad");
+  return PASE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+"""Shared test utilities: golden loading, deterministic parameters, comparisons."""
+import json
+import os
+import torch
+
+from detweights import fill_state_dict, seeded_randn, sample_view  # noqa: F401
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF_CFG = {
+    "cfg/frontend/PASE+.cfg": {
+        "kwidths": [251, 20, 11, 11, 11, 11, 11, 11], "strides": [1, 10, 2, 1, 2, 1, 2, 2],
+        "fmaps": [64, 64, 128, 128, 256, 256, 512, 512], "rnn_dim": 512, "denseskips": True,
+        "norm_out": True, "rnn_pool": True, "rnn_layers": 1},
+    "cfg/frontend/PASE.cfg": {
+        "kwidths": [251, 20, 11, 11, 11, 11, 11, 11], "strides": [1, 10, 2, 1, 2, 1, 2, 2],
+        "fmaps": [64, 64, 128, 128, 256, 256, 512, 512], "emb_dim": 100, "norm_out": True},
+}
+
+
+def load_golden(name):
+    d = torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu")
+    meta = json.loads(d["meta"])
+    return d, meta
+
+
+def resolve_cfg(cfg):
+    """golden meta stores either a dict or the reference-relative cfg path."""
+    if isinstance(cfg, str):
+        return dict(REF_CFG[cfg])
+    return dict(cfg)
+
+
+def rel_l2(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def assert_close(actual, expected, rtol, atol, what=""):
+    actual, expected = actual.detach().cpu().float(), expected.detach().cpu().float()
+    assert actual.shape == expected.shape, "%s: shape %s vs %s" % (what, tuple(actual.shape),
+                                                                    tuple(expected.shape))
+    err = (actual - expected).abs()
+    tol = atol + rtol * expected.abs()
+    bad = err > tol
+    if bad.any():
+        i = int(torch.argmax(err - tol))
+        raise AssertionError(
+            "%s: %d/%d elements out of tolerance (rtol=%g atol=%g); worst |err|=%.3e at flat "
+            "index %d (actual %.6e expected %.6e); rel-L2=%.3e"
+            % (what, int(bad.sum()), bad.numel(), rtol, atol, float(err.reshape(-1)[i]), i,
+               float(actual.reshape(-1)[i]), float(expected.reshape(-1)[i]),
+               rel_l2(actual, expected)))
+
+
+def check_grads(grads, golden, rtol, atol_scale, prefix=""):
+    """grads: name -> tensor.  golden holds grad/<k>, or gsample/<k> + gnorm/<k>.  The
+    absolute tolerance scales with the gradient's own magnitude (atol_scale * max|g|)."""
+    n = 0
+    for key, val in golden.items():
+        if key.startswith("grad/"):
+            k = key[5:]
+            g = grads[prefix + k]
+            atol = atol_scale * max(float(val.abs().max()), 1e-6)
+            if k.endswith("conv.bias") or k == "W.bias" or k == "frontend.W.bias":
+                atol = max(atol, 1e-4)      # analytically zero under train-mode BN: fp noise
+            assert_close(g, val, rtol, atol, "grad " + k)
+            n += 1
+        elif key.startswith("gsample/"):
+            k = key[8:]
+            g = grads[prefix + k].detach().cpu()
+            atol = atol_scale * max(float(val.abs().max()), 1e-6)
+            assert_close(sample_view(g), val, rtol, atol, "grad-sample " + k)
+            gn = float(golden["gnorm/" + k])
+            assert abs(float(g.double().norm()) - gn) <= 2e-3 * gn + 1e-7, "grad-norm " + k
+            n += 1
+    return n
