@@ -358,12 +358,15 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
          rows, rows, rows, 1, None, None, 0)
     dWcat = plan.dWcat.view(emb, Kc)
     first = plan.H if plan.rnn else plan.Clast
-    grads["W.weight"] = dWcat[:, :first].reshape(params["W.weight"].shape)
+    # gradients handed to autograd must not alias plan-owned buffers (the next backward
+    # would overwrite them): copy the slices out
+    grads["W.weight"] = dWcat[:, :first].clone().reshape(params["W.weight"].shape)
     if plan.skips:
         for i in range(plan.nblk - 1):
             c0 = plan.col_off[i]
             grads["denseskips.%d.weight" % i] = \
-                dWcat[:, c0:c0 + G[i].Cout].reshape(params["denseskips.%d.weight" % i].shape)
+                dWcat[:, c0:c0 + G[i].Cout].clone().reshape(
+                    params["denseskips.%d.weight" % i].shape)
 
     Cl = plan.Clast
     if plan.rnn:

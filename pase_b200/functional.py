@@ -1,0 +1,269 @@
+"""Differentiable building blocks of the worker heads over the C-ABI kernels.
+
+Tensors are channel-last "row" matrices (rows = sample*time, columns =
+channels) with a leading dimension that is a multiple of 4 floats; padding
+columns are kept at zero so a padded matrix can be fed straight back as a GEMM
+operand.  Each autograd Function launches only kernels of pase_b200/csrc.
+"""
+import torch
+
+from . import ops
+
+
+def _ru4(n):
+    return (n + 3) // 4 * 4
+
+
+def _rows_ld(x):
+    """(rows, cols) fp32 tensor with unit inner stride -> (flat view at its first element, ld)."""
+    assert x.dim() == 2 and x.dtype == torch.float32, (x.shape, x.dtype)
+    if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) % 4 != 0) or x.storage_offset() % 4 != 0:
+        x = x.contiguous()
+        if x.shape[1] % 4 != 0:
+            pad = torch.zeros(x.shape[0], _ru4(x.shape[1]), dtype=x.dtype, device=x.device)
+            pad[:, :x.shape[1]] = x
+            x = pad[:, :x.shape[1]]
+    ld = x.stride(0) if x.shape[0] > 1 else _ru4(x.shape[1])
+    if ld % 4 != 0:
+        pad = torch.zeros(x.shape[0], _ru4(x.shape[1]), dtype=x.dtype, device=x.device)
+        pad[:, :x.shape[1]] = x
+        x, ld = pad[:, :x.shape[1]], pad.stride(0)
+    return x, ld
+
+
+def _flat_from(x):
+    """1-D view of x's storage starting at x's first element (base-pointer semantics)."""
+    st = x.untyped_storage()
+    n = st.nbytes() // 4 - x.storage_offset()
+    return torch.as_strided(x, (n,), (1,), x.storage_offset())
+
+
+class _LinearRows(torch.autograd.Function):
+    """Y[rows, :N] = X[rows, :K] @ W[N, K]^T + b   (1x1 Conv1d / Linear on channel-last rows;
+    minions.py:494-524, modules.py:543-556).  Y has ld = roundup(N, 4), padding zeroed."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, ldx = _rows_ld(x.detach())
+        rows, K = x.shape
+        N = weight.shape[0]
+        w2 = weight.detach().reshape(N, -1)
+        assert w2.shape[1] == K and K % 4 == 0, "in-features %d must match and be a multiple of 4" % K
+        w2 = w2.contiguous()
+        ldo = _ru4(N)
+        out = torch.empty(rows, ldo, dtype=torch.float32, device=x.device)
+        if ldo != N:
+            out[:, N:].zero_()
+        ops.call("pase_gemm_nt", _flat_from(x), ldx, w2.reshape(-1), K, out.reshape(-1), ldo,
+                 rows, N, K, 1.0, None if bias is None else bias.detach().reshape(-1),
+                 rows, rows, rows, 1, None, None, 0)
+        ctx.save_for_backward(x, w2)
+        ctx.ldx, ctx.N, ctx.has_bias, ctx.wshape = ldx, N, bias is not None, weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2 = ctx.saved_tensors
+        rows, K = x.shape
+        N, ldx = ctx.N, ctx.ldx
+        ldo = _ru4(N)
+        dy = dy.contiguous()
+        assert dy.shape == (rows, ldo)
+        dev = x.device
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            wT = torch.empty(K, ldo, dtype=torch.float32, device=dev)
+            ops.call("pase_transpose_pad", w2.reshape(-1), K, wT.reshape(-1), ldo, N, K)
+            dx = torch.empty(rows, K, dtype=torch.float32, device=dev)
+            ops.call("pase_gemm_nt", dy.reshape(-1), ldo, wT.reshape(-1), ldo, dx.reshape(-1), K,
+                     rows, K, ldo, 1.0, None, rows, rows, rows, 1, None, None, 0)
+        if ctx.needs_input_grad[1]:
+            dWp = torch.empty(ldo, K, dtype=torch.float32, device=dev)
+            ops.call("pase_gemm_tn", dy.reshape(-1), ldo, rows, 0, _flat_from(x), ldx, rows, 0,
+                     dWp.reshape(-1), K, ldo, K, 1, rows, 1.0, 0)
+            dW = dWp[:N].reshape(ctx.wshape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            acc = torch.zeros(ldo, dtype=torch.float64, device=dev)
+            ops.call("pase_colsum", dy.reshape(-1), ldo, rows, ldo, acc)
+            dbf = torch.empty(ldo, dtype=torch.float32, device=dev)
+            ops.call("pase_cast_d2f", acc, dbf, ldo, 1.0)
+            db = dbf[:N]
+        return dx, dW, db
+
+
+def linear_rows(x, weight, bias=None):
+    return _LinearRows.apply(x, weight, bias)
+
+
+class _PReLURows(torch.autograd.Function):
+    """Per-channel PReLU on (rows, ld) with C valid columns (modules.py:550, 111-113)."""
+
+    @staticmethod
+    def forward(ctx, u, alpha, C):
+        u = u.detach()
+        rows, ld = u.shape
+        h = torch.empty_like(u)
+        if ld != C:
+            h[:, C:].zero_()
+        ops.call("pase_prelu_fwd", u.reshape(-1), h.reshape(-1), alpha.detach().reshape(-1), rows,
+                 C, ld, ld)
+        ctx.save_for_backward(u, alpha.detach())
+        ctx.C = C
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        u, alpha = ctx.saved_tensors
+        rows, ld = u.shape
+        C = ctx.C
+        dh = dh.contiguous()
+        du = torch.empty_like(u)
+        if ld != C:
+            du[:, C:].zero_()
+        acc = torch.zeros(C, dtype=torch.float64, device=u.device)
+        ops.call("pase_prelu_bwd", u.reshape(-1), dh.reshape(-1), alpha.reshape(-1), du.reshape(-1),
+                 acc, rows, C, ld, ld, ld)
+        da = torch.empty(C, dtype=torch.float32, device=u.device)
+        ops.call("pase_cast_d2f", acc, da, C, 1.0)
+        return du, da.view_as(alpha), None
+
+
+def prelu_rows(u, alpha, C):
+    return _PReLURows.apply(u, alpha, C)
+
+
+class _TimeMean(torch.autograd.Function):
+    """(B*T, C) rows -> (B, C): mean over time (GIM, cls_minions.py:96)."""
+
+    @staticmethod
+    def forward(ctx, x, B, T):
+        x, ldx = _rows_ld(x.detach())
+        C = x.shape[1]
+        out = torch.empty(B, C, dtype=torch.float32, device=x.device)
+        ops.call("pase_time_mean_fwd", _flat_from(x), ldx, out.reshape(-1), C, B, T, C)
+        ctx.B, ctx.T, ctx.C = B, T, C
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, C = ctx.B, ctx.T, ctx.C
+        dout = dout.contiguous()
+        dx = torch.empty(B * T, C, dtype=torch.float32, device=dout.device)
+        ops.call("pase_time_mean_bwd", dout.reshape(-1), C, dx.reshape(-1), C, B, T, C, 0)
+        return dx, None, None
+
+
+def time_mean_rows(x, B, T):
+    return _TimeMean.apply(x, B, T)
+
+
+class _NctToRows(torch.autograd.Function):
+    """(B,C,T) -> (B*T, C) channel-last rows (boundary conversion for tensors that did not
+    come from the encoder's channel-last output)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.detach().contiguous().float()
+        B, C, T = x.shape
+        out = torch.empty(B * T, C, dtype=torch.float32, device=x.device)
+        ops.call("pase_nct_to_ntc", x.reshape(-1), out.reshape(-1), B, C, T, C)
+        ctx.shape = (B, C, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, T = ctx.shape
+        g = g.contiguous()
+        dx = torch.empty(B, C, T, dtype=torch.float32, device=g.device)
+        ops.call("pase_ntc_to_nct", g.reshape(-1), C, dx.reshape(-1), B, C, T)
+        return dx
+
+
+def nct_to_rows(x):
+    return _NctToRows.apply(x)
+
+
+# ------------------------------------------------------------------ losses ---
+def _loss_scalar(acc, numel):
+    return (acc / float(numel)).float().reshape(())
+
+
+class _CtxMSE(torch.autograd.Function):
+    """mean((pred - contextualise_r(label))^2) on channel-last predictions without
+    materialising the r-times unfolded label (losses.py:15-37 + nn.MSELoss)."""
+
+    @staticmethod
+    def forward(ctx, pred, label, F, r):
+        pred = pred.detach()
+        rows, ldp = pred.shape
+        label = label.detach().contiguous().float()
+        B, Fl, T = label.shape
+        assert Fl == F and rows == B * T, (label.shape, pred.shape)
+        acc = torch.zeros(1, dtype=torch.float64, device=pred.device)
+        ops.call("pase_ctx_mse_fwd", pred.reshape(-1), ldp, label.reshape(-1), B, F, T, r, acc)
+        ctx.save_for_backward(pred, label)
+        ctx.dims = (B, F, T, r, ldp)
+        return _loss_scalar(acc, rows * F * r)
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, label = ctx.saved_tensors
+        B, F, T, r, ldp = ctx.dims
+        dpred = torch.empty_like(pred)
+        if ldp != F * r:
+            dpred[:, F * r:].zero_()
+        ops.call("pase_ctx_mse_bwd", pred.reshape(-1), ldp, label.reshape(-1), B, F, T, r,
+                 2.0 / float(B * T * F * r), g.detach().reshape(-1).float(), dpred.reshape(-1), ldp)
+        return dpred, None, None, None
+
+
+def ctx_mse_rows(pred, label, F, r):
+    return _CtxMSE.apply(pred, label, F, r if r is not None else 1)
+
+
+class _L1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred, target = pred.detach().contiguous(), target.detach().contiguous().float()
+        assert pred.numel() == target.numel()
+        acc = torch.zeros(1, dtype=torch.float64, device=pred.device)
+        ops.call("pase_l1_fwd", pred.reshape(-1), target.reshape(-1), pred.numel(), acc)
+        ctx.save_for_backward(pred, target)
+        return _loss_scalar(acc, pred.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        d = torch.empty_like(pred)
+        ops.call("pase_l1_bwd", pred.reshape(-1), target.reshape(-1), pred.numel(),
+                 1.0 / float(pred.numel()), g.detach().reshape(-1).float(), d.reshape(-1))
+        return d, None
+
+
+def l1_loss(pred, target):
+    return _L1.apply(pred, target)
+
+
+class _BCEPairs(torch.autograd.Function):
+    """BCEWithLogits against [ones; zeros] (make_labels, cls_minions.py:47-51)."""
+
+    @staticmethod
+    def forward(ctx, logit, n_pos):
+        logit = logit.detach().contiguous()
+        acc = torch.zeros(1, dtype=torch.float64, device=logit.device)
+        ops.call("pase_bce_pairs_fwd", logit.reshape(-1), logit.numel(), n_pos, acc)
+        ctx.save_for_backward(logit)
+        ctx.n_pos = n_pos
+        return _loss_scalar(acc, logit.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        (logit,) = ctx.saved_tensors
+        d = torch.empty_like(logit)
+        ops.call("pase_bce_pairs_bwd", logit.reshape(-1), logit.numel(), ctx.n_pos,
+                 1.0 / float(logit.numel()), g.detach().reshape(-1).float(), d.reshape(-1))
+        return d, None
+
+
+def bce_pairs(logit, n_pos):
+    return _BCEPairs.apply(logit, n_pos)

@@ -1,0 +1,54 @@
+"""N>1 host path: flat-gradient all-reduce over 2 ranks with the gloo backend (CPU)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pase_b200.dp import FlatGradAllReducer
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                       # identical replicas
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.PReLU(16), torch.nn.Linear(16, 4))
+    red = FlatGradAllReducer(list(model.parameters()))
+    g = torch.Generator().manual_seed(100 + rank)     # distinct shard per rank
+    x = torch.randn(5, 8, generator=g)
+    red.zero()
+    model(x).square().mean().backward()
+    # every .grad is a view of the single flat buffer
+    assert all(p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr()
+               for p in model.parameters())
+    red.all_reduce()
+    torch.save(red.flat.clone(), os.path.join(out, "g%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_two_ranks(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g0 = torch.load(tmp_path / "g0.pt")
+    g1 = torch.load(tmp_path / "g1.pt")
+    assert torch.equal(g0, g1)
+    # equals the average of the two single-rank gradients
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.PReLU(16), torch.nn.Linear(16, 4))
+    ref = 0
+    for r in range(2):
+        model.zero_grad()
+        x = torch.randn(5, 8, generator=torch.Generator().manual_seed(100 + r))
+        model(x).square().mean().backward()
+        ref = ref + torch.cat([p.grad.reshape(-1) for p in model.parameters()]) / 2
+    assert torch.allclose(g0, ref, rtol=1e-5, atol=1e-7)

@@ -1,0 +1,166 @@
+"""End-to-end parity of the CUDA encoder path (through WaveFe / the C-ABI) on the GPU:
+(1) against golden vectors produced by the unmodified reference, (2) against the CPU
+oracle at the BASELINE.json shape (T=32000) on a few chunks, (3) size-independent
+properties at the full benchmark size (B=32, T=32000)."""
+import json
+import os
+
+import pytest
+import torch
+
+import pase_oracle as O
+from helpers import GOLDEN, load_golden, resolve_cfg, fill_state_dict, seeded_randn, \
+    assert_close, check_grads, rel_l2
+from pase_b200 import wf_builder
+from pase_b200.frontend import WaveFe
+
+pytestmark = pytest.mark.gpu
+
+# fp32 parity bar from BASELINE.json north_star
+RTOL, ATOL = 1e-3, 1e-5
+
+CASES = ["enc_pase_eval_16000", "enc_pasep_eval_3200", "enc_pasep_train_3200",
+         "enc_pasep_train_4001", "enc_pase_train_2400", "enc_mini_train_2000",
+         "enc_mini_train_1763", "enc_mininornn_train_1600"]
+
+
+def _native(cfg, seed, training):
+    m = WaveFe(**cfg)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    return m.cuda().train(training)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_encoder_matches_reference_golden(name):
+    gold, meta = load_golden(name)
+    cfg = resolve_cfg(meta["cfg"])
+    model = _native(cfg, meta["seed"], meta["training"])
+    x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5).cuda()
+    assert model.frame_counts(meta["T"]) == gold["frame_counts"].tolist()
+    if not meta["training"]:
+        with torch.no_grad():
+            y = model(x)
+        assert_close(y, gold["y"], RTOL, ATOL, name)
+        return
+    y = model(x)
+    assert tuple(y.shape) == tuple(gold["y"].shape)
+    assert_close(y, gold["y"], RTOL, ATOL, name)
+    cot = seeded_randn(tuple(y.shape), meta["seed"] + 2).cuda()
+    (y * cot).sum().backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert check_grads(grads, gold, 2e-3, 2e-4) > 10
+    sd = model.state_dict()
+    for key, val in gold.items():
+        if key.startswith("stat/"):
+            assert_close(sd[key[5:]].float(), val.float(), 1e-4, 1e-6, key)
+
+
+def test_baseline_config0_shape():
+    """BASELINE.json configs[0]: PASE.cfg forward of randn(1,1,16000).  The reference
+    produces (1,100,100) for this cfg (emb_dim:100), see SURVEY.md finding 4."""
+    m = wf_builder(resolve_cfg("cfg/frontend/PASE.cfg")).cuda().eval()
+    with torch.no_grad():
+        y = m(torch.randn(1, 1, 16000).cuda())
+    assert tuple(y.shape) == (1, 100, 100)
+    m2 = wf_builder(resolve_cfg("cfg/frontend/PASE+.cfg")).cuda().eval()
+    with torch.no_grad():
+        assert tuple(m2(torch.randn(1, 1, 100000).cuda()).shape) == (1, 256, 625)   # README.md:37-39
+
+
+def test_frame_counts_bit_exact():
+    table = json.load(open(os.path.join(GOLDEN, "frame_counts.json")))
+    m = WaveFe(**resolve_cfg("cfg/frontend/PASE+.cfg"))
+    for T, lens in table.items():
+        assert m.frame_counts(int(T)) == lens
+
+
+def test_dict_batch_and_modes():
+    cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
+    m = _native(cfg, 11, True)
+    B, T = 2, 3200
+    batch = {k: seeded_randn((B, 1, T), 20 + i, 0.5) for i, k in
+             enumerate(["chunk", "chunk_ctxt", "chunk_rand"])}          # CPU tensors, like a DataLoader
+    emb, chunk = m(batch, device="cuda")
+    assert len(emb) == 3 and tuple(chunk.shape) == (B, 256, 20) and chunk.is_cuda
+    # same weights through the oracle on the concatenated batch (train-mode BN over 3B)
+    sd = fill_state_dict(WaveFe(**cfg).state_dict(), 11)
+    xcat = torch.cat([batch[k] for k in ["chunk", "chunk_ctxt", "chunk_rand"]], 0)
+    with torch.no_grad():
+        ref = O.encoder_forward(xcat, sd, cfg, training=True)
+    assert_close(torch.cat(emb, 0), ref, RTOL, ATOL, "dict batch")
+    m.eval()
+    with torch.no_grad():
+        x = batch["chunk"].cuda()
+        base = m(x)
+        for mode in ("avg_norm", "avg_concat", "avg_norm_concat"):
+            assert_close(m(x, mode=mode), O.select_output(base.cpu(), mode), 1e-5, 1e-6, mode)
+
+
+def test_full_length_against_oracle():
+    """T=32000 (the BASELINE.json chunk length), N=3 chunks, fwd + bwd vs the CPU oracle."""
+    cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
+    seed, N, T = 21, 3, 32000
+    model = _native(cfg, seed, True)
+    sd = fill_state_dict(WaveFe(**cfg).state_dict(), seed)
+    x = seeded_randn((N, 1, T), seed + 1, 0.5)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(leaves)
+    y_ref = O.encoder_forward(x, full, cfg, training=True)
+    cot = seeded_randn(tuple(y_ref.shape), seed + 2)
+    (y_ref * cot).sum().backward()
+    y = model(x.cuda())
+    assert tuple(y.shape) == (N, 256, 200)
+    assert_close(y, y_ref, RTOL, ATOL, "T=32000 fwd")
+    assert rel_l2(y.cpu(), y_ref) < 1e-3
+    (y * cot.cuda()).sum().backward()
+    for k, p in model.named_parameters():
+        ref = leaves[k].grad
+        atol = 2e-4 * max(float(ref.abs().max()), 1e-6)
+        if k.endswith("conv.bias") or k == "W.bias":
+            atol = max(atol, 1e-3)
+        assert_close(p.grad, ref, 2e-3, atol, "grad " + k)
+
+
+def test_benchmark_shape_properties():
+    """B=32, T=32000 (BASELINE.json configs[1]): properties that do not need the oracle."""
+    cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
+    model = _native(cfg, 5, True)
+    x = seeded_randn((32, 1, 32000), 77, 0.5).cuda()
+    y = model(x)
+    assert tuple(y.shape) == (32, 256, 200) and bool(torch.isfinite(y).all())
+    # norm_out is BatchNorm(affine=False) in train mode: per-channel mean 0 / biased var 1
+    mu = y.mean(dim=(0, 2))
+    var = y.var(dim=(0, 2), unbiased=False)
+    assert float(mu.abs().max()) < 1e-4 and float((var - 1).abs().max()) < 1e-3
+    y.square().mean().backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+    # determinism of the forward up to atomics ordering
+    model.zero_grad()
+    y2 = model(x)
+    assert rel_l2(y2, y) < 1e-5
+    # linearity of the gradient in the cotangent: backward(2c) == 2 backward(c)
+    c = torch.randn_like(y2)
+    g1 = torch.autograd.grad((y2 * c).sum(), model.W.weight, retain_graph=False)[0]
+    y3 = model(x)
+    g2 = torch.autograd.grad((y3 * (2 * c)).sum(), model.W.weight)[0]
+    assert rel_l2(g2, 2 * g1) < 1e-4
+
+
+def test_stale_plan_is_detected():
+    cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
+    m = _native(cfg, 1, True)
+    x = seeded_randn((2, 1, 3200), 3, 0.5).cuda()
+    y1 = m(x)
+    y2 = m(x)                       # overwrites the (N,T) plan's activations
+    with pytest.raises(RuntimeError, match="overwritten"):
+        y1.sum().backward()
+    y2.sum().backward()
+
+
+def test_cpu_input_without_cuda_module_raises():
+    m = WaveFe(**resolve_cfg("cfg/frontend/PASE+.cfg"))          # parameters on CPU
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(1, 1, 3200))

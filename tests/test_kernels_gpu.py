@@ -1,0 +1,222 @@
+"""Every C-ABI kernel, called through ctypes on the GPU, against its torch
+semantic spec (tests/emul_ops.py) on identical random inputs."""
+import pytest
+import torch
+
+import emul_ops
+from pase_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(name, args, rtol=1e-4, atol=1e-5, cmp_scale=None):
+    """args: list of tensors (CPU) / scalars / None.  Runs the emulation on clones and the
+    CUDA kernel on device copies; compares every tensor argument afterwards."""
+    cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    emul_ops.call(name, *cpu)
+    _lib.call(name, *dev)
+    torch.cuda.synchronize()
+    for i, (c, d) in enumerate(zip(cpu, dev)):
+        if not isinstance(c, torch.Tensor):
+            continue
+        d = d.cpu()
+        if c.dtype == torch.float64:
+            c, d = c.float(), d.float()
+        scale = max(float(c.abs().max()), 1.0) if cmp_scale is None else cmp_scale
+        err = (c - d).abs()
+        tol = atol * scale + rtol * c.abs()
+        assert bool((err <= tol).all()), "%s arg %d: max err %.3e (scale %.3e)" % (
+            name, i, float(err.max()), scale)
+    return cpu, dev
+
+
+def R(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return scale * torch.randn(*shape, generator=g)
+
+
+@pytest.mark.parametrize("M,N,K,lda,rows_in,t_valid,rows_out,fold,bias,stats,acc", [
+    (300, 64, 256, 256, 300, 300, 300, 1, True, True, 0),          # plain, BN=64 tile
+    (517, 128, 704, 128, 47, 40, 40, 1, True, True, 0),            # overlapping view, row groups
+    (260, 256, 256, 4, 65, 250, 63, 4, False, True, 0),            # folded sinc shape
+    (129, 100, 512, 512, 129, 129, 129, 1, True, False, 0),        # N tail (emb 100)
+    (200, 85, 256, 256, 200, 200, 200, 1, True, False, 1),         # accumulate, odd N + ldc
+    (1030, 640, 128, 64, 103, 101, 101, 1, False, False, 0),       # dgrad shape
+])
+def test_gemm_nt(M, N, K, lda, rows_in, t_valid, rows_out, fold, bias, stats, acc):
+    A = R(M * lda + K + 8, seed=1)
+    B = R(N * K, seed=2, scale=0.1)
+    groups = (M + rows_in - 1) // rows_in
+    ldc = N if N % 4 == 0 else N + 1
+    C = R(groups * rows_out * ldc + 8, seed=3)
+    bs = R(N, seed=4) if bias else None
+    cs = torch.zeros(N, dtype=torch.float64) if stats else None
+    cq = torch.zeros(N, dtype=torch.float64) if stats else None
+    run_both("pase_gemm_nt", [A, lda, B, K, C, ldc, M, N, K, 0.5, bs, rows_in, t_valid, rows_out,
+                              fold, cs, cq, acc], rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("I,J,groups,rpg,lda,pitchA,offA,ldb,pitchB,offB,acc", [
+    (64, 1280, 3, 100, 64, 103, 1, 640, 102, 0, 0),
+    (256, 256, 2, 500, 256, 500, 0, 4, 520, 0, 0),
+    (100, 1920, 1, 77, 100, 77, 0, 1920, 77, 0, 1),
+    (512, 64, 4, 33, 512, 40, 5, 64, 33, 0, 0),
+])
+def test_gemm_tn(I, J, groups, rpg, lda, pitchA, offA, ldb, pitchB, offB, acc):
+    A = R(groups * pitchA * lda + I + 8, seed=5)
+    B = R(groups * pitchB * ldb + J + 8, seed=6)
+    C = R(I * J, seed=7)
+    run_both("pase_gemm_tn", [A, lda, pitchA, offA, B, ldb, pitchB, offB, C, J, I, J, groups, rpg,
+                              0.25, acc], rtol=2e-4, atol=2e-5)
+
+
+def test_weight_layouts():
+    Cout, Cin, k, s = 24, 16, 11, 2
+    taps = -(-k // s)
+    W = R(Cout * Cin * k, seed=8)
+    run_both("pase_conv_w_to_fwd", [W, torch.zeros(Cout * Cin * k), Cout, Cin, k])
+    run_both("pase_conv_w_from_fwd", [W, torch.zeros(Cout * Cin * k), Cout, Cin, k])
+    run_both("pase_conv_w_to_dgrad", [W, torch.zeros(s * Cin * taps * Cout), Cout, Cin, k, s, taps])
+    k2, s2 = 30, 4
+    t2 = -(-k2 // s2)
+    Wd = R(Cin * Cout * k2, seed=9)
+    run_both("pase_deconv_w_to_fwd", [Wd, torch.zeros(s2 * Cout * t2 * Cin), Cin, Cout, k2, s2, t2])
+    run_both("pase_deconv_w_from_fwd", [R(s2 * Cout * t2 * Cin, seed=10),
+                                        torch.zeros(Cin * Cout * k2), Cin, Cout, k2, s2, t2])
+    run_both("pase_deconv_w_to_bwd", [Wd, torch.zeros(Cin * Cout * k2), Cin, Cout, k2])
+    run_both("pase_transpose_pad", [R(37 * 21, seed=11), 21, torch.zeros(21 * 40), 40, 37, 21])
+
+
+def test_sinc_make_and_grad():
+    from pase_b200.encoder import sinc_constants
+    from detweights import fill_state_dict
+    C, k, fold, Kv = 64, 251, 4, 256
+    sd = fill_state_dict({"blocks.0.conv.low_hz_": torch.zeros(C, 1),
+                          "blocks.0.conv.band_hz_": torch.zeros(C, 1)}, 3)
+    low, band = sd["blocks.0.conv.low_hz_"].reshape(-1), sd["blocks.0.conv.band_hz_"].reshape(-1)
+    band[5] = 9000.0          # forces the clamp at sr/2
+    low[7] = -low[7]          # abs() branch
+    n_, win = sinc_constants(k, 16000, "cpu")
+    run_both("pase_sinc_make", [low, band, n_, win, torch.zeros(C * k), torch.zeros(fold * C * Kv),
+                                C, k, fold, Kv, 50.0, 50.0, 16000.0], rtol=2e-3, atol=2e-5)
+    dWp = R(fold * C * Kv, seed=12)
+    run_both("pase_sinc_grad", [dWp, low, band, n_, win, torch.zeros(C), torch.zeros(C), C, k, fold,
+                                Kv, 50.0, 50.0, 16000.0], rtol=5e-3, atol=2e-4)
+
+
+def test_reflect_pad_and_bn_finalize():
+    N, T = 3, 700
+    run_both("pase_reflect_pad_wave", [R(N * T, seed=13), torch.zeros(N * 960), N, T, 125, 125, 960])
+    C, fold = 48, 4
+    cs = R(C * fold, seed=14).double() * 100
+    cq = (R(C * fold, seed=15).double().abs() + 1.0) * 5000
+    run_both("pase_bn_finalize", [cs, cq, C, fold, 4000.0, R(C, seed=16), R(C, seed=17),
+                                  R(C, seed=18), R(C, seed=19).abs(), 0.1, 1e-5, torch.zeros(C),
+                                  torch.zeros(C), torch.zeros(C), torch.zeros(C)])
+    run_both("pase_bn_eval_affine", [R(C, seed=18), R(C, seed=19).abs() + 0.1, R(C, seed=16), None,
+                                     C, 1e-5, torch.zeros(C), torch.zeros(C), torch.zeros(C),
+                                     torch.zeros(C)])
+
+
+@pytest.mark.parametrize("N,T,C,padL,padR,pool_d", [(2, 203, 64, 4, 5, 16), (3, 77, 48, 0, 0, 0),
+                                                    (2, 1001, 128, 5, 5, 8), (2, 50, 512, 9, 10, 2)])
+def test_bn_prelu_pad_fwd(N, T, C, padL, padR, pool_d):
+    Tp = T + padL + padR
+    y = R(N * (T + 3) * C, seed=20)
+    d_rs = C + 8
+    dst = torch.zeros(N * (Tp + 2) * d_rs)
+    pool_T = T // pool_d if pool_d else 0
+    pool = torch.zeros(N * max(pool_T, 1) * 200 + C) if pool_d else None
+    run_both("pase_bn_prelu_pad_fwd", [y, (T + 3) * C, N, T, C, R(C, seed=21), R(C, seed=22),
+                                       R(C, seed=23, scale=0.3), dst, (Tp + 2) * d_rs, d_rs, padL,
+                                       padR, pool, max(pool_T, 1) * 200, 200, pool_d, pool_T])
+
+
+@pytest.mark.parametrize("N,T,C,padL,padR,pool_d,useB", [(2, 203, 64, 4, 5, 16, False),
+                                                         (3, 77, 48, 0, 0, 0, True),
+                                                         (2, 40, 512, 9, 10, 2, False)])
+def test_bn_prelu_bwd(N, T, C, padL, padR, pool_d, useB):
+    Tp = T + padL + padR
+    y = R(N * T * C, seed=24)
+    mean, invstd = R(C, seed=25, scale=0.1), R(C, seed=26).abs() + 0.5
+    scale, shift, alpha = R(C, seed=27), R(C, seed=28), R(C, seed=29, scale=0.3)
+    srcA = R(N * Tp * C, seed=30)
+    srcB = R(N * T * 2 * C, seed=31) if useB else None
+    pool_T = T // pool_d if pool_d else 0
+    pool = R(N * max(pool_T, 1) * C, seed=32) if pool_d else None
+    dst = torch.zeros(N * T * C)
+    S1, S2, dal = (torch.zeros(C, dtype=torch.float64) for _ in range(3))
+    cpu, dev = run_both("pase_bn_prelu_bwd_reduce", [
+        y, T * C, N, T, C, mean, invstd, scale, shift, alpha, srcA, Tp * C, C, padL, padR,
+        srcB, T * 2 * C, 2 * C, 1, pool, max(pool_T, 1) * C, C, pool_d, pool_T, dst, T * C,
+        S1, S2, dal], rtol=2e-4, atol=2e-5)
+    du, s1, s2 = cpu[24], cpu[26], cpu[27]
+    run_both("pase_bn_prelu_bwd_apply", [y, T * C, N, T, C, mean, invstd, R(C, seed=33), s1, s2,
+                                         float(N * T), du, T * C, torch.zeros(C, dtype=torch.float64)],
+             rtol=2e-4, atol=2e-5)
+
+
+def test_prelu_colsum_cast():
+    rows, C = 333, 84
+    u, dh, a = R(rows * 90, seed=34), R(rows * 88, seed=35), R(C, seed=36, scale=0.3)
+    run_both("pase_prelu_fwd", [u, torch.zeros(rows * 96), a, rows, C, 90, 96])
+    run_both("pase_prelu_bwd", [u, dh, a, torch.zeros(rows * 96), torch.zeros(C, dtype=torch.float64),
+                                rows, C, 90, 88, 96])
+    run_both("pase_colsum", [u, 90, rows, C, torch.zeros(C, dtype=torch.float64)])
+    run_both("pase_cast_d2f", [R(100, seed=37).double(), torch.zeros(100), 100, 0.5])
+
+
+def test_output_norm_kernels():
+    N, T, C = 3, 37, 100
+    y = R(N * T * C, seed=38)
+    sc, sh = R(C, seed=39), R(C, seed=40)
+    run_both("pase_out_affine_nct", [y, sc, sh, torch.zeros(N * C * T), torch.zeros(N * T * C), N, T, C])
+    mean, invstd = R(C, seed=41, scale=0.1), R(C, seed=42).abs() + 0.5
+    S1, S2 = torch.zeros(C, dtype=torch.float64), torch.zeros(C, dtype=torch.float64)
+    cpu, _ = run_both("pase_out_bwd_reduce", [R(N * C * T, seed=43), R(N * T * C, seed=44), y, mean,
+                                              invstd, N, T, C, torch.zeros(N * T * C), S1, S2])
+    run_both("pase_out_bwd_apply", [cpu[8], y, mean, invstd, invstd, cpu[9], cpu[10], float(N * T), 1,
+                                    N * T, C])
+    run_both("pase_nct_to_ntc", [R(N * C * T, seed=45), torch.zeros(N * T * 104), N, C, T, 104])
+    run_both("pase_ntc_to_nct", [R(N * T * 104, seed=46), 104, torch.zeros(N * C * T), N, C, T])
+
+
+def test_qrnn_scan():
+    N, T, H = 3, 23, 96
+    Y = R(N * T * 3 * H, seed=47)
+    ldh = H + 32
+    cpu, _ = run_both("pase_qrnn_scan_fwd", [Y, torch.zeros(N * T * ldh), ldh, torch.zeros(N * T * H),
+                                             N, T, H], rtol=2e-4, atol=2e-5)
+    run_both("pase_qrnn_scan_bwd", [Y, cpu[3], R(N * T * ldh, seed=48), ldh, torch.zeros(N * T * 3 * H),
+                                    N, T, H], rtol=5e-4, atol=5e-5)
+
+
+def test_losses():
+    B, F, T, r = 2, 13, 21, 7
+    ldp = F * r + 1
+    pred, label = R(B * T * ldp, seed=49), R(B * F * T, seed=50)
+    run_both("pase_ctx_mse_fwd", [pred, ldp, label, B, F, T, r, torch.zeros(1, dtype=torch.float64)])
+    gs = torch.tensor([0.7])
+    run_both("pase_ctx_mse_bwd", [pred, ldp, label, B, F, T, r, 0.01, gs, torch.zeros(B * T * ldp), ldp])
+    run_both("pase_ctx_mse_fwd", [pred, ldp, label, B, F, T, 1, torch.zeros(1, dtype=torch.float64)])
+    n = 5000
+    p, t = R(n, seed=51), R(n, seed=52)
+    run_both("pase_l1_fwd", [p, t, n, torch.zeros(1, dtype=torch.float64)])
+    run_both("pase_l1_bwd", [p, t, n, 0.01, gs, torch.zeros(n)])
+    run_both("pase_bce_pairs_fwd", [p * 3, n, n // 2, torch.zeros(1, dtype=torch.float64)])
+    run_both("pase_bce_pairs_bwd", [p * 3, n, n // 2, 0.01, None, torch.zeros(n)])
+    Bm, Tm, Cm = 4, 19, 96
+    x = R(Bm * Tm * 100, seed=53)
+    run_both("pase_time_mean_fwd", [x, 100, torch.zeros(Bm * Cm), Cm, Bm, Tm, Cm])
+    run_both("pase_time_mean_bwd", [R(Bm * Cm, seed=54), Cm, R(Bm * Tm * 100, seed=55), 100, Bm, Tm, Cm, 1])
+    run_both("pase_axpy", [p, t, n, 0.3])
+    run_both("pase_scale_dev", [p, n, gs, 2.0])
+
+
+def test_error_reporting():
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        _lib.call("pase_gemm_nt", torch.zeros(64).cuda(), 3, torch.zeros(64).cuda(), 4,
+                  torch.zeros(64).cuda(), 4, 4, 4, 4, 1.0, None, 4, 4, 4, 1, None, None, 0)
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        _lib.call("pase_axpy", torch.zeros(4), torch.zeros(4).cuda(), 4, 1.0)
