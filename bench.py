@@ -213,6 +213,7 @@ def run_native(args):
 
     torch.manual_seed(0)                               # identical replicas
     model = wf_builder(dict(PASE_PLUS)).to(dev).train()
+    model.precision = args.precision
     params = list(model.parameters())
     red = FlatGradAllReducer(params)
     opt = torch.optim.Adam(params, lr=1e-4, fused=True)
@@ -284,15 +285,19 @@ def run_native(args):
         real_call = ops.call
 
         def spy(name, *a):
-            if name in ("pase_gemm_nt", "pase_gemm_tn"):
+            if name in ("pase_gemm_nt", "pase_gemm_tn", "pase_tc_gemm_nt", "pase_tc_gemm_tn"):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 r = real_call(name, *a)
                 e.record()
                 if name == "pase_gemm_nt":
                     fl = 2.0 * a[6] * a[7] * a[8]
-                else:
+                elif name == "pase_gemm_tn":
                     fl = 2.0 * a[10] * a[11] * a[12] * a[13]
+                elif name == "pase_tc_gemm_nt":
+                    fl = 2.0 * a[9] * a[10] * a[11]
+                else:
+                    fl = 2.0 * a[12] * a[13] * a[14] * a[15]
                 recs.append((name, s, e, fl))
                 return r
             return real_call(name, *a)
@@ -325,11 +330,13 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": {"fp32": "f32", "3xtf32": "f32 (3xTF32 split on tcgen05, fp32 accumulate: "
+                      "fp32-equivalent products)", "tf32": "tf32"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": "PASE+.cfg encoder fwd+bwd+adam, B=32/GPU, T=32000, fp32, "
                                    "train-mode BN, no workers (BASELINE configs[1])",
                        "global_batch": B_PER_GPU * world, "seq_len": T_CHUNK,
-                       "parallelism": "dp%d" % world,
+                       "parallelism": "dp%d" % world, "gemm_precision": args.precision,
                        "l2": "no flush: per-step working set (~1.7 GB activations) >> 126 MB L2",
                        "grad_allreduce_bytes": red.nbytes if world > 1 else 0},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
@@ -337,7 +344,12 @@ def run_native(args):
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
             "roofline": {
-                "kernel": "pase_gemm_nt + pase_gemm_tn (fp32 FFMA implicit-GEMM conv fwd/dgrad/wgrad)",
+                "kernel": {"fp32": "pase_gemm_nt + pase_gemm_tn (fp32 FFMA implicit-GEMM conv "
+                                   "fwd/dgrad/wgrad)",
+                           "3xtf32": "pase_tc_gemm_nt + pase_tc_gemm_tn (tcgen05 kind::tf32, 3 MMAs "
+                                     "per product; FLOPs counted once)",
+                           "tf32": "pase_tc_gemm_nt + pase_tc_gemm_tn (tcgen05 kind::tf32)"}[
+                    args.precision],
                 "bound": "tensor", "achieved": ach_tf, "peak": peaks["tf_sustained"],
                 "unit": "TFLOP/s", "frac": ach_tf / peaks["tf_sustained"], "traffic": None,
                 "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
@@ -374,6 +386,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("PASE_B200_PRECISION", "fp32"),
+                    choices=["fp32", "3xtf32", "tf32"],
+                    help="GEMM numerics: fp32 FFMA, 3xTF32 tcgen05 (fp32-equivalent), TF32 tcgen05")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

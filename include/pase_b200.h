@@ -65,6 +65,25 @@ int pase_gemm_tn(const float* A, long lda, int pitchA, int offA,
                  int groups, int rows_per_group,
                  float alpha, int accumulate, void* stream);
 
+
+/* ---- tensor-core (tcgen05 / TMEM / TMA) GEMMs ------------------------------
+ * Same contract as pase_gemm_nt / pase_gemm_tn, computed with kind::tf32 UMMA
+ * instructions and fp32 accumulation in tensor memory.
+ *   mode 0: single TF32 pass;  mode 1: 3xTF32 (operands pre-split by
+ *   pase_split_tf32 into exactly-representable hi/lo parts) = fp32-equivalent.
+ * A is a plain 2-D tensor [a_rows x R] (R floats per folded row, R % 32 == 0):
+ * element (m, k) is read at row m + k/R, column k%R. */
+int pase_split_tf32(const float* x, float* hi, float* lo, long n, void* stream);
+int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R,
+                    const float* Bhi, const float* Blo, long ldb,
+                    float* C, long ldc, int M, int N, int K, float alpha, const float* bias,
+                    int rows_in, int t_valid, int rows_out, int fold,
+                    double* colsum, double* colsumsq, int accumulate, int mode, void* stream);
+int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, int offA,
+                    const float* Bhi, const float* Blo, int R, int pitchB, long b_rows_total,
+                    float* C, long ldc, int I, int J, int groups, int rows_per_group,
+                    float alpha, int accumulate, int mode, void* stream);
+
 /* ---- weight re-layout (implicit-GEMM operand preparation) ---------------- */
 /* (Cout,Cin,k) -> Wt[co, j*Cin+ci]                      (forward operand)   */
 int pase_conv_w_to_fwd(const float* W, float* Wt, int Cout, int Cin, int k, void* stream);

@@ -602,16 +602,20 @@ int pase_prelu_bwd(const float* u, const float* dh, const float* alpha, float* d
 }
 
 int pase_colsum(const float* X, long ld, long rows, int C, double* acc, void* stream) {
-  PASE_CHECK_ARG(X && acc && rows > 0 && C > 0 && C <= 8192, "pase_colsum: bad args");
-  const int cpb = C < THREADS ? C : THREADS;
-  const int rpp = THREADS / cpb;
-  long nb = (rows + rpp * 8 - 1) / (rpp * 8);
-  long cap = (long)pase_num_sms() * 4;
-  if (nb > cap) nb = cap;
-  if (nb < 1) nb = 1;
-  colsum_kernel<<<(unsigned)nb, THREADS, C * sizeof(float), (cudaStream_t)stream>>>(X, ld, rows, C,
-                                                                                   acc);
-  PASE_LAUNCH_CHECK("pase_colsum");
+  PASE_CHECK_ARG(X && acc && rows > 0 && C > 0, "pase_colsum: bad args");
+  // wide matrices (e.g. the 21525-column lps head) are processed in column panels
+  for (int c0 = 0; c0 < C; c0 += 4096) {
+    const int Cp = (C - c0) < 4096 ? (C - c0) : 4096;
+    const int cpb = Cp < THREADS ? Cp : THREADS;
+    const int rpp = THREADS / cpb;
+    long nb = (rows + rpp * 8 - 1) / (rpp * 8);
+    long cap = (long)pase_num_sms() * 4;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    colsum_kernel<<<(unsigned)nb, THREADS, Cp * sizeof(float), (cudaStream_t)stream>>>(
+        X + c0, ld, rows, Cp, acc + c0);
+    PASE_LAUNCH_CHECK("pase_colsum");
+  }
   return PASE_OK;
 }
 

@@ -1,0 +1,750 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a.
+//
+//   pase_tc_gemm_nt : C[map(m), n] = alpha * sum_k A[m, k] * B[n, k] + bias[n]
+//       A is addressed through a plain (non-overlapping) 2-D tensor [a_rows x R]:
+//       element (m, k) lives at row m + k / R, column k % R, so the implicit im2col
+//       matrix of a strided convolution (R = stride * Cin) needs no materialisation
+//       and no overlapping TMA strides.  B is [N x K], K-major.
+//   pase_tc_gemm_tn : C[i, j] += alpha * sum_r A[r, i] * B[r, j]   (weight gradients)
+//       both operands MN-major in shared memory (transpose bits set in the UMMA
+//       instruction descriptor); split over the reduction, fp32 red.add epilogue.
+//
+// Numerics: kind::tf32 MMAs with fp32 accumulation in TMEM.
+//   mode 0: single TF32 pass (10-bit mantissa operands);
+//   mode 1: 3xTF32 error-compensated: operands are pre-split into exactly
+//           representable tf32 "hi" and "lo" parts (hi + lo == fp32 value to 2^-22),
+//           D = Ahi*Bhi + Alo*Bhi + Ahi*Blo  -> fp32-equivalent products.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+// (one elected lane), warps 2-5 = epilogue (tcgen05.ld -> bias / row map / BatchNorm
+// column statistics -> global).  K-major tiles are 128-byte rows with the 128B swizzle.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKF = 32;                  // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;                // tf32
+constexpr int NTHREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 200u * 1000u * 1000u;
+
+// ------------------------------------------------------------------ PTX helpers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) {
+      printf("pase tc gemm: mbarrier wait timed out (tag %d, block %d,%d,%d thread %d)\n", tag,
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(slot)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128B swizzle.
+//   K-major : rows of 128 B, 8-row atoms of 1024 B -> SBO = 1024 B, LBO unused.
+//   MN-major: 128 B (32 fp32) along MN per row, 8 k-rows per 1024 B atom; SBO = 1024 B
+//             (next 8 k), LBO = byte distance between consecutive 32-element MN blocks.
+//   MN-major fp32/tf32 operands must use the 32-byte-base 128B swizzle (layout type 1,
+//   TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 128 B (MN) x 4 k-rows, SBO = 512 B.
+template <int LAYOUT = 2>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)LAYOUT << 61;                 // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=tf32 (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct RowMap {
+  int rows_in, t_valid, rows_out, fold, cols_per_fold;
+};
+
+// transposed butterfly: v[j] per lane (lane = row) -> lane j holds sum over lanes of v[j]
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = up ? v[i + off] : v[i];
+      const float send = up ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, bool SPLIT>
+struct NTCfg {
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                              2 * BN * 4 /*stats*/;
+};
+
+// ------------------------------------------------------------------ NT kernel ----
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                  const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
+                  int R, float* __restrict__ C, long ldc, int M, int N, int K, float alpha,
+                  const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
+                  double* __restrict__ colsumsq, int accumulate) {
+  using Cfg = NTCfg<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* done_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int nkb = (K + BKF - 1) / BKF;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tmap_prefetch(&mAhi);
+    tmap_prefetch(&mBhi);
+    if (SPLIT) {
+      tmap_prefetch(&mAlo);
+      tmap_prefetch(&mBlo);
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * BN; i += NTHREADS) s_stats[i] = 0.f;
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        const int kf = kb * BKF;
+        const int arow = m0 + kf / R, acol = kf % R;
+        tma_load_2d(st, &mAhi, &full_bar[s], acol, arow);
+        tma_load_2d(st + Cfg::A_BYTES, &mBhi, &full_bar[s], kf, n0);
+        if (SPLIT) {
+          tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mAlo, &full_bar[s], acol, arow);
+          tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mBlo, &full_bar[s], kf, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph, 2);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+        const uint32_t b_hi = a_hi + Cfg::A_BYTES;
+        const uint32_t a_lo = b_hi + Cfg::B_BYTES;
+        const uint32_t b_lo = a_lo + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKF / UMMA_K; ++k) {
+          const uint32_t off = k * UMMA_K * 4;
+          const uint64_t dah = make_desc(a_hi + off, 16, 1024);
+          const uint64_t dbh = make_desc(b_hi + off, 16, 1024);
+          if (SPLIT) {
+            const uint64_t dal = make_desc(a_lo + off, 16, 1024);
+            const uint64_t dbl = make_desc(b_lo + off, 16, 1024);
+            umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);
+            umma_tf32(tmem_base, dah, dbl, idesc, 1);
+            umma_tf32(tmem_base, dah, dbh, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, dah, dbh, idesc, (kb | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[s]);            // frees the smem stage once the MMAs retire
+      }
+      umma_commit(done_bar);                   // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: 4 warps, TMEM lane quarter = warp % 4 ----------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int m = m0 + r;
+    mbar_wait(done_bar, 0, 3);
+    tc_fence_after();
+    const bool row_ok = m < M;
+    int g = 0, u = 0;
+    if (row_ok) {
+      g = m / rm.rows_in;
+      u = m - g * rm.rows_in;
+    }
+    const long orow = (long)g * rm.rows_out + u;
+    const bool want_stats = colsum != nullptr;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), raw);
+      float v[32], sq[32];
+      const int nb = n0 + cc * 32;
+      float* cp = C + orow * ldc + nb;
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = nb + j;
+        const bool ok = row_ok && (n < N) && (u * rm.fold + n / rm.cols_per_fold < rm.t_valid);
+        float x = __uint_as_float(raw[j]) * alpha;
+        if (bias != nullptr && n < N) x += bias[n];
+        if (ok && accumulate) x += cp[j];
+        okmask |= ok ? (1u << j) : 0u;
+        v[j] = ok ? x : 0.f;
+        sq[j] = ok ? x * x : 0.f;
+      }
+      if (okmask == 0xFFFFFFFFu && vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else if (okmask != 0u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (okmask & (1u << j)) cp[j] = v[j];
+      }
+      if (want_stats) {
+        const float s1 = colsum32(v, lane);
+        const float s2 = colsum32(sq, lane);
+        atomicAdd(&s_stats[cc * 32 + lane], s1);
+        atomicAdd(&s_stats[BN + cc * 32 + lane], s2);
+      }
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps only
+      const int t = threadIdx.x - 64;
+      for (int c = t; c < 2 * BN; c += 128) {
+        const int which = c / BN, col = c - which * BN;
+        if (n0 + col < N)
+          atomicAdd((which == 0 ? colsum : colsumsq) + n0 + col, (double)s_stats[c]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ TN kernel ----
+// C[i,j] += alpha * sum_r A[r,i] B[r,j].  A: 3-D tensor (I inner, rows-per-group, groups);
+// B addressed through the folded-row trick: (r, j) -> row u + j/R of group g, column j % R.
+constexpr int TN_KR = 32;                // reduction rows per stage (4 UMMA k-steps of 8)
+
+template <int BN, bool SPLIT>
+struct TNCfg {
+  static constexpr int A_BYTES = TN_KR * BM * 4;          // 4 MN-blocks of [32 rows x 128 B]
+  static constexpr int B_BYTES = TN_KR * BN * 4;
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                  const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
+                  int R, float* __restrict__ C, long ldc, int I, int J, int groups,
+                  int rows_per_group, float alpha, int chunks_per_split) {
+  using Cfg = TNCfg<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* done_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * BN, i0 = blockIdx.y * BM;
+  const int cpg = (rows_per_group + TN_KR - 1) / TN_KR;       // chunks per group
+  const long total_chunks = (long)groups * cpg;
+  const long c_begin = (long)blockIdx.z * chunks_per_split;
+  long c_end = c_begin + chunks_per_split;
+  if (c_end > total_chunks) c_end = total_chunks;
+  const int nch = (int)(c_end - c_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tmap_prefetch(&mAhi);
+    tmap_prefetch(&mBhi);
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (nch <= 0) {                      // uniform across the CTA
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<BN>(tmem_base);
+    return;
+  }
+  const int jq = j0 / R, jc = j0 % R;  // folded-row offset / column of this B tile
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nch; ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 11);
+        const long ch = c_begin + it;
+        const int g = (int)(ch / cpg);
+        const int u0 = (int)(ch - (long)g * cpg) * TN_KR;
+        uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        uint8_t* a_hi = st;
+        uint8_t* b_hi = st + Cfg::A_BYTES;
+        uint8_t* a_lo = b_hi + Cfg::B_BYTES;
+        uint8_t* b_lo = a_lo + Cfg::A_BYTES;
+#pragma unroll
+        for (int mb = 0; mb < BM / 32; ++mb) {
+          tma_load_3d(a_hi + mb * TN_KR * 128, &mAhi, &full_bar[s], i0 + mb * 32, u0, g);
+          if (SPLIT) tma_load_3d(a_lo + mb * TN_KR * 128, &mAlo, &full_bar[s], i0 + mb * 32, u0, g);
+        }
+#pragma unroll
+        for (int nb = 0; nb < BN / 32; ++nb) {
+          // 32 consecutive columns never straddle a folded row (R % 32 == 0)
+          const int col = jc + nb * 32;
+          const int qq = jq + col / R, cc = col % R;
+          tma_load_3d(b_hi + nb * TN_KR * 128, &mBhi, &full_bar[s], cc, u0 + qq, g);
+          if (SPLIT) tma_load_3d(b_lo + nb * TN_KR * 128, &mBlo, &full_bar[s], cc, u0 + qq, g);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
+      for (int it = 0; it < nch; ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph, 12);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+        const uint32_t b_hi = a_hi + Cfg::A_BYTES;
+        const uint32_t a_lo = b_hi + Cfg::B_BYTES;
+        const uint32_t b_lo = a_lo + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TN_KR / UMMA_K; ++k) {
+          const uint32_t off = k * 1024;               // 8 k-rows of 128 B
+          const uint64_t dah = make_desc<1>(a_hi + off, TN_KR * 128, 512);
+          const uint64_t dbh = make_desc<1>(b_hi + off, TN_KR * 128, 512);
+          if (SPLIT) {
+            const uint64_t dal = make_desc<1>(a_lo + off, TN_KR * 128, 512);
+            const uint64_t dbl = make_desc<1>(b_lo + off, TN_KR * 128, 512);
+            umma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);
+            umma_tf32(tmem_base, dah, dbl, idesc, 1);
+            umma_tf32(tmem_base, dah, dbh, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, dah, dbh, idesc, (it | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int i = i0 + q * 32 + lane;
+    mbar_wait(done_bar, 0, 13);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), raw);
+      if (i < I) {
+        float* cp = C + (long)i * ldc + j0 + cc * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j0 + cc * 32 + j < J) atomicAdd(cp + j, __uint_as_float(raw[j]) * alpha);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rank-2 or rank-3 fp32 tensor map, 128B swizzle, zero OOB fill.
+int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims,
+             const uint64_t* strides_bytes, const uint32_t* box, const char* what,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    pase_set_error("pase tc gemm: cuTensorMapEncodeTiled not available");
+    return PASE_ERR_UNSUPPORTED;
+  }
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base,
+                   (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes,
+                   (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pase_set_error("pase tc gemm: cuTensorMapEncodeTiled(%s) failed with %d (dims %llu,%llu,%llu "
+                   "stride %llu,%llu box %u,%u,%u)",
+                   what, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)(rank > 2 ? dims[2] : 0),
+                   (unsigned long long)strides_bytes[0],
+                   (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), box[0], box[1],
+                   rank > 2 ? box[2] : 0);
+    return PASE_ERR_ARG;
+  }
+  return PASE_OK;
+}
+
+template <int BN, bool SPLIT>
+int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+              const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
+              const float* bias, RowMap rm, double* cs, double* cq, int accumulate,
+              cudaStream_t st) {
+  using Cfg = NTCfg<BN, SPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, SPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      pase_set_error("pase_tc_gemm_nt: smem attribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  tc_gemm_nt_kernel<BN, SPLIT><<<grid, NTHREADS, Cfg::SMEM, st>>>(ah, al, bh, bl, R, C, ldc, M, N, K,
+                                                                 alpha, bias, rm, cs, cq, accumulate);
+  PASE_LAUNCH_CHECK("pase_tc_gemm_nt");
+  return PASE_OK;
+}
+
+template <int BN, bool SPLIT>
+int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+              const CUtensorMap& bl, int R, float* C, long ldc, int I, int J, int groups,
+              int rows_per_group, float alpha, cudaStream_t st) {
+  using Cfg = TNCfg<BN, SPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, SPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      pase_set_error("pase_tc_gemm_tn: smem attribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr = true;
+  }
+  const int ti = (I + BM - 1) / BM, tj = (J + BN - 1) / BN;
+  const int cpg = (rows_per_group + TN_KR - 1) / TN_KR;
+  const long total = (long)groups * cpg;
+  long splits = (2L * pase_num_sms() + (long)ti * tj - 1) / ((long)ti * tj);
+  if (splits > total) splits = total;
+  if (splits < 1) splits = 1;
+  long cps = (total + splits - 1) / splits;
+  splits = (total + cps - 1) / cps;
+  dim3 grid(tj, ti, (unsigned)splits);
+  tc_gemm_tn_kernel<BN, SPLIT><<<grid, NTHREADS, Cfg::SMEM, st>>>(ah, al, bh, bl, R, C, ldc, I, J,
+                                                                 groups, rows_per_group, alpha,
+                                                                 (int)cps);
+  PASE_LAUNCH_CHECK("pase_tc_gemm_tn");
+  return PASE_OK;
+}
+
+// split kernel: hi = tf32-truncated value (low 13 mantissa bits cleared), lo = tf32(x - hi)
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                  float* __restrict__ lo, long n) {
+  const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long stride = (long)gridDim.x * blockDim.x * 4;
+  for (long i = i4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+      l.x = __uint_as_float(__float_as_uint(v.x - h.x) & 0xFFFFE000u);
+      l.y = __uint_as_float(__float_as_uint(v.y - h.y) & 0xFFFFE000u);
+      l.z = __uint_as_float(__float_as_uint(v.z - h.z) & 0xFFFFE000u);
+      l.w = __uint_as_float(__float_as_uint(v.w - h.w) & 0xFFFFE000u);
+      *reinterpret_cast<float4*>(hi + i) = h;
+      *reinterpret_cast<float4*>(lo + i) = l;
+    } else {
+      for (long j = i; j < n; ++j) {
+        const float v = x[j];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[j] = h;
+        lo[j] = __uint_as_float(__float_as_uint(v - h) & 0xFFFFE000u);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pase_split_tf32(const float* x, float* hi, float* lo, long n, void* stream) {
+  PASE_CHECK_ARG(x && hi && lo && n > 0, "pase_split_tf32: bad args");
+  PASE_CHECK_ARG(aligned16(x) && aligned16(hi) && aligned16(lo), "pase_split_tf32: alignment");
+  long blocks = (n / 4 + 255) / 256;
+  long cap = (long)pase_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+  PASE_LAUNCH_CHECK("pase_split_tf32");
+  return PASE_OK;
+}
+
+// A: [a_rows x R] fp32 (hi / lo parts, lo may be NULL for mode 0); B: [N x K] (ldb = K).
+int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, const float* Bhi,
+                    const float* Blo, long ldb, float* C, long ldc, int M, int N, int K,
+                    float alpha, const float* bias, int rows_in, int t_valid, int rows_out,
+                    int fold, double* colsum, double* colsumsq, int accumulate, int mode,
+                    void* stream) {
+  PASE_CHECK_ARG(Ahi && Bhi && C && M > 0 && N > 0 && K > 0, "pase_tc_gemm_nt: bad args");
+  PASE_CHECK_ARG(mode == 0 || (Alo && Blo), "pase_tc_gemm_nt: mode 1 needs lo operands");
+  PASE_CHECK_ARG(R >= 32 && (R % 32) == 0, "pase_tc_gemm_nt: R=%d must be a multiple of 32", R);
+  PASE_CHECK_ARG((K % 4) == 0 && (ldb % 4) == 0 && ldb >= K, "pase_tc_gemm_nt: K/ldb alignment");
+  PASE_CHECK_ARG(aligned16(Ahi) && aligned16(Bhi), "pase_tc_gemm_nt: operand alignment");
+  PASE_CHECK_ARG(rows_in > 0 && rows_out > 0 && fold > 0 && (N % fold) == 0,
+                 "pase_tc_gemm_nt: bad row map");
+  PASE_CHECK_ARG((colsum == nullptr) == (colsumsq == nullptr), "pase_tc_gemm_nt: stats pair");
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap ah, al, bh, bl;
+  uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
+  uint64_t astr[1] = {(uint64_t)R * 4};
+  uint32_t abox[2] = {32, (uint32_t)BM};
+  uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
+  uint64_t bstr[1] = {(uint64_t)ldb * 4};
+  uint32_t bbox[2] = {32, (uint32_t)BN};
+  int rc;
+  if ((rc = make_map(&ah, Ahi, 2, adims, astr, abox, "A.hi")) != 0) return rc;
+  if ((rc = make_map(&bh, Bhi, 2, bdims, bstr, bbox, "B.hi")) != 0) return rc;
+  if (mode == 1) {
+    if ((rc = make_map(&al, Alo, 2, adims, astr, abox, "A.lo")) != 0) return rc;
+    if ((rc = make_map(&bl, Blo, 2, bdims, bstr, bbox, "B.lo")) != 0) return rc;
+  } else {
+    al = ah;
+    bl = bh;
+  }
+  RowMap rm{rows_in, t_valid, rows_out, fold, N / fold};
+  cudaStream_t st = (cudaStream_t)stream;
+#define PASE_NT(BNV)                                                                             \
+  (mode == 1 ? launch_nt<BNV, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, colsum, \
+                                    colsumsq, accumulate, st)                                    \
+             : launch_nt<BNV, false>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,        \
+                                     colsum, colsumsq, accumulate, st))
+  if (BN == 64) return PASE_NT(64);
+  if (BN == 128) return PASE_NT(128);
+  return PASE_NT(256);
+#undef PASE_NT
+}
+
+// A: groups x [rows_per_group x lda] starting `offA` rows into each group of pitch `pitchA`
+// rows (columns 0..I-1 used); B: folded rows of R floats, group pitch `pitchB` rows.
+int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, int offA,
+                    const float* Bhi, const float* Blo, int R, int pitchB, long b_rows_total,
+                    float* C, long ldc, int I, int J, int groups, int rows_per_group, float alpha,
+                    int accumulate, int mode, void* stream) {
+  PASE_CHECK_ARG(Ahi && Bhi && C && I > 0 && J > 0 && groups > 0 && rows_per_group > 0,
+                 "pase_tc_gemm_tn: bad args");
+  PASE_CHECK_ARG(mode == 0 || (Alo && Blo), "pase_tc_gemm_tn: mode 1 needs lo operands");
+  PASE_CHECK_ARG(R >= 32 && (R % 32) == 0 && (lda % 4) == 0 && (I % 4) == 0 && (J % 32) == 0,
+                 "pase_tc_gemm_tn: need R%%32==0, lda%%4==0, I%%4==0, J%%32==0 (R=%d lda=%ld I=%d "
+                 "J=%d)", R, lda, I, J);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    cudaError_t e =
+        cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)J * sizeof(float), (size_t)I, st);
+    if (e != cudaSuccess) {
+      pase_set_error("pase_tc_gemm_tn: memset failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  const int BN = J <= 64 ? 64 : (J <= 128 ? 128 : 256);
+  CUtensorMap ah, al, bh, bl;
+  uint64_t adims[3] = {(uint64_t)I, (uint64_t)rows_per_group, (uint64_t)groups};
+  uint64_t astr[2] = {(uint64_t)lda * 4, (uint64_t)pitchA * lda * 4};
+  uint32_t abox[3] = {32, TN_KR, 1};
+  // B group g covers folded rows [g*pitchB, ...): rows beyond the allocation are zero-filled
+  long rows_in_group = b_rows_total - (long)(groups - 1) * pitchB;
+  if (rows_in_group > pitchB + (J + R - 1) / R + 1) rows_in_group = pitchB + (J + R - 1) / R + 1;
+  uint64_t bdims[3] = {(uint64_t)R, (uint64_t)rows_in_group, (uint64_t)groups};
+  uint64_t bstr[2] = {(uint64_t)R * 4, (uint64_t)pitchB * R * 4};
+  uint32_t bbox[3] = {32, TN_KR, 1};
+  int rc;
+  const CUtensorMapSwizzle sw32 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if ((rc = make_map(&ah, Ahi + (long)offA * lda, 3, adims, astr, abox, "tn A.hi", sw32)) != 0)
+    return rc;
+  if ((rc = make_map(&bh, Bhi, 3, bdims, bstr, bbox, "tn B.hi", sw32)) != 0) return rc;
+  if (mode == 1) {
+    if ((rc = make_map(&al, Alo + (long)offA * lda, 3, adims, astr, abox, "tn A.lo", sw32)) != 0)
+      return rc;
+    if ((rc = make_map(&bl, Blo, 3, bdims, bstr, bbox, "tn B.lo", sw32)) != 0) return rc;
+  } else {
+    al = ah;
+    bl = bh;
+  }
+#define PASE_TN(BNV)                                                                            \
+  (mode == 1 ? launch_tn<BNV, true>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,    \
+                                    alpha, st)                                                  \
+             : launch_tn<BNV, false>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,   \
+                                     alpha, st))
+  if (BN == 64) return PASE_TN(64);
+  if (BN == 128) return PASE_TN(128);
+  return PASE_TN(256);
+#undef PASE_TN
+}
+
+}  // extern "C"

@@ -22,7 +22,10 @@ from . import ops
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-SINC_FOLD = 4
+SINC_FOLD = 4            # polyphase fold of the sinc layer on the fp32 FFMA path
+TC_SINC_FOLD = 32        # on the tensor-core path one folded row = one 128-byte TMA row
+# numerics of the GEMMs: None = fp32 FFMA; 1 = 3xTF32 tcgen05 (fp32-equivalent); 0 = TF32
+PRECISIONS = {"fp32": None, "3xtf32": 1, "tf32": 0}
 
 
 def _cdiv(a, b):
@@ -48,7 +51,7 @@ def conv_pads(k, stride, sinc):
 class ConvGeom(object):
     """Static geometry of one encoder block for a given input length."""
 
-    def __init__(self, idx, sinc, Cin, Cout, k, s, L_in):
+    def __init__(self, idx, sinc, Cin, Cout, k, s, L_in, sinc_fold=4):
         self.idx, self.sinc = idx, sinc
         self.Cin, self.Cout, self.k, self.s, self.L_in = Cin, Cout, k, s, L_in
         self.padL, self.padR = conv_pads(k, s, sinc)
@@ -59,12 +62,12 @@ class ConvGeom(object):
         self.T_out = (self.Tpad - k) // s + 1
         if sinc:
             # polyphase fold: row u of the GEMM produces times fold*u .. fold*u+fold-1
-            self.fold = SINC_FOLD
-            self.lda = SINC_FOLD                       # floats between consecutive rows
-            self.K = _ru(k + SINC_FOLD - 1, 4)
-            self.Nn = SINC_FOLD * Cout
-            self.P = _cdiv(self.Tpad, SINC_FOLD)       # rows per sample
-            self.rows_out = _cdiv(self.T_out, SINC_FOLD)
+            self.fold = sinc_fold
+            self.lda = sinc_fold                       # floats between consecutive rows
+            self.K = _ru(k + sinc_fold - 1, 32 if sinc_fold >= 32 else 4)
+            self.Nn = sinc_fold * Cout
+            self.P = _cdiv(self.Tpad, sinc_fold)       # rows per sample
+            self.rows_out = _cdiv(self.T_out, sinc_fold)
         else:
             self.fold = 1
             self.lda = s * Cin
@@ -83,13 +86,13 @@ class ConvGeom(object):
         return self.T_out
 
 
-def build_geometry(cfg, T):
+def build_geometry(cfg, T, sinc_fold=4):
     geoms, L, cin = [], T, cfg["num_inputs"]
     for i, (k, s, f) in enumerate(zip(cfg["kwidths"], cfg["strides"], cfg["fmaps"])):
         sinc = bool(cfg["sincnet"]) and i == 0
         if sinc and k % 2 == 0:
             k += 1                                     # modules.py:835-836
-        g = ConvGeom(i, sinc, cin, f, k, s, L)
+        g = ConvGeom(i, sinc, cin, f, k, s, L, sinc_fold)
         geoms.append(g)
         L, cin = g.T_out, f
     return geoms
@@ -105,9 +108,13 @@ class EncoderPlan(object):
     buffers are zero-initialised once; kernels only ever write their valid
     region, so halos / slack stay finite."""
 
-    def __init__(self, cfg, N, T, device):
+    def __init__(self, cfg, N, T, device, prec="fp32"):
         self.cfg, self.N, self.T, self.device = cfg, N, T, device
-        self.geoms = build_geometry(cfg, T)
+        if prec not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (sorted(PRECISIONS),))
+        self.prec, self.mode = prec, PRECISIONS[prec]
+        self._twins = {}
+        self.geoms = build_geometry(cfg, T, TC_SINC_FOLD if self.mode is not None else SINC_FOLD)
         G = self.geoms
         self.nblk = len(G)
         self.Tq = G[-1].T_out
@@ -192,6 +199,42 @@ class EncoderPlan(object):
         self.zeros64 = torch.zeros(max(2 * max(g.Cout for g in G), 2 * self.emb), **f64)
         self.generation = 0
 
+    # -- GEMM dispatch: fp32 FFMA kernels or tcgen05 tensor-core kernels -------------
+    def split(self, name, buf, fresh=True):
+        """mode 1 (3xTF32): exactly-representable tf32 hi/lo parts of an operand, kept in
+        twin buffers; `fresh=False` reuses the split made earlier in the same step."""
+        if self.mode != 1:
+            return buf, None
+        tw = self._twins.get(name)
+        if tw is None or tw[0].numel() != buf.numel():
+            tw = (torch.empty_like(buf), torch.empty_like(buf))
+            self._twins[name] = tw
+            fresh = True
+        if fresh:
+            ops.call("pase_split_tf32", buf, tw[0], tw[1], buf.numel())
+        return tw
+
+    def nt(self, an, A, lda, afresh, bn, B, ldb, bfresh, C, ldc, M, N, K, alpha, bias,
+           rows_in, t_valid, rows_out, fold, cs, cq, acc):
+        if self.mode is None or lda % 32 != 0 or K % 4 != 0 or ldb % 4 != 0:
+            return ops.call("pase_gemm_nt", A, lda, B, ldb, C, ldc, M, N, K, alpha, bias,
+                            rows_in, t_valid, rows_out, fold, cs, cq, acc)
+        Ah, Al = self.split(an, A, afresh)
+        Bh, Bl = self.split(bn, B, bfresh)
+        return ops.call("pase_tc_gemm_nt", Ah, Al, A.numel() // lda, lda, Bh, Bl, ldb, C, ldc,
+                        M, N, K, alpha, bias, rows_in, t_valid, rows_out, fold, cs, cq, acc,
+                        self.mode)
+
+    def tn(self, an, A, lda, pitchA, offA, afresh, bn, B, ldb, pitchB, bfresh, C, ldc, I, J,
+           groups, rpg, alpha, acc):
+        if self.mode is None or ldb % 32 != 0 or lda % 4 != 0 or I % 4 != 0 or J % 32 != 0:
+            return ops.call("pase_gemm_tn", A, lda, pitchA, offA, B, ldb, pitchB, 0, C, ldc, I, J,
+                            groups, rpg, alpha, acc)
+        Ah, Al = self.split(an, A, afresh)
+        Bh, Bl = self.split(bn, B, bfresh)
+        return ops.call("pase_tc_gemm_tn", Ah, Al, lda, pitchA, offA, Bh, Bl, ldb, pitchB,
+                        B.numel() // ldb, C, ldc, I, J, groups, rpg, alpha, acc, self.mode)
+
     def nbytes(self):
         tot = 0
         for v in self.__dict__.values():
@@ -260,8 +303,9 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
             cs, cq = plan.stats_f[o:o + g.Nn], plan.stats_f[o + g.Nn:o + 2 * g.Nn]
         else:
             cs = cq = None
-        call("pase_gemm_nt", plan.apad[l], g.lda, plan.Wt[l], g.K, plan.y[l], g.Nn,
-             N * g.P, g.Nn, g.K, 1.0, bias, g.P, g.T_out, g.rows_out, g.fold, cs, cq, 0)
+        plan.nt(("apad", l), plan.apad[l], g.lda, True, ("Wt", l), plan.Wt[l], g.K, True,
+                plan.y[l], g.Nn, N * g.P, g.Nn, g.K, 1.0, bias, g.P, g.T_out, g.rows_out,
+                g.fold, cs, cq, 0)
         mean, invstd, scale, shift = plan.bn[l][0], plan.bn[l][1], plan.bn[l][2], plan.bn[l][3]
         if training:
             call("pase_bn_finalize", cs, cq, g.Cout, g.fold, float(N * g.T_out),
@@ -293,9 +337,9 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
         Wl = params["rnn.layers.0.linear.weight"].detach()
         Wq = torch.cat([Wl[:, Cq:], Wl[:, :Cq]], 1).contiguous()      # [x_{t-1} | x_t] order
         plan.Wq = Wq
-        call("pase_gemm_nt", plan.xq, Cq, Wq.reshape(-1), 2 * Cq, plan.Yg, 3 * H,
-             N * (Tq + 1), 3 * H, 2 * Cq, 1.0, P("rnn.layers.0.linear.bias"),
-             Tq + 1, Tq, Tq, 1, None, None, 0)
+        plan.nt("xq", plan.xq, Cq, True, "Wq", Wq.reshape(-1), 2 * Cq, True, plan.Yg, 3 * H,
+                N * (Tq + 1), 3 * H, 2 * Cq, 1.0, P("rnn.layers.0.linear.bias"),
+                Tq + 1, Tq, Tq, 1, None, None, 0)
         call("pase_qrnn_scan_fwd", plan.Yg, plan.cat, Kc, plan.Cst, N, Tq, H)
 
     parts = [params["W.weight"].detach().reshape(emb, -1)]
@@ -310,8 +354,8 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
         cs, cq = plan.stats_f[o:o + emb], plan.stats_f[o + emb:o + 2 * emb]
     else:
         cs = cq = None
-    call("pase_gemm_nt", plan.cat, Kc, Wcat.reshape(-1), Kc, plan.yout, emb, rows, emb, Kc,
-         1.0, P("W.bias"), rows, rows, rows, 1, cs, cq, 0)
+    plan.nt("cat", plan.cat, Kc, True, "Wcat", Wcat.reshape(-1), Kc, True, plan.yout, emb,
+            rows, emb, Kc, 1.0, P("W.bias"), rows, rows, rows, 1, cs, cq, 0)
     bo = plan.bn_out
     if plan.norm_out:
         if training:
@@ -351,11 +395,11 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
     call("pase_out_bwd_apply", plan.g, plan.yout, bo[0], bo[1], bo[2], S1o, S2o, float(rows),
          use_stats, rows, emb)
     call("pase_colsum", plan.g, emb, rows, emb, sb[plan.bs_bw:plan.bs_bw + emb])
-    call("pase_gemm_tn", plan.g, emb, rows, 0, plan.cat, Kc, rows, 0, plan.dWcat, Kc,
-         emb, Kc, 1, rows, 1.0, 0)
+    plan.tn("g", plan.g, emb, rows, 0, True, "cat", plan.cat, Kc, rows, False, plan.dWcat, Kc,
+            emb, Kc, 1, rows, 1.0, 0)
     call("pase_transpose_pad", plan.Wcat.reshape(-1), Kc, plan.WcatT, emb, emb, Kc)
-    call("pase_gemm_nt", plan.g, emb, plan.WcatT, emb, plan.dcat, Kc, rows, Kc, emb, 1.0, None,
-         rows, rows, rows, 1, None, None, 0)
+    plan.nt("g", plan.g, emb, False, "WcatT", plan.WcatT, emb, True, plan.dcat, Kc, rows, Kc,
+            emb, 1.0, None, rows, rows, rows, 1, None, None, 0)
     dWcat = plan.dWcat.view(emb, Kc)
     first = plan.H if plan.rnn else plan.Clast
     # gradients handed to autograd must not alias plan-owned buffers (the next backward
@@ -373,13 +417,13 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
         Cq, H = Cl, plan.H
         call("pase_qrnn_scan_bwd", plan.Yg, plan.Cst, plan.dcat, Kc, plan.dYg, N, Tq, H)
         call("pase_colsum", plan.dYg, 3 * H, rows, 3 * H, sb[plan.bs_bq:plan.bs_bq + 3 * H])
-        call("pase_gemm_tn", plan.dYg, 3 * H, Tq, 0, plan.xq, Cq, Tq + 1, 0, plan.dWq, 2 * Cq,
-             3 * H, 2 * Cq, N, Tq, 1.0, 0)
+        plan.tn("dYg", plan.dYg, 3 * H, Tq, 0, True, "xq", plan.xq, Cq, Tq + 1, False,
+                plan.dWq, 2 * Cq, 3 * H, 2 * Cq, N, Tq, 1.0, 0)
         dWq = plan.dWq.view(3 * H, 2 * Cq)
         grads["rnn.layers.0.linear.weight"] = torch.cat([dWq[:, Cq:], dWq[:, :Cq]], 1)
         call("pase_transpose_pad", plan.Wq.reshape(-1), 2 * Cq, plan.WqT, 3 * H, 3 * H, 2 * Cq)
-        call("pase_gemm_nt", plan.dYg, 3 * H, plan.WqT, 3 * H, plan.dsrc, 2 * Cq, rows, 2 * Cq,
-             3 * H, 1.0, None, rows, rows, rows, 1, None, None, 0)
+        plan.nt("dYg", plan.dYg, 3 * H, False, "WqT", plan.WqT, 3 * H, True, plan.dsrc, 2 * Cq,
+                rows, 2 * Cq, 3 * H, 1.0, None, rows, rows, rows, 1, None, None, 0)
         last_src = dict(A=plan.dsrc[Cq:], a_ss=Tq * 2 * Cq, a_rs=2 * Cq,
                         B=plan.dsrc, b_ss=Tq * 2 * Cq, b_rs=2 * Cq, b_shift=1)
     else:
@@ -421,8 +465,8 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
              P(pre + "norm.weight"), a1, a2, float(N * g.T_out), dst, d_ss,
              None if g.sinc else dbi)
         if g.sinc:
-            call("pase_gemm_tn", plan.dyz[l], g.Nn, g.rows_out, 0, plan.apad[l], g.lda, g.P, 0,
-                 plan.dWt[l], g.K, g.Nn, g.K, N, g.rows_out, 1.0, 0)
+            plan.tn(("dyz", l), plan.dyz[l], g.Nn, g.rows_out, 0, True, ("apad", l), plan.apad[l],
+                    g.lda, g.P, False, plan.dWt[l], g.K, g.Nn, g.K, N, g.rows_out, 1.0, 0)
             dlow = torch.empty_like(params[pre + "conv.low_hz_"])
             dband = torch.empty_like(params[pre + "conv.band_hz_"])
             call("pase_sinc_grad", plan.dWt[l], P(pre + "conv.low_hz_"),
@@ -431,17 +475,17 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
             grads[pre + "conv.low_hz_"] = dlow
             grads[pre + "conv.band_hz_"] = dband
         else:
-            call("pase_gemm_tn", plan.dyz[l], C, g.Pd, g.taps - 1, plan.apad[l], g.lda, g.P, 0,
-                 plan.dWt[l], g.K, C, g.K, N, g.T_out, 1.0, 0)
+            plan.tn(("dyz", l), plan.dyz[l], C, g.Pd, g.taps - 1, True, ("apad", l), plan.apad[l],
+                    g.lda, g.P, False, plan.dWt[l], g.K, C, g.K, N, g.T_out, 1.0, 0)
             dW = torch.empty_like(params[pre + "conv.weight"])
             call("pase_conv_w_from_fwd", plan.dWt[l], dW.reshape(-1), g.Cout, g.Cin, g.k)
             grads[pre + "conv.weight"] = dW
             if l > 0:
                 call("pase_conv_w_to_dgrad", P(pre + "conv.weight"), plan.Wd[l], g.Cout, g.Cin,
                      g.k, g.s, g.taps)
-                call("pase_gemm_nt", plan.dyz[l], C, plan.Wd[l], g.taps * C, plan.dxpad[l],
-                     g.s * g.Cin, N * g.Pd, g.s * g.Cin, g.taps * C, 1.0, None,
-                     g.Pd, g.P, g.P, 1, None, None, 0)
+                plan.nt(("dyz", l), plan.dyz[l], C, False, ("Wd", l), plan.Wd[l], g.taps * C, True,
+                        plan.dxpad[l], g.s * g.Cin, N * g.Pd, g.s * g.Cin, g.taps * C, 1.0, None,
+                        g.Pd, g.P, g.P, 1, None, None, 0)
 
     # one cast for every small reduction (double accumulators -> fp32 gradients)
     call("pase_cast_d2f", sb, plan.grad_vec, sb.numel(), 1.0)

@@ -9,6 +9,7 @@ default initialisation); their own ``forward`` is never called on this path.
 """
 import json
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -17,6 +18,8 @@ import torch.nn as nn
 
 from .modules import Model, format_frontend_chunk, format_frontend_output
 from . import encoder as _enc
+
+DEFAULT_PRECISION = "fp32"
 
 _DEFAULTS = dict(
     num_inputs=1, sincnet=True,
@@ -133,6 +136,8 @@ class WaveFe(Model):
         if cfg["norm_out"]:
             self.norm_out = nn.BatchNorm1d(emb, affine=False)
         self._plans = OrderedDict()
+        # GEMM numerics: "fp32" (FFMA), "3xtf32" (tcgen05, fp32-equivalent), "tf32" (tcgen05)
+        self.precision = os.environ.get("PASE_B200_PRECISION", DEFAULT_PRECISION)
         self._sinc_n = self._sinc_win = None
         self.last_output_ntc = None
 
@@ -164,10 +169,10 @@ class WaveFe(Model):
 
     # -- engine plumbing ---------------------------------------------------
     def _plan(self, N, T, device):
-        key = (N, T, str(device))
+        key = (N, T, str(device), self.precision)
         plan = self._plans.get(key)
         if plan is None:
-            plan = _enc.EncoderPlan(self.cfg, N, T, device)
+            plan = _enc.EncoderPlan(self.cfg, N, T, device, self.precision)
             self._plans[key] = plan
             while len(self._plans) > self.MAX_PLANS:
                 self._plans.popitem(last=False)

@@ -394,3 +394,44 @@ def call(name, *args):
         else:
             fn(*args)
     return 0
+
+
+# ---- tensor-core GEMM entry points (semantic spec: exact product of hi+lo operands) ----
+def _tf32_trunc(x):
+    return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def pase_split_tf32(x, hi, lo, n):
+    h = _tf32_trunc(x[:n])
+    hi[:n] = h
+    lo[:n] = _tf32_trunc(x[:n] - h)
+
+
+def pase_tc_gemm_nt(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, C, ldc, M, N, K, alpha, bias, rows_in,
+                    t_valid, rows_out, fold, colsum, colsumsq, accumulate, mode):
+    need = M * R + K
+    A = torch.zeros(need)
+    lim = min(a_rows * R, Ahi.numel(), need)         # TMA zero-fills rows >= a_rows
+    A[:lim] = Ahi[:lim]
+    if mode == 1:
+        A[:lim] += Alo[:lim]
+    B = Bhi[:N * ldb].clone()
+    if mode == 1:
+        B += Blo[:N * ldb]
+    pase_gemm_nt(A, R, B, ldb, C, ldc, M, N, K, alpha, bias, rows_in, t_valid, rows_out, fold,
+                 colsum, colsumsq, accumulate)
+
+
+def pase_tc_gemm_tn(Ahi, Alo, lda, pitchA, offA, Bhi, Blo, R, pitchB, b_rows_total, C, ldc, I, J,
+                    groups, rows_per_group, alpha, accumulate, mode):
+    A = Ahi.clone()
+    if mode == 1:
+        A = A + Alo
+    needB = ((groups - 1) * pitchB + rows_per_group) * R + J
+    B = torch.zeros(max(needB, Bhi.numel()))
+    lim = min(b_rows_total * R, Bhi.numel())
+    B[:lim] = Bhi[:lim]
+    if mode == 1:
+        B[:lim] += Blo[:lim]
+    pase_gemm_tn(A, lda, pitchA, offA, B, R, pitchB, 0, C, ldc, I, J, groups, rows_per_group,
+                 alpha, accumulate)

@@ -24,17 +24,21 @@ CASES = ["enc_pase_eval_16000", "enc_pasep_eval_3200", "enc_pasep_train_3200",
          "enc_mini_train_1763", "enc_mininornn_train_1600"]
 
 
-def _native(cfg, seed, training):
+def _native(cfg, seed, training, precision="fp32"):
     m = WaveFe(**cfg)
     m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    m.precision = precision
     return m.cuda().train(training)
 
 
+# "fp32": FFMA kernels; "3xtf32": tcgen05 tensor cores with error-compensated TF32
+# (fp32-equivalent) -- both must meet the fp32 parity bar.
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
 @pytest.mark.parametrize("name", CASES)
-def test_encoder_matches_reference_golden(name):
+def test_encoder_matches_reference_golden(name, precision):
     gold, meta = load_golden(name)
     cfg = resolve_cfg(meta["cfg"])
-    model = _native(cfg, meta["seed"], meta["training"])
+    model = _native(cfg, meta["seed"], meta["training"], precision)
     x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5).cuda()
     assert model.frame_counts(meta["T"]) == gold["frame_counts"].tolist()
     if not meta["training"]:
@@ -96,11 +100,12 @@ def test_dict_batch_and_modes():
             assert_close(m(x, mode=mode), O.select_output(base.cpu(), mode), 1e-5, 1e-6, mode)
 
 
-def test_full_length_against_oracle():
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+def test_full_length_against_oracle(precision):
     """T=32000 (the BASELINE.json chunk length), N=3 chunks, fwd + bwd vs the CPU oracle."""
     cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
     seed, N, T = 21, 3, 32000
-    model = _native(cfg, seed, True)
+    model = _native(cfg, seed, True, precision)
     sd = fill_state_dict(WaveFe(**cfg).state_dict(), seed)
     x = seeded_randn((N, 1, T), seed + 1, 0.5)
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
@@ -123,10 +128,28 @@ def test_full_length_against_oracle():
         assert_close(p.grad, ref, 2e-3, atol, "grad " + k)
 
 
-def test_benchmark_shape_properties():
+def test_tf32_mode_is_l2_equivalent():
+    """Single-pass TF32 tensor-core mode (the numerics cuDNN uses by default for the
+    reference on an Ampere+ GPU): not elementwise-fp32, but L2-equivalent within 1e-3
+    (BASELINE.json north_star: 'encoder output L2-equivalent to reference within 1e-3')."""
+    gold, meta = load_golden("enc_pasep_train_4001")
+    cfg = resolve_cfg(meta["cfg"])
+    model = _native(cfg, meta["seed"], True, "tf32")
+    x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5).cuda()
+    y = model(x)
+    assert rel_l2(y.detach().cpu(), gold["y"]) < 2e-3
+    cot = seeded_randn(tuple(y.shape), meta["seed"] + 2).cuda()
+    (y * cot).sum().backward()
+    g = model.blocks[4].conv.weight.grad.cpu()
+    from helpers import sample_view
+    assert rel_l2(sample_view(g), gold["gsample/blocks.4.conv.weight"]) < 2e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+def test_benchmark_shape_properties(precision):
     """B=32, T=32000 (BASELINE.json configs[1]): properties that do not need the oracle."""
     cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
-    model = _native(cfg, 5, True)
+    model = _native(cfg, 5, True, precision)
     x = seeded_randn((32, 1, 32000), 77, 0.5).cuda()
     y = model(x)
     assert tuple(y.shape) == (32, 256, 200) and bool(torch.isfinite(y).all())

@@ -36,11 +36,15 @@ CASES = ["enc_pase_eval_16000", "enc_pasep_eval_3200", "enc_pasep_train_3200",
          "enc_mini_train_1763", "enc_mininornn_train_1600"]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
 @pytest.mark.parametrize("name", CASES)
-def test_encoder_host_logic(name, emulated):
+def test_encoder_host_logic(name, precision, emulated):
+    """precision='3xtf32' exercises the tensor-core plan (sinc fold 32, hi/lo operand twins,
+    folded-row addressing) with the emulated kernels."""
     gold, meta = load_golden(name)
     cfg = resolve_cfg(meta["cfg"])
     model = WaveFe(**cfg)
+    model.precision = precision
     model.load_state_dict(fill_state_dict(model.state_dict(), meta["seed"]))
     model.train(meta["training"])
     x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5)

@@ -164,6 +164,8 @@ def test_prelu_colsum_cast():
     run_both("pase_prelu_bwd", [u, dh, a, torch.zeros(rows * 96), torch.zeros(C, dtype=torch.float64),
                                 rows, C, 90, 88, 96])
     run_both("pase_colsum", [u, 90, rows, C, torch.zeros(C, dtype=torch.float64)])
+    wide = R(7 * 9000, seed=60)
+    run_both("pase_colsum", [wide, 9000, 7, 8999, torch.zeros(8999, dtype=torch.float64)])
     run_both("pase_cast_d2f", [R(100, seed=37).double(), torch.zeros(100), 100, 0.5])
 
 
