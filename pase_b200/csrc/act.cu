@@ -94,13 +94,17 @@ bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
     }
     pacc = make_float4(0.f, 0.f, 0.f, 0.f);
   };
-#pragma unroll 1
+  const int nvalid = (Tp - tau0) < RUN ? (int)(Tp - tau0) : RUN;
+  float4 vals[RUN];
+#pragma unroll
+  for (int i = 0; i < RUN; ++i)
+    if (i < nvalid) vals[i] = ld4(yn + (long)reflect_idx((int)tau0 + i - padL, T) * C + c);
+#pragma unroll
   for (int i = 0; i < RUN; ++i) {
+    if (i >= nvalid) break;
     const long tau = tau0 + i;
-    if (tau >= Tp) break;
     const int tr = (int)tau - padL;
-    const int t = reflect_idx(tr, T);
-    const float4 v = ld4(yn + (long)t * C + c);
+    const float4 v = vals[i];
     float4 a;
     a.x = prelu1(fmaf(v.x, sc.x, sh.x), al.x);
     a.y = prelu1(fmaf(v.y, sc.y, sh.y), al.y);
@@ -142,43 +146,53 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
   const int q = (int)(idx % C4);
   const long run = idx / C4;
   const long t0 = run * RUN;
+  const int c = q * 4;
+  float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, a3[4] = {0, 0, 0, 0};
   if (t0 < T) {
-    const int c = q * 4;
     const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
     const float4 mu = ld4(mean + c), is = ld4(invstd + c);
     const float* yn = y + (long)n * y_ss;
     float* dn = dst + (long)n * d_ss;
     const int pool_len = s.pool_d > 0 ? s.pool_T * s.pool_d : 0;
     const float inv_d = s.pool_d > 0 ? 1.f / (float)s.pool_d : 0.f;
-    float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, a3[4] = {0, 0, 0, 0};
-#pragma unroll 1
+    const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
+    float4 gs[RUN], ys[RUN];
+    // phase 1: issue every load of the run (gradient sources + saved pre-activation)
+#pragma unroll
     for (int i = 0; i < RUN; ++i) {
-      const int t = (int)t0 + i;
-      if (t >= T) break;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto add4 = [&](const float* p, float w) {
-        const float4 v = ld4(p);
-        g.x += v.x * w; g.y += v.y * w; g.z += v.z * w; g.w += v.w * w;
-      };
-      if (s.A) {
-        const float* an = s.A + (long)n * s.a_ss + c;
-        add4(an + (long)(t + s.padL) * s.a_rs, 1.f);
-        if (s.padL > 0 && t >= 1 && t <= s.padL) add4(an + (long)(s.padL - t) * s.a_rs, 1.f);
-        if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
-          add4(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs, 1.f);
+      if (i < nvalid) {
+        const int t = (int)t0 + i;
+        auto add4 = [&](const float* p, float w) {
+          const float4 v = ld4(p);
+          g.x += v.x * w; g.y += v.y * w; g.z += v.z * w; g.w += v.w * w;
+        };
+        if (s.A) {
+          const float* an = s.A + (long)n * s.a_ss + c;
+          add4(an + (long)(t + s.padL) * s.a_rs, 1.f);
+          if (s.padL > 0 && t >= 1 && t <= s.padL) add4(an + (long)(s.padL - t) * s.a_rs, 1.f);
+          if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
+            add4(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs, 1.f);
+        }
+        if (s.B) {
+          const int tb = t + s.b_shift;
+          if (tb >= 0 && tb < T) add4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c, 1.f);
+        }
+        if (s.P && t < pool_len)
+          add4(s.P + (long)n * s.p_ss + (long)(t / s.pool_d) * s.p_rs + c, inv_d);
+        ys[i] = ld4(yn + (long)t * C + c);
       }
-      if (s.B) {
-        const int tb = t + s.b_shift;
-        if (tb >= 0 && tb < T) add4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c, 1.f);
-      }
-      if (s.P && t < pool_len)
-        add4(s.P + (long)n * s.p_ss + (long)(t / s.pool_d) * s.p_rs + c, inv_d);
-      const float4 v = ld4(yn + (long)t * C + c);
-      const float gg[4] = {g.x, g.y, g.z, g.w};
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-      const float alv[4] = {al.x, al.y, al.z, al.w};
-      const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+      gs[i] = g;
+    }
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const float alv[4] = {al.x, al.y, al.z, al.w};
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      if (i >= nvalid) break;
+      const int t = (int)t0 + i;
+      const float gg[4] = {gs[i].x, gs[i].y, gs[i].z, gs[i].w};
+      const float vv[4] = {ys[i].x, ys[i].y, ys[i].z, ys[i].w};
       float du[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -192,6 +206,21 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
       }
       st4(dn + (long)t * C + c, make_float4(du[0], du[1], du[2], du[3]));
     }
+  }
+  // lanes that own the same channel quad (C/4 < 32, power of two) combine before the
+  // shared-memory atomics; every lane of the warp takes part (idle lanes contribute zeros)
+  const bool pre = (C4 < 32) && ((C4 & (C4 - 1)) == 0) && ((blockDim.x % C4) == 0);
+  if (pre) {
+    for (int off = 16; off >= C4; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a1[k] += __shfl_xor_sync(0xffffffffu, a1[k], off);
+        a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], off);
+        a3[k] += __shfl_xor_sync(0xffffffffu, a3[k], off);
+      }
+    }
+  }
+  if ((pre && (threadIdx.x & 31) < C4) || (!pre && t0 < T)) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       atomicAdd(&red[0 * C + c + k], a1[k]);
@@ -236,13 +265,20 @@ bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
     const float* yn = y + (long)n * y_ss;
     float* dn = dst + (long)n * d_ss;
     float acc[4] = {0, 0, 0, 0};
-#pragma unroll 1
+    const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
+    float4 vs[RUN], ds[RUN];
+#pragma unroll
+    for (int i = 0; i < RUN; ++i)
+      if (i < nvalid) {
+        vs[i] = ld4(yn + (long)((int)t0 + i) * C + c);
+        ds[i] = ld4(dn + (long)((int)t0 + i) * C + c);
+      }
+#pragma unroll
     for (int i = 0; i < RUN; ++i) {
+      if (i >= nvalid) break;
       const int t = (int)t0 + i;
-      if (t >= T) break;
-      const float4 v = ld4(yn + (long)t * C + c);
-      const float4 d = ld4(dn + (long)t * C + c);
-      const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+      const float vv[4] = {vs[i].x, vs[i].y, vs[i].z, vs[i].w};
+      const float dd[4] = {ds[i].x, ds[i].y, ds[i].z, ds[i].w};
       float o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {

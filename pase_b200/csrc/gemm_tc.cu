@@ -177,45 +177,140 @@ __device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Thread layout shared by both kernels: warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// issuer, warps 2..17 = 16 epilogue warps.  Epilogue warp w reads TMEM lanes 32*(w%4)..
+// (hardware restriction) and owns column chunk (w-2)/4 of the tile, so every warp folds /
+// stores only 32 columns: short per-warp instruction streams, 4 warps per scheduler.
+constexpr int N_EPI_WARPS = 16;
+constexpr int NTHREADS_V3 = (2 + N_EPI_WARPS) * 32;
+constexpr int OUT_STG_FLOATS = 32 * 8;                                // 32 rows x 8 cols per pass
+constexpr int OUT_STAGE_BYTES = N_EPI_WARPS * OUT_STG_FLOATS * 4;     // 16 KB
+constexpr int SMEM_LIMIT = 232448;                                    // 227 KB opt-in maximum
+constexpr int BAR_BYTES = 256;
+constexpr int MAX_STAGES = 8;
+
+inline int pick_stages(int stage_bytes, int stat_bytes) {
+  int st = (SMEM_LIMIT - 1024 - BAR_BYTES - OUT_STAGE_BYTES - stat_bytes) / stage_bytes;
+  return st > MAX_STAGES ? MAX_STAGES : st;
+}
+inline int smem_bytes(int stages, int stage_bytes, int stat_bytes) {
+  return stages * stage_bytes + 1024 + BAR_BYTES + OUT_STAGE_BYTES + stat_bytes;
+}
+
+// Coalesced store of one warp's 32 rows x 32 columns (v[j] = column j of this lane's row).
+// Four passes of 8 columns through a 1 KB swizzled staging tile; after the transpose a
+// lane owns 16 B of a row and 2 lanes cover a full 32 B sector.  `nlim` = first invalid
+// column of this lane's row (0 for rows that must not be written).
+template <bool RED>
+__device__ __forceinline__ void store_chunk(float* stg, const float (&v)[32], int lane,
+                                            float* __restrict__ C, long ldc, long orow, int nlim,
+                                            int nb, bool vec_ok, int accumulate) {
+  const int sw = (lane >> 2) & 1;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    *reinterpret_cast<float4*>(&stg[lane * 8 + 4 * (0 ^ sw)]) =
+        make_float4(v[pass * 8 + 0], v[pass * 8 + 1], v[pass * 8 + 2], v[pass * 8 + 3]);
+    *reinterpret_cast<float4*>(&stg[lane * 8 + 4 * (1 ^ sw)]) =
+        make_float4(v[pass * 8 + 4], v[pass * 8 + 5], v[pass * 8 + 6], v[pass * 8 + 7]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = it * 16 + (lane >> 1), h = lane & 1;
+      const float4 val =
+          *reinterpret_cast<const float4*>(&stg[r * 8 + 4 * (h ^ ((r >> 2) & 1))]);
+      const long orow_r = __shfl_sync(0xffffffffu, orow, r);
+      const int nlim_r = __shfl_sync(0xffffffffu, nlim, r);
+      const int n = nb + pass * 8 + h * 4;
+      float* cp = C + orow_r * ldc + n;
+      float x[4] = {val.x, val.y, val.z, val.w};
+      if (n + 3 < nlim_r && vec_ok) {
+        if (RED) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(x[0]),
+                       "f"(x[1]), "f"(x[2]), "f"(x[3])
+                       : "memory");
+        } else {
+          if (accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(cp);
+            x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+          }
+          *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < nlim_r) {
+            if (RED) atomicAdd(cp + j, x[j]);
+            else cp[j] = accumulate ? cp[j] + x[j] : x[j];
+          }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// one 64-bit shared-memory descriptor = constant bits | (address >> 4)
+template <int LAYOUT>
+__device__ __forceinline__ uint64_t desc_hi_bits(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc<LAYOUT>(0, lbo_bytes, sbo_bytes);
+}
+
 template <int BN, bool SPLIT>
 struct NTCfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                              2 * BN * 4 /*stats*/;
+  static constexpr int TMEM_COLS = 2 * BN;      // two accumulator buffers
+  static constexpr int EPI_ACTIVE = 4 * (BN / 32);
 };
 
 // ------------------------------------------------------------------ NT kernel ----
+// Persistent: CTA b processes tiles b, b+grid, ... (n-tile fastest so concurrently running
+// CTAs share A rows in L2).  The MMA warp accumulates `flush_kb` k-blocks into one of two
+// TMEM buffers; the epilogue warps fold each finished buffer into fp32 register sums with
+// round-to-nearest adds (the tensor core's own accumulator rounds toward zero, which drifts
+// over long K) while the MMAs of the next chunk / next tile run.
 template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_V3, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
                   int R, float* __restrict__ C, long ldc, int M, int N, int K, float alpha,
                   const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
-                  double* __restrict__ colsumsq, int accumulate) {
+                  double* __restrict__ colsumsq, int accumulate, int flush_kb, int stages,
+                  int stat_cols) {
   using Cfg = NTCfg<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* done_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
-  float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_full = empty_bar + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_out = reinterpret_cast<float*>(smem + stages * Cfg::STAGE_BYTES + BAR_BYTES);
+  float* s_stats = s_out + OUT_STAGE_BYTES / 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
+  const int total_tiles = n_tiles * m_tiles;
   const int nkb = (K + BKF - 1) / BKF;
+  if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
+  const int nchunks = (nkb + flush_kb - 1) / flush_kb;
+  const bool want_stats = colsum != nullptr;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(done_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], Cfg::EPI_ACTIVE);       // one arrival per active epilogue warp
+    }
     fence_barrier_init();
     tmap_prefetch(&mAhi);
     tmap_prefetch(&mBhi);
@@ -224,8 +319,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       tmap_prefetch(&mBlo);
     }
   }
-  for (int i = threadIdx.x; i < 2 * BN; i += NTHREADS) s_stats[i] = 0.f;
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (want_stats)
+    for (int i = threadIdx.x; i < 2 * stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -233,19 +329,23 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 1);
-        uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        const int kf = kb * BKF;
-        const int arow = m0 + kf / R, acol = kf % R;
-        tma_load_2d(st, &mAhi, &full_bar[s], acol, arow);
-        tma_load_2d(st + Cfg::A_BYTES, &mBhi, &full_bar[s], kf, n0);
-        if (SPLIT) {
-          tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mAlo, &full_bar[s], acol, arow);
-          tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mBlo, &full_bar[s], kf, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1, 1);
+          uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          const int kf = kb * BKF;
+          const int arow = m0 + kf / R, acol = kf % R;
+          tma_load_2d(st, &mAhi, &full_bar[s], acol, arow);
+          tma_load_2d(st + Cfg::A_BYTES, &mBhi, &full_bar[s], kf, n0);
+          if (SPLIT) {
+            tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mAlo, &full_bar[s], acol, arow);
+            tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mBlo, &full_bar[s], kf, n0);
+          }
         }
       }
     }
@@ -253,93 +353,119 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph, 2);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-        const uint32_t b_hi = a_hi + Cfg::A_BYTES;
-        const uint32_t a_lo = b_hi + Cfg::B_BYTES;
-        const uint32_t b_lo = a_lo + Cfg::A_BYTES;
+      const uint64_t dconst = desc_hi_bits<2>(16, 1024);
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      uint32_t it = 0, c = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int ch = 0; ch < nchunks; ++ch, ++c) {
+          const uint32_t b = c & 1, aph = (c >> 1) & 1;
+          mbar_wait(&acc_empty[b], aph ^ 1, 4);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + b * BN;
+          const int kb_lo = ch * flush_kb;
+          const int kb_hi = (kb_lo + flush_kb < nkb) ? kb_lo + flush_kb : nkb;
+          for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (it / stages) & 1;
+            mbar_wait(&full_bar[s], ph, 2);
+            tc_fence_after();
+            // descriptor = constant bits + (byte address >> 4); k-step of 8 tf32 = +32 B = +2
+            const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
+            const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
+            const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
+            const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
+            const uint32_t first = (kb == kb_lo) ? 0u : 1u;
 #pragma unroll
-        for (int k = 0; k < BKF / UMMA_K; ++k) {
-          const uint32_t off = k * UMMA_K * 4;
-          const uint64_t dah = make_desc(a_hi + off, 16, 1024);
-          const uint64_t dbh = make_desc(b_hi + off, 16, 1024);
-          if (SPLIT) {
-            const uint64_t dal = make_desc(a_lo + off, 16, 1024);
-            const uint64_t dbl = make_desc(b_lo + off, 16, 1024);
-            umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);
-            umma_tf32(tmem_base, dah, dbl, idesc, 1);
-            umma_tf32(tmem_base, dah, dbh, idesc, 1);
-          } else {
-            umma_tf32(tmem_base, dah, dbh, idesc, (kb | k) != 0);
+            for (int k = 0; k < BKF / UMMA_K; ++k) {
+              const uint32_t acc = (k == 0) ? first : 1u;
+              if (SPLIT) {
+                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
+                umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+              } else {
+                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
+              }
+            }
+            umma_commit(&empty_bar[s]);          // frees the smem stage once the MMAs retire
           }
+          umma_commit(&acc_full[b]);             // this chunk's accumulator is complete
         }
-        umma_commit(&empty_bar[s]);            // frees the smem stage once the MMAs retire
       }
-      umma_commit(done_bar);                   // accumulator complete
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: 4 warps, TMEM lane quarter = warp % 4 ----------------
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int m = m0 + r;
-    mbar_wait(done_bar, 0, 3);
-    tc_fence_after();
-    const bool row_ok = m < M;
-    int g = 0, u = 0;
-    if (row_ok) {
-      g = m / rm.rows_in;
-      u = m - g * rm.rows_in;
-    }
-    const long orow = (long)g * rm.rows_out + u;
-    const bool want_stats = colsum != nullptr;
-    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
-#pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), raw);
-      float v[32], sq[32];
-      const int nb = n0 + cc * 32;
-      float* cp = C + orow * ldc + nb;
-      uint32_t okmask = 0;
+    // ---------------- epilogue: 16 warps = 4 TMEM lane quarters x 4 column chunks ------------
+    const int e = warp - 2;
+    const int q = warp & 3;                      // hardware: warp w may access lanes 32*(w%4)..
+    const int cc = e >> 2;                       // this warp's 32-column chunk of the tile
+    if (cc < BN / 32) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+      float* stg = s_out + e * OUT_STG_FLOATS;
+      uint32_t c = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        float sums[32];
+        for (int ch = 0; ch < nchunks; ++ch, ++c) {
+          const uint32_t b = c & 1, aph = (c >> 1) & 1;
+          mbar_wait(&acc_full[b], aph, 3);
+          tc_fence_after();
+          uint32_t raw[32];
+          tmem_ld32(taddr + b * BN, raw);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[b]);        // buffer may be overwritten now
+          if (ch == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = nb + j;
-        const bool ok = row_ok && (n < N) && (u * rm.fold + n / rm.cols_per_fold < rm.t_valid);
-        float x = __uint_as_float(raw[j]) * alpha;
-        if (bias != nullptr && n < N) x += bias[n];
-        if (ok && accumulate) x += cp[j];
-        okmask |= ok ? (1u << j) : 0u;
-        v[j] = ok ? x : 0.f;
-        sq[j] = ok ? x * x : 0.f;
-      }
-      if (okmask == 0xFFFFFFFFu && vec_ok) {
+            for (int j = 0; j < 32; ++j) sums[j] = __uint_as_float(raw[j]);
+          } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else if (okmask != 0u) {
+            for (int j = 0; j < 32; ++j) sums[j] += __uint_as_float(raw[j]);
+          }
+        }
+        // ---- output: bias, row map / validity, optional accumulate, BatchNorm statistics ----
+        const int m = m0 + q * 32 + lane;
+        long orow = 0;
+        int nlim = 0;                            // columns [0, nlim) of this row are valid
+        if (m < M) {
+          const int g = m / rm.rows_in;
+          const int u = m - g * rm.rows_in;
+          orow = (long)g * rm.rows_out + u;
+          const long lim = (long)(rm.t_valid - u * rm.fold) * rm.cols_per_fold;
+          nlim = lim <= 0 ? 0 : (lim >= N ? N : (int)lim);
+        }
+        const int nb = n0 + cc * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (okmask & (1u << j)) cp[j] = v[j];
-      }
-      if (want_stats) {
-        const float s1 = colsum32(v, lane);
-        const float s2 = colsum32(sq, lane);
-        atomicAdd(&s_stats[cc * 32 + lane], s1);
-        atomicAdd(&s_stats[BN + cc * 32 + lane], s2);
+        for (int j = 0; j < 32; ++j) {
+          float x = sums[j] * alpha;
+          if (bias != nullptr && nb + j < N) x += __ldg(bias + nb + j);
+          sums[j] = x;
+        }
+        store_chunk<false>(stg, sums, lane, C, ldc, orow, nlim, nb, vec_ok, accumulate);
+        if (want_stats) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sums[j] = (nb + j < nlim) ? sums[j] : 0.f;
+            sq[j] = sums[j] * sums[j];
+          }
+          const float s1 = colsum32(sums, lane);
+          const float s2 = colsum32(sq, lane);
+          if (nb + lane < N) {
+            atomicAdd(&s_stats[nb + lane], s1);
+            atomicAdd(&s_stats[stat_cols + nb + lane], s2);
+          }
+        }
       }
     }
     if (want_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps only
-      const int t = threadIdx.x - 64;
-      for (int c = t; c < 2 * BN; c += 128) {
-        const int which = c / BN, col = c - which * BN;
-        if (n0 + col < N)
-          atomicAdd((which == 0 ? colsum : colsumsq) + n0 + col, (double)s_stats[c]);
+      asm volatile("bar.sync 1, 512;" ::: "memory");     // the 16 epilogue warps only
+      for (int col = threadIdx.x - 64; col < N; col += N_EPI_WARPS * 32) {
+        const float a = s_stats[col], b2 = s_stats[stat_cols + col];
+        if (a != 0.f || b2 != 0.f) {
+          atomicAdd(colsum + col, (double)a);
+          atomicAdd(colsumsq + col, (double)b2);
+        }
       }
     }
     tc_fence_before();
@@ -347,7 +473,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -361,25 +487,28 @@ struct TNCfg {
   static constexpr int A_BYTES = TN_KR * BM * 4;          // 4 MN-blocks of [32 rows x 128 B]
   static constexpr int B_BYTES = TN_KR * BN * 4;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int EPI_ACTIVE = 4 * (BN / 32);
 };
 
 template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_V3, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
                   int R, float* __restrict__ C, long ldc, int I, int J, int groups,
-                  int rows_per_group, float alpha, int chunks_per_split) {
+                  int rows_per_group, float alpha, int chunks_per_split, int flush_ch,
+                  int stages) {
   using Cfg = TNCfg<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* done_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_full = empty_bar + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_out = reinterpret_cast<float*>(smem + stages * Cfg::STAGE_BYTES + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * BN, i0 = blockIdx.y * BM;
@@ -389,25 +518,30 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   long c_end = c_begin + chunks_per_split;
   if (c_end > total_chunks) c_end = total_chunks;
   const int nch = (int)(c_end - c_begin);
+  if (flush_ch <= 0 || flush_ch > nch) flush_ch = nch > 0 ? nch : 1;
+  const int nflush = (nch + flush_ch - 1) / flush_ch;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(done_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], Cfg::EPI_ACTIVE);
+    }
     fence_barrier_init();
     tmap_prefetch(&mAhi);
     tmap_prefetch(&mBhi);
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (nch <= 0) {                      // uniform across the CTA
     __syncthreads();
-    if (warp == 1) tmem_dealloc<BN>(tmem_base);
+    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     return;
   }
   const int jq = j0 / R, jc = j0 % R;  // folded-row offset / column of this B tile
@@ -415,8 +549,8 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < nch; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        const int s = it % stages;
+        const uint32_t ph = (it / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1, 11);
         const long ch = c_begin + it;
         const int g = (int)(ch / cpg);
@@ -446,57 +580,80 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
-      for (int it = 0; it < nch; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (it / Cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph, 12);
+      const uint64_t dconst = desc_hi_bits<1>(TN_KR * 128, 512);
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      for (int f = 0; f < nflush; ++f) {
+        const uint32_t b = f & 1, aph = (f >> 1) & 1;
+        mbar_wait(&acc_empty[b], aph ^ 1, 14);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-        const uint32_t b_hi = a_hi + Cfg::A_BYTES;
-        const uint32_t a_lo = b_hi + Cfg::B_BYTES;
-        const uint32_t b_lo = a_lo + Cfg::A_BYTES;
+        const uint32_t d_tmem = tmem_base + b * BN;
+        const int it_lo = f * flush_ch;
+        const int it_hi = (it_lo + flush_ch < nch) ? it_lo + flush_ch : nch;
+        for (int it = it_lo; it < it_hi; ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&full_bar[s], ph, 12);
+          tc_fence_after();
+          const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
+          const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
+          const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
+          const uint32_t first = (it == it_lo) ? 0u : 1u;
 #pragma unroll
-        for (int k = 0; k < TN_KR / UMMA_K; ++k) {
-          const uint32_t off = k * 1024;               // 8 k-rows of 128 B
-          const uint64_t dah = make_desc<1>(a_hi + off, TN_KR * 128, 512);
-          const uint64_t dbh = make_desc<1>(b_hi + off, TN_KR * 128, 512);
-          if (SPLIT) {
-            const uint64_t dal = make_desc<1>(a_lo + off, TN_KR * 128, 512);
-            const uint64_t dbl = make_desc<1>(b_lo + off, TN_KR * 128, 512);
-            umma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);
-            umma_tf32(tmem_base, dah, dbl, idesc, 1);
-            umma_tf32(tmem_base, dah, dbh, idesc, 1);
-          } else {
-            umma_tf32(tmem_base, dah, dbh, idesc, (it | k) != 0);
+          for (int k = 0; k < TN_KR / UMMA_K; ++k) {
+            const uint32_t acc = (k == 0) ? first : 1u;
+            const uint32_t o = k * (1024 >> 4);          // 8 k-rows of 128 B
+            if (SPLIT) {
+              umma_tf32(d_tmem, dal + o, dbh + o, idesc, acc);
+              umma_tf32(d_tmem, dah + o, dbl + o, idesc, 1);
+              umma_tf32(d_tmem, dah + o, dbh + o, idesc, 1);
+            } else {
+              umma_tf32(d_tmem, dah + o, dbh + o, idesc, acc);
+            }
           }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[b]);
       }
-      umma_commit(done_bar);
     }
     __syncwarp();
   } else {
+    const int e = warp - 2;
     const int q = warp & 3;
-    const int i = i0 + q * 32 + lane;
-    mbar_wait(done_bar, 0, 13);
-    tc_fence_after();
-#pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), raw);
-      if (i < I) {
-        float* cp = C + (long)i * ldc + j0 + cc * 32;
+    const int cc = e >> 2;
+    if (cc < BN / 32) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+      float sums[32];
+      for (int f = 0; f < nflush; ++f) {
+        const uint32_t b = f & 1, aph = (f >> 1) & 1;
+        mbar_wait(&acc_full[b], aph, 13);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(taddr + b * BN, raw);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        if (f == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j0 + cc * 32 + j < J) atomicAdd(cp + j, __uint_as_float(raw[j]) * alpha);
+          for (int j = 0; j < 32; ++j) sums[j] = __uint_as_float(raw[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sums[j] += __uint_as_float(raw[j]);
+        }
       }
+      const int i = i0 + q * 32 + lane;
+      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sums[j] *= alpha;
+      store_chunk<true>(s_out + e * OUT_STG_FLOATS, sums, lane, C, ldc, (long)i, i < I ? J : 0,
+                        j0 + cc * 32, vec_ok, 0);
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -549,22 +706,31 @@ int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims
 template <int BN, bool SPLIT>
 int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
               const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
-              const float* bias, RowMap rm, double* cs, double* cq, int accumulate,
+              const float* bias, RowMap rm, double* cs, double* cq, int accumulate, int flush_kb,
               cudaStream_t st) {
   using Cfg = NTCfg<BN, SPLIT>;
   static bool attr = false;
+  const int stat_cols = cs ? ((N + 31) / 32) * 32 : 0;
+  const int stages = pick_stages(Cfg::STAGE_BYTES, 2 * stat_cols * 4);
+  const int smem = smem_bytes(stages, Cfg::STAGE_BYTES, 2 * stat_cols * 4);
+  if (stages < 2) {
+    pase_set_error("pase_tc_gemm_nt: not enough shared memory for 2 pipeline stages");
+    return PASE_ERR_UNSUPPORTED;
+  }
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, SPLIT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
       pase_set_error("pase_tc_gemm_nt: smem attribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  tc_gemm_nt_kernel<BN, SPLIT><<<grid, NTHREADS, Cfg::SMEM, st>>>(ah, al, bh, bl, R, C, ldc, M, N, K,
-                                                                 alpha, bias, rm, cs, cq, accumulate);
+  const long tiles = (long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const int grid = (int)(tiles < pase_num_sms() ? tiles : pase_num_sms());
+  tc_gemm_nt_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(
+      ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
+      stat_cols);
   PASE_LAUNCH_CHECK("pase_tc_gemm_nt");
   return PASE_OK;
 }
@@ -572,12 +738,14 @@ int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
 template <int BN, bool SPLIT>
 int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
               const CUtensorMap& bl, int R, float* C, long ldc, int I, int J, int groups,
-              int rows_per_group, float alpha, cudaStream_t st) {
+              int rows_per_group, float alpha, int flush_ch, cudaStream_t st) {
   using Cfg = TNCfg<BN, SPLIT>;
   static bool attr = false;
+  const int stages = pick_stages(Cfg::STAGE_BYTES, 0);
+  const int smem = smem_bytes(stages, Cfg::STAGE_BYTES, 0);
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, SPLIT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
       pase_set_error("pase_tc_gemm_tn: smem attribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -593,9 +761,9 @@ int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   long cps = (total + splits - 1) / splits;
   splits = (total + cps - 1) / cps;
   dim3 grid(tj, ti, (unsigned)splits);
-  tc_gemm_tn_kernel<BN, SPLIT><<<grid, NTHREADS, Cfg::SMEM, st>>>(ah, al, bh, bl, R, C, ldc, I, J,
-                                                                 groups, rows_per_group, alpha,
-                                                                 (int)cps);
+  tc_gemm_tn_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, R, C, ldc, I, J, groups,
+                                                            rows_per_group, alpha, (int)cps,
+                                                            flush_ch, stages);
   PASE_LAUNCH_CHECK("pase_tc_gemm_tn");
   return PASE_OK;
 }
@@ -617,13 +785,13 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
       l.y = __uint_as_float(__float_as_uint(v.y - h.y) & 0xFFFFE000u);
       l.z = __uint_as_float(__float_as_uint(v.z - h.z) & 0xFFFFE000u);
       l.w = __uint_as_float(__float_as_uint(v.w - h.w) & 0xFFFFE000u);
-      *reinterpret_cast<float4*>(hi + i) = h;
+      if (hi != nullptr) *reinterpret_cast<float4*>(hi + i) = h;
       *reinterpret_cast<float4*>(lo + i) = l;
     } else {
       for (long j = i; j < n; ++j) {
         const float v = x[j];
         const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        hi[j] = h;
+        if (hi != nullptr) hi[j] = h;
         lo[j] = __uint_as_float(__float_as_uint(v - h) & 0xFFFFE000u);
       }
     }
@@ -635,8 +803,11 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
 extern "C" {
 
 int pase_split_tf32(const float* x, float* hi, float* lo, long n, void* stream) {
-  PASE_CHECK_ARG(x && hi && lo && n > 0, "pase_split_tf32: bad args");
-  PASE_CHECK_ARG(aligned16(x) && aligned16(hi) && aligned16(lo), "pase_split_tf32: alignment");
+  // hi may be NULL: kind::tf32 ignores the low 13 mantissa bits of its fp32 operands
+  // (verified on B200, tools/tf32_probe.py), so the original array serves as "hi".
+  PASE_CHECK_ARG(x && lo && n > 0, "pase_split_tf32: bad args");
+  PASE_CHECK_ARG(aligned16(x) && aligned16(lo) && (hi == nullptr || aligned16(hi)),
+                 "pase_split_tf32: alignment");
   long blocks = (n / 4 + 255) / 256;
   long cap = (long)pase_num_sms() * 16;
   if (blocks > cap) blocks = cap;
@@ -660,7 +831,11 @@ int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, cons
   PASE_CHECK_ARG(rows_in > 0 && rows_out > 0 && fold > 0 && (N % fold) == 0,
                  "pase_tc_gemm_nt: bad row map");
   PASE_CHECK_ARG((colsum == nullptr) == (colsumsq == nullptr), "pase_tc_gemm_nt: stats pair");
-  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  PASE_CHECK_ARG(colsum == nullptr || N <= 2048, "pase_tc_gemm_nt: stats need N <= 2048");
+  PASE_CHECK_ARG(colsum == nullptr || !accumulate, "pase_tc_gemm_nt: stats + accumulate");
+  const int BN = N <= 64 ? 64 : 128;
+  // 3xTF32: fold the TMEM accumulator into fp32 register sums every 4 k-blocks (K = 128)
+  const int flush_kb = (mode == 1) ? 4 : 0;
   CUtensorMap ah, al, bh, bl;
   uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
   uint64_t astr[1] = {(uint64_t)R * 4};
@@ -682,12 +857,11 @@ int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, cons
   cudaStream_t st = (cudaStream_t)stream;
 #define PASE_NT(BNV)                                                                             \
   (mode == 1 ? launch_nt<BNV, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, colsum, \
-                                    colsumsq, accumulate, st)                                    \
+                                    colsumsq, accumulate, flush_kb, st)                          \
              : launch_nt<BNV, false>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,        \
-                                     colsum, colsumsq, accumulate, st))
+                                     colsum, colsumsq, accumulate, flush_kb, st))
   if (BN == 64) return PASE_NT(64);
-  if (BN == 128) return PASE_NT(128);
-  return PASE_NT(256);
+  return PASE_NT(128);
 #undef PASE_NT
 }
 
@@ -712,7 +886,8 @@ int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, in
       return (int)e;
     }
   }
-  const int BN = J <= 64 ? 64 : (J <= 128 ? 128 : 256);
+  const int BN = J <= 64 ? 64 : 128;
+  const int flush_ch = (mode == 1) ? 4 : 0;      // fold TMEM into fp32 sums every 128 rows
   CUtensorMap ah, al, bh, bl;
   uint64_t adims[3] = {(uint64_t)I, (uint64_t)rows_per_group, (uint64_t)groups};
   uint64_t astr[2] = {(uint64_t)lda * 4, (uint64_t)pitchA * lda * 4};
@@ -738,12 +913,11 @@ int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, in
   }
 #define PASE_TN(BNV)                                                                            \
   (mode == 1 ? launch_tn<BNV, true>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,    \
-                                    alpha, st)                                                  \
+                                    alpha, flush_ch, st)                                        \
              : launch_tn<BNV, false>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,   \
-                                     alpha, st))
+                                     alpha, flush_ch, st))
   if (BN == 64) return PASE_TN(64);
-  if (BN == 128) return PASE_TN(128);
-  return PASE_TN(256);
+  return PASE_TN(128);
 #undef PASE_TN
 }
 

@@ -201,18 +201,20 @@ class EncoderPlan(object):
 
     # -- GEMM dispatch: fp32 FFMA kernels or tcgen05 tensor-core kernels -------------
     def split(self, name, buf, fresh=True):
-        """mode 1 (3xTF32): exactly-representable tf32 hi/lo parts of an operand, kept in
-        twin buffers; `fresh=False` reuses the split made earlier in the same step."""
+        """mode 1 (3xTF32): (hi, lo) parts of an operand.  kind::tf32 reads only the upper 19
+        bits of an fp32 operand, so the operand itself is "hi"; only the residual
+        lo = tf32(x - tf32(x)) needs a twin buffer.  `fresh=False` reuses the residual
+        computed earlier in the same step."""
         if self.mode != 1:
             return buf, None
-        tw = self._twins.get(name)
-        if tw is None or tw[0].numel() != buf.numel():
-            tw = (torch.empty_like(buf), torch.empty_like(buf))
-            self._twins[name] = tw
+        lo = self._twins.get(name)
+        if lo is None or lo.numel() != buf.numel():
+            lo = torch.empty_like(buf)
+            self._twins[name] = lo
             fresh = True
         if fresh:
-            ops.call("pase_split_tf32", buf, tw[0], tw[1], buf.numel())
-        return tw
+            ops.call("pase_split_tf32", buf, None, lo, buf.numel())
+        return buf, lo
 
     def nt(self, an, A, lda, afresh, bn, B, ldb, bfresh, C, ldc, M, N, K, alpha, bias,
            rows_in, t_valid, rows_out, fold, cs, cq, acc):

@@ -403,7 +403,8 @@ def _tf32_trunc(x):
 
 def pase_split_tf32(x, hi, lo, n):
     h = _tf32_trunc(x[:n])
-    hi[:n] = h
+    if hi is not None:
+        hi[:n] = h
     lo[:n] = _tf32_trunc(x[:n] - h)
 
 
@@ -412,26 +413,27 @@ def pase_tc_gemm_nt(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, C, ldc, M, N, K, alpha, 
     need = M * R + K
     A = torch.zeros(need)
     lim = min(a_rows * R, Ahi.numel(), need)         # TMA zero-fills rows >= a_rows
-    A[:lim] = Ahi[:lim]
+    # the tensor core reads only the upper 19 bits of each fp32 operand (truncation)
+    A[:lim] = _tf32_trunc(Ahi[:lim])
     if mode == 1:
-        A[:lim] += Alo[:lim]
-    B = Bhi[:N * ldb].clone()
+        A[:lim] += _tf32_trunc(Alo[:lim])
+    B = _tf32_trunc(Bhi[:N * ldb])
     if mode == 1:
-        B += Blo[:N * ldb]
+        B += _tf32_trunc(Blo[:N * ldb])
     pase_gemm_nt(A, R, B, ldb, C, ldc, M, N, K, alpha, bias, rows_in, t_valid, rows_out, fold,
                  colsum, colsumsq, accumulate)
 
 
 def pase_tc_gemm_tn(Ahi, Alo, lda, pitchA, offA, Bhi, Blo, R, pitchB, b_rows_total, C, ldc, I, J,
                     groups, rows_per_group, alpha, accumulate, mode):
-    A = Ahi.clone()
+    A = _tf32_trunc(Ahi)
     if mode == 1:
-        A = A + Alo
+        A = A + _tf32_trunc(Alo)
     needB = ((groups - 1) * pitchB + rows_per_group) * R + J
     B = torch.zeros(max(needB, Bhi.numel()))
     lim = min(b_rows_total * R, Bhi.numel())
-    B[:lim] = Bhi[:lim]
+    B[:lim] = _tf32_trunc(Bhi[:lim])
     if mode == 1:
-        B[:lim] += Blo[:lim]
+        B[:lim] += _tf32_trunc(Blo[:lim])
     pase_gemm_tn(A, lda, pitchA, offA, B, R, pitchB, 0, C, ldc, I, J, groups, rows_per_group,
                  alpha, accumulate)

@@ -10,19 +10,24 @@ from test_kernels_gpu import R
 pytestmark = pytest.mark.gpu
 
 
-def _split(x):
+def _split(x, keep_raw_hi=True):
+    """(hi, lo).  keep_raw_hi: pass the raw fp32 array as 'hi' like the product does (the
+    tensor core truncates it); otherwise the explicitly truncated copy."""
     hi = torch.zeros_like(x)
     lo = torch.zeros_like(x)
     emul_ops.pase_split_tf32(x, hi, lo, x.numel())
-    return hi, lo
+    return (x.clone() if keep_raw_hi else hi), lo
 
 
 def test_split_kernel_bit_exact():
     x = R(100003, seed=1) * 37.0
-    hi, lo = _split(x)
+    hi, lo = _split(x, keep_raw_hi=False)
     dh, dl = torch.zeros_like(x).cuda(), torch.zeros_like(x).cuda()
     _lib.call("pase_split_tf32", x.cuda(), dh, dl, x.numel())
     assert torch.equal(dh.cpu(), hi) and torch.equal(dl.cpu(), lo)
+    dl2 = torch.zeros_like(x).cuda()
+    _lib.call("pase_split_tf32", x.cuda(), None, dl2, x.numel())       # hi omitted
+    assert torch.equal(dl2.cpu(), lo)
     assert float((x - hi - lo).abs().max()) <= float(x.abs().max()) * 2.0 ** -21
 
 
@@ -61,7 +66,7 @@ def test_tc_gemm_nt(M, N, K, Rr, rows_in, t_valid, rows_out, fold, bias, stats, 
     _lib.call("pase_tc_gemm_nt", *dev)
     torch.cuda.synchronize()
     scale = float((A.abs().mean() * B.abs().mean() * K ** 0.5))
-    tol = (3e-5 if mode == 1 else 4e-3) * max(scale, 1e-3) * 8
+    tol = (2e-6 if mode == 1 else 2e-5) * max(scale, 1e-3) * 8
     out_c, out_d = cpu[7], dev[7].cpu()
     err = float((out_c - out_d).abs().max())
     assert err <= tol, "C max err %.3e > %.3e (mode %d)" % (err, tol, mode)
@@ -69,7 +74,7 @@ def test_tc_gemm_nt(M, N, K, Rr, rows_in, t_valid, rows_out, fold, bias, stats, 
         for i in (18, 19):
             c, d = cpu[i].float(), dev[i].cpu().float()
             e = float((c - d).abs().max())
-            lim = (2e-4 if mode == 1 else 2e-2) * max(float(c.abs().max()), 1.0)
+            lim = (2e-5 if mode == 1 else 2e-4) * max(float(c.abs().max()), 1.0)
             assert e <= lim, "stats arg %d err %.3e > %.3e" % (i, e, lim)
 
 
@@ -104,6 +109,6 @@ def test_tc_gemm_tn(I, J, groups, rpg, lda, pitchA, offA, Rr, pitchB, acc, mode)
     torch.cuda.synchronize()
     out_c, out_d = cpu[10], dev[10].cpu()
     scale = float(out_c.abs().max())
-    tol = (2e-5 if mode == 1 else 3e-3) * max(scale, 1.0)
+    tol = (4e-6 if mode == 1 else 4e-5) * max(scale, 1.0)
     err = float((out_c - out_d).abs().max())
     assert err <= tol, "C max err %.3e > %.3e (mode %d)" % (err, tol, mode)
