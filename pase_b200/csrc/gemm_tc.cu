@@ -84,6 +84,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -497,7 +505,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
                   int R, float* __restrict__ C, long ldc, int I, int J, int groups,
                   int rows_per_group, float alpha, int chunks_per_split, int flush_ch,
-                  int stages) {
+                  int stages, int b_blocked) {
   using Cfg = TNCfg<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -561,18 +569,24 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         uint8_t* b_hi = st + Cfg::A_BYTES;
         uint8_t* a_lo = b_hi + Cfg::B_BYTES;
         uint8_t* b_lo = a_lo + Cfg::A_BYTES;
+        // A: one 4-D box = (32 floats, 32 rows, BM/32 column blocks, 1 group) lands as
+        // BM/32 consecutive [32 rows x 128 B] MN-blocks
+        tma_load_4d(a_hi, &mAhi, &full_bar[s], 0, u0, i0 / 32, g);
+        if (SPLIT) tma_load_4d(a_lo, &mAlo, &full_bar[s], 0, u0, i0 / 32, g);
+        if (b_blocked) {
+          // the BN columns of this tile lie inside one folded row (R % BN == 0)
+          tma_load_4d(b_hi, &mBhi, &full_bar[s], 0, u0 + jq, jc / 32, g);
+          if (SPLIT) tma_load_4d(b_lo, &mBlo, &full_bar[s], 0, u0 + jq, jc / 32, g);
+        } else {
 #pragma unroll
-        for (int mb = 0; mb < BM / 32; ++mb) {
-          tma_load_3d(a_hi + mb * TN_KR * 128, &mAhi, &full_bar[s], i0 + mb * 32, u0, g);
-          if (SPLIT) tma_load_3d(a_lo + mb * TN_KR * 128, &mAlo, &full_bar[s], i0 + mb * 32, u0, g);
-        }
-#pragma unroll
-        for (int nb = 0; nb < BN / 32; ++nb) {
-          // 32 consecutive columns never straddle a folded row (R % 32 == 0)
-          const int col = jc + nb * 32;
-          const int qq = jq + col / R, cc = col % R;
-          tma_load_3d(b_hi + nb * TN_KR * 128, &mBhi, &full_bar[s], cc, u0 + qq, g);
-          if (SPLIT) tma_load_3d(b_lo + nb * TN_KR * 128, &mBlo, &full_bar[s], cc, u0 + qq, g);
+          for (int nb = 0; nb < BN / 32; ++nb) {
+            // 32 consecutive columns never straddle a folded row (R % 32 == 0)
+            const int col = jc + nb * 32;
+            const int qq = jq + col / R, cc = col % R;
+            tma_load_4d(b_hi + nb * TN_KR * 128, &mBhi, &full_bar[s], 0, u0 + qq, cc / 32, g);
+            if (SPLIT)
+              tma_load_4d(b_lo + nb * TN_KR * 128, &mBlo, &full_bar[s], 0, u0 + qq, cc / 32, g);
+          }
         }
       }
     }
@@ -684,7 +698,7 @@ int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims
     pase_set_error("pase tc gemm: cuTensorMapEncodeTiled not available");
     return PASE_ERR_UNSUPPORTED;
   }
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base,
                    (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes,
                    (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -738,7 +752,7 @@ int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
 template <int BN, bool SPLIT>
 int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
               const CUtensorMap& bl, int R, float* C, long ldc, int I, int J, int groups,
-              int rows_per_group, float alpha, int flush_ch, cudaStream_t st) {
+              int rows_per_group, float alpha, int flush_ch, int b_blocked, cudaStream_t st) {
   using Cfg = TNCfg<BN, SPLIT>;
   static bool attr = false;
   const int stages = pick_stages(Cfg::STAGE_BYTES, 0);
@@ -763,36 +777,48 @@ int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   dim3 grid(tj, ti, (unsigned)splits);
   tc_gemm_tn_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, R, C, ldc, I, J, groups,
                                                             rows_per_group, alpha, (int)cps,
-                                                            flush_ch, stages);
+                                                            flush_ch, stages, b_blocked);
   PASE_LAUNCH_CHECK("pase_tc_gemm_tn");
   return PASE_OK;
 }
 
-// split kernel: hi = tf32-truncated value (low 13 mantissa bits cleared), lo = tf32(x - hi)
+// tf32 helpers: the tensor core reads the upper 19 bits of an fp32 operand (truncation).
+__device__ __forceinline__ float tf32_trunc(float v) {
+  return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float tf32_rn(float v) {          // round to nearest even
+  uint32_t u = __float_as_uint(v);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+// split kernel.
+//   hi == nullptr (activations): the operand itself is "hi" (hardware truncation), and
+//        lo = rn(x - trunc(x));
+//   hi != nullptr (weights): hi = rn(x), lo = rn(x - hi): explicit, exactly representable,
+//        zero-mean residuals, so the dropped lo*lo / residual terms carry no coherent bias.
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                   float* __restrict__ lo, long n) {
   const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const long stride = (long)gridDim.x * blockDim.x * 4;
+  const bool explicit_hi = hi != nullptr;
   for (long i = i4; i < n; i += stride) {
     if (i + 3 < n) {
       const float4 v = *reinterpret_cast<const float4*>(x + i);
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-      l.x = __uint_as_float(__float_as_uint(v.x - h.x) & 0xFFFFE000u);
-      l.y = __uint_as_float(__float_as_uint(v.y - h.y) & 0xFFFFE000u);
-      l.z = __uint_as_float(__float_as_uint(v.z - h.z) & 0xFFFFE000u);
-      l.w = __uint_as_float(__float_as_uint(v.w - h.w) & 0xFFFFE000u);
-      if (hi != nullptr) *reinterpret_cast<float4*>(hi + i) = h;
-      *reinterpret_cast<float4*>(lo + i) = l;
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      float h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        h[k] = explicit_hi ? tf32_rn(vv[k]) : tf32_trunc(vv[k]);
+        l[k] = tf32_rn(vv[k] - h[k]);
+      }
+      if (explicit_hi) *reinterpret_cast<float4*>(hi + i) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(lo + i) = make_float4(l[0], l[1], l[2], l[3]);
     } else {
       for (long j = i; j < n; ++j) {
         const float v = x[j];
-        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        if (hi != nullptr) hi[j] = h;
-        lo[j] = __uint_as_float(__float_as_uint(v - h) & 0xFFFFE000u);
+        const float h = explicit_hi ? tf32_rn(v) : tf32_trunc(v);
+        if (explicit_hi) hi[j] = h;
+        lo[j] = tf32_rn(v - h);
       }
     }
   }
@@ -889,33 +915,39 @@ int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, in
   const int BN = J <= 64 ? 64 : 128;
   const int flush_ch = (mode == 1) ? 4 : 0;      // fold TMEM into fp32 sums every 128 rows
   CUtensorMap ah, al, bh, bl;
-  uint64_t adims[3] = {(uint64_t)I, (uint64_t)rows_per_group, (uint64_t)groups};
-  uint64_t astr[2] = {(uint64_t)lda * 4, (uint64_t)pitchA * lda * 4};
-  uint32_t abox[3] = {32, TN_KR, 1};
+  // A as (32 floats, rows-in-group, column blocks of 32, groups): the block dimension has the
+  // smallest stride after the inner one, so one box brings BM/32 MN-blocks of [32 rows x 128 B]
+  uint64_t adims[4] = {32, (uint64_t)rows_per_group, (uint64_t)((I + 31) / 32), (uint64_t)groups};
+  uint64_t astr[3] = {(uint64_t)lda * 4, 128, (uint64_t)pitchA * lda * 4};
+  uint32_t abox[4] = {32, TN_KR, (uint32_t)(BM / 32), 1};
   // B group g covers folded rows [g*pitchB, ...): rows beyond the allocation are zero-filled
   long rows_in_group = b_rows_total - (long)(groups - 1) * pitchB;
   if (rows_in_group > pitchB + (J + R - 1) / R + 1) rows_in_group = pitchB + (J + R - 1) / R + 1;
-  uint64_t bdims[3] = {(uint64_t)R, (uint64_t)rows_in_group, (uint64_t)groups};
-  uint64_t bstr[2] = {(uint64_t)R * 4, (uint64_t)pitchB * R * 4};
-  uint32_t bbox[3] = {32, TN_KR, 1};
+  const int b_blocked = (R % BN) == 0;
+  uint64_t bdims[4] = {32, (uint64_t)rows_in_group, (uint64_t)(R / 32), (uint64_t)groups};
+  uint64_t bstr[3] = {(uint64_t)R * 4, 128, (uint64_t)pitchB * R * 4};
+  uint32_t bbox[4] = {32, TN_KR, (uint32_t)(b_blocked ? BN / 32 : 1), 1};
+  // NOTE: when I % 32 != 0 the last A column block reads up to 31 floats past a row's I
+  // columns (they only feed output rows >= I, which are never stored); the caller must
+  // keep 32 floats of slack after the last row of A.
   int rc;
   const CUtensorMapSwizzle sw32 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if ((rc = make_map(&ah, Ahi + (long)offA * lda, 3, adims, astr, abox, "tn A.hi", sw32)) != 0)
+  if ((rc = make_map(&ah, Ahi + (long)offA * lda, 4, adims, astr, abox, "tn A.hi", sw32)) != 0)
     return rc;
-  if ((rc = make_map(&bh, Bhi, 3, bdims, bstr, bbox, "tn B.hi", sw32)) != 0) return rc;
+  if ((rc = make_map(&bh, Bhi, 4, bdims, bstr, bbox, "tn B.hi", sw32)) != 0) return rc;
   if (mode == 1) {
-    if ((rc = make_map(&al, Alo + (long)offA * lda, 3, adims, astr, abox, "tn A.lo", sw32)) != 0)
+    if ((rc = make_map(&al, Alo + (long)offA * lda, 4, adims, astr, abox, "tn A.lo", sw32)) != 0)
       return rc;
-    if ((rc = make_map(&bl, Blo, 3, bdims, bstr, bbox, "tn B.lo", sw32)) != 0) return rc;
+    if ((rc = make_map(&bl, Blo, 4, bdims, bstr, bbox, "tn B.lo", sw32)) != 0) return rc;
   } else {
     al = ah;
     bl = bh;
   }
 #define PASE_TN(BNV)                                                                            \
   (mode == 1 ? launch_tn<BNV, true>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,    \
-                                    alpha, flush_ch, st)                                        \
+                                    alpha, flush_ch, b_blocked, st)                             \
              : launch_tn<BNV, false>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,   \
-                                     alpha, flush_ch, st))
+                                     alpha, flush_ch, b_blocked, st))
   if (BN == 64) return PASE_TN(64);
   return PASE_TN(128);
 #undef PASE_TN

@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int UNROLL = 4;
+constexpr int UNROLL = 8;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -58,21 +58,43 @@ qrnn_scan_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ Cst,
   const float* dhp = dh + (long)n * T * lddh + c;
   float* dy = dY + (long)n * T * 3 * H + c;
   float carry = 0.f;
-  for (int t = T - 1; t >= 0; --t) {
+  int t = T - 1;
+  // the loads do not depend on the recurrence: issue UNROLL time steps of them up front
+  for (; t - (UNROLL - 1) >= 0; t -= UNROLL) {
+    float z[UNROLL], f[UNROLL], o[UNROLL], c[UNROLL], cm[UNROLL], g[UNROLL];
+#pragma unroll
+    for (int i = 0; i < UNROLL; ++i) {
+      const int tt = t - i;
+      const float* yr = y + (long)tt * 3 * H;
+      z[i] = yr[0]; f[i] = yr[H]; o[i] = yr[2 * H];
+      c[i] = cp[(long)tt * H];
+      cm[i] = tt > 0 ? cp[(long)(tt - 1) * H] : 0.f;
+      g[i] = dhp[(long)tt * lddh];
+    }
+#pragma unroll
+    for (int i = 0; i < UNROLL; ++i) {
+      const int tt = t - i;
+      const float zz = tanhf(z[i]), ff = sigmoidf_(f[i]), oo = sigmoidf_(o[i]);
+      const float dc = g[i] * oo + carry;
+      carry = dc * (1.f - ff);
+      float* dr = dy + (long)tt * 3 * H;
+      dr[0] = dc * ff * (1.f - zz * zz);
+      dr[H] = dc * (zz - cm[i]) * ff * (1.f - ff);
+      dr[2 * H] = g[i] * c[i] * oo * (1.f - oo);
+    }
+  }
+  for (; t >= 0; --t) {
     const float* yr = y + (long)t * 3 * H;
     const float zz = tanhf(yr[0]), ff = sigmoidf_(yr[H]), oo = sigmoidf_(yr[2 * H]);
     const float ct = cp[(long)t * H];
     const float cm1 = t > 0 ? cp[(long)(t - 1) * H] : 0.f;
     const float g = dhp[(long)t * lddh];
     const float dc = g * oo + carry;
-    const float d_o = g * ct;
-    const float d_f = dc * (zz - cm1);
-    const float d_z = dc * ff;
     carry = dc * (1.f - ff);
     float* dr = dy + (long)t * 3 * H;
-    dr[0] = d_z * (1.f - zz * zz);
-    dr[H] = d_f * ff * (1.f - ff);
-    dr[2 * H] = d_o * oo * (1.f - oo);
+    dr[0] = dc * ff * (1.f - zz * zz);
+    dr[H] = dc * (zz - cm1) * ff * (1.f - ff);
+    dr[2 * H] = g * ct * oo * (1.f - oo);
   }
 }
 

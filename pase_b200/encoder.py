@@ -169,7 +169,7 @@ class EncoderPlan(object):
         self.WcatT = e(self.Kc * self.emb)
         self.dWcat = e(self.emb * self.Kc)
         self.yout = e(rows * self.emb)
-        self.g = e(rows * self.emb)
+        self.g = torch.zeros(rows * self.emb + 64, **f32)     # +slack: TC wgrad reads 32-col blocks
         self.bn_out = torch.zeros(4, self.emb, **f32)
         self.bn_out[1].fill_(1.0)
         self.bn_out[2].fill_(1.0)
@@ -200,21 +200,23 @@ class EncoderPlan(object):
         self.generation = 0
 
     # -- GEMM dispatch: fp32 FFMA kernels or tcgen05 tensor-core kernels -------------
-    def split(self, name, buf, fresh=True):
-        """mode 1 (3xTF32): (hi, lo) parts of an operand.  kind::tf32 reads only the upper 19
-        bits of an fp32 operand, so the operand itself is "hi"; only the residual
-        lo = tf32(x - tf32(x)) needs a twin buffer.  `fresh=False` reuses the residual
-        computed earlier in the same step."""
+    def split(self, name, buf, fresh=True, weights=False):
+        """mode 1 (3xTF32): (hi, lo) parts of an operand.
+        Activations: kind::tf32 reads only the upper 19 bits of an fp32 operand, so the
+        operand itself is "hi" and only lo = rn(x - trunc(x)) needs a twin buffer.
+        Weights (small): explicit hi = rn(x), lo = rn(x - hi), so that the dropped lo*lo and
+        residual terms have random sign (no coherent bias in strongly cancelling sums).
+        `fresh=False` reuses the split computed earlier in the same step."""
         if self.mode != 1:
             return buf, None
-        lo = self._twins.get(name)
-        if lo is None or lo.numel() != buf.numel():
-            lo = torch.empty_like(buf)
-            self._twins[name] = lo
+        tw = self._twins.get(name)
+        if tw is None or tw[1].numel() != buf.numel():
+            tw = (torch.empty_like(buf) if weights else None, torch.empty_like(buf))
+            self._twins[name] = tw
             fresh = True
         if fresh:
-            ops.call("pase_split_tf32", buf, None, lo, buf.numel())
-        return buf, lo
+            ops.call("pase_split_tf32", buf, tw[0], tw[1], buf.numel())
+        return (tw[0] if weights else buf), tw[1]
 
     def nt(self, an, A, lda, afresh, bn, B, ldb, bfresh, C, ldc, M, N, K, alpha, bias,
            rows_in, t_valid, rows_out, fold, cs, cq, acc):
@@ -222,7 +224,7 @@ class EncoderPlan(object):
             return ops.call("pase_gemm_nt", A, lda, B, ldb, C, ldc, M, N, K, alpha, bias,
                             rows_in, t_valid, rows_out, fold, cs, cq, acc)
         Ah, Al = self.split(an, A, afresh)
-        Bh, Bl = self.split(bn, B, bfresh)
+        Bh, Bl = self.split(bn, B, bfresh, weights=True)
         return ops.call("pase_tc_gemm_nt", Ah, Al, A.numel() // lda, lda, Bh, Bl, ldb, C, ldc,
                         M, N, K, alpha, bias, rows_in, t_valid, rows_out, fold, cs, cq, acc,
                         self.mode)

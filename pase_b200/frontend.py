@@ -19,7 +19,11 @@ import torch.nn as nn
 from .modules import Model, format_frontend_chunk, format_frontend_output
 from . import encoder as _enc
 
-DEFAULT_PRECISION = "fp32"
+# "3xtf32": tcgen05 tensor cores with error-compensated TF32 (fp32-equivalent, meets the
+# fp32 parity bar); "fp32": FFMA kernels; "tf32": single-pass TF32 (L2-equivalent only).
+# Shapes the tensor-core kernels cannot take (channel counts not multiples of 32) fall back
+# to the FFMA kernels per GEMM -- still on the GPU, never to a CPU path.
+DEFAULT_PRECISION = "3xtf32"
 
 _DEFAULTS = dict(
     num_inputs=1, sincnet=True,

@@ -401,11 +401,22 @@ def _tf32_trunc(x):
     return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
 
 
+def _tf32_rn(x):
+    u = x.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    u = (u + 0xFFF + ((u >> 13) & 1)) & 0xFFFFE000
+    u = torch.where(u >= 2 ** 31, u - 2 ** 32, u)
+    return u.to(torch.int32).view(torch.float32)
+
+
 def pase_split_tf32(x, hi, lo, n):
-    h = _tf32_trunc(x[:n])
+    """hi None (activations): lo = rn(x - trunc(x)); hi given (weights): hi = rn(x),
+    lo = rn(x - hi)."""
     if hi is not None:
+        h = _tf32_rn(x[:n])
         hi[:n] = h
-    lo[:n] = _tf32_trunc(x[:n] - h)
+    else:
+        h = _tf32_trunc(x[:n])
+    lo[:n] = _tf32_rn(x[:n] - h)
 
 
 def pase_tc_gemm_nt(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, C, ldc, M, N, K, alpha, bias, rows_in,

@@ -10,25 +10,31 @@ from test_kernels_gpu import R
 pytestmark = pytest.mark.gpu
 
 
-def _split(x, keep_raw_hi=True):
-    """(hi, lo).  keep_raw_hi: pass the raw fp32 array as 'hi' like the product does (the
-    tensor core truncates it); otherwise the explicitly truncated copy."""
-    hi = torch.zeros_like(x)
+def _split(x, weights=False):
+    """(hi, lo) as the product builds them: activations pass the raw array as 'hi' (the
+    tensor core truncates it) with lo = rn(x - trunc(x)); weights get explicit rn hi/lo."""
     lo = torch.zeros_like(x)
-    emul_ops.pase_split_tf32(x, hi, lo, x.numel())
-    return (x.clone() if keep_raw_hi else hi), lo
+    if weights:
+        hi = torch.zeros_like(x)
+        emul_ops.pase_split_tf32(x, hi, lo, x.numel())
+        return hi, lo
+    emul_ops.pase_split_tf32(x, None, lo, x.numel())
+    return x.clone(), lo
 
 
 def test_split_kernel_bit_exact():
     x = R(100003, seed=1) * 37.0
-    hi, lo = _split(x, keep_raw_hi=False)
+    hi, lo = _split(x, weights=True)
     dh, dl = torch.zeros_like(x).cuda(), torch.zeros_like(x).cuda()
     _lib.call("pase_split_tf32", x.cuda(), dh, dl, x.numel())
     assert torch.equal(dh.cpu(), hi) and torch.equal(dl.cpu(), lo)
+    assert float((x - hi - lo).abs().max()) <= float(x.abs().max()) * 2.0 ** -22
+    _, lo_a = _split(x)
     dl2 = torch.zeros_like(x).cuda()
-    _lib.call("pase_split_tf32", x.cuda(), None, dl2, x.numel())       # hi omitted
-    assert torch.equal(dl2.cpu(), lo)
-    assert float((x - hi - lo).abs().max()) <= float(x.abs().max()) * 2.0 ** -21
+    _lib.call("pase_split_tf32", x.cuda(), None, dl2, x.numel())       # activation form
+    assert torch.equal(dl2.cpu(), lo_a)
+    xt = emul_ops._tf32_trunc(x)
+    assert float((x - xt - lo_a).abs().max()) <= float(x.abs().max()) * 2.0 ** -21
 
 
 NT_CASES = [
@@ -55,7 +61,7 @@ def test_tc_gemm_nt(M, N, K, Rr, rows_in, t_valid, rows_out, fold, bias, stats, 
     cs = torch.zeros(N, dtype=torch.float64) if stats else None
     cq = torch.zeros(N, dtype=torch.float64) if stats else None
     if mode == 1:
-        (Ah, Al), (Bh, Bl) = _split(A), _split(B)
+        (Ah, Al), (Bh, Bl) = _split(A), _split(B, weights=True)
     else:
         Ah, Al, Bh, Bl = A, None, B, None
     args = [Ah, Al, a_rows, Rr, Bh, Bl, K, C, N, M, N, K, 0.5, bs, rows_in, t_valid, rows_out,
