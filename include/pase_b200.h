@@ -139,7 +139,9 @@ int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, in
                           float* dst, long dst_sample_stride, long dst_row_stride,
                           int padL, int padR,
                           float* pool, long pool_sample_stride, long pool_row_stride,
-                          int pool_d, int pool_T, void* stream);
+                          int pool_d, int pool_T,
+                          float* dst_lo /* optional: tf32 residual of dst, same layout */,
+                          void* stream);
 /* backward, pass 1: g = sum of gradient sources; du = PReLU'(u) g written to
  * dst; accumulates S1=sum du, S2=sum du*xhat, dalpha (double[C] each). */
 int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T, int C,
@@ -159,7 +161,8 @@ int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, 
                             const float* mean, const float* invstd, const float* gamma,
                             const double* S1, const double* S2, double count,
                             float* dst, long dst_sample_stride,
-                            double* dbias_acc, void* stream);
+                            double* dbias_acc,
+                            float* dst_lo /* optional: tf32 residual of dst */, void* stream);
 /* plain per-channel PReLU on (rows,C) (MLPBlock / GDeconv1DBlock act) */
 int pase_prelu_fwd(const float* u, float* h, const float* alpha, long rows, int C,
                    long ldu, long ldh, void* stream);

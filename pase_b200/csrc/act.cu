@@ -62,13 +62,20 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ rm, const float*
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float prelu1(float u, float a) { return u > 0.f ? u : a * u; }
+// lo = rn_tf32(x - trunc_tf32(x)): the part of x the tensor core drops when it reads x as tf32
+__device__ __forceinline__ float tf32_residual(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  uint32_t u = __float_as_uint(r);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
 
 __global__ void __launch_bounds__(THREADS)
 bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ alpha, float* __restrict__ dst, long d_ss,
                         long d_rs, int padL, int Tp, float* __restrict__ pool, long p_ss,
-                        long p_rs, int pool_d, int pool_T) {
+                        long p_rs, int pool_d, int pool_T, float* __restrict__ dst_lo) {
   const int C4 = C >> 2;
   const int n = blockIdx.y;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,6 +118,10 @@ bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
     a.z = prelu1(fmaf(v.z, sc.z, sh.z), al.z);
     a.w = prelu1(fmaf(v.w, sc.w, sh.w), al.w);
     st4(dn + tau * d_rs + c, a);
+    if (dst_lo != nullptr)      // 3xTF32 residual of the operand just written (see gemm_tc.cu)
+      st4(dst_lo + (long)n * d_ss + tau * d_rs + c,
+          make_float4(tf32_residual(a.x), tf32_residual(a.y), tf32_residual(a.z),
+                      tf32_residual(a.w)));
     if (tr >= 0 && tr < pool_len) {
       const int w = tr / pool_d;
       if (w != pw) {
@@ -241,7 +252,8 @@ bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ gamma, const double* __restrict__ S1,
                           const double* __restrict__ S2, double inv_count,
-                          float* __restrict__ dst, long d_ss, double* __restrict__ dbias) {
+                          float* __restrict__ dst, long d_ss, double* __restrict__ dbias,
+                          float* __restrict__ dst_lo) {
   extern __shared__ float red[];      // [C]
   for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
@@ -287,6 +299,10 @@ bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
         acc[k] += o[k];
       }
       st4(dn + (long)t * C + c, make_float4(o[0], o[1], o[2], o[3]));
+      if (dst_lo != nullptr)
+        st4(dst_lo + (long)n * d_ss + (long)t * C + c,
+            make_float4(tf32_residual(o[0]), tf32_residual(o[1]), tf32_residual(o[2]),
+                        tf32_residual(o[3])));
     }
     if (dbias) {
 #pragma unroll
@@ -552,7 +568,7 @@ int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, in
                           const float* scale, const float* shift, const float* alpha, float* dst,
                           long dst_sample_stride, long dst_row_stride, int padL, int padR,
                           float* pool, long pool_sample_stride, long pool_row_stride, int pool_d,
-                          int pool_T, void* stream) {
+                          int pool_T, float* dst_lo, void* stream) {
   PASE_CHECK_ARG(y && dst && scale && shift && alpha, "pase_bn_prelu_pad_fwd: null pointer");
   PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0,
                  "pase_bn_prelu_pad_fwd: C=%d must be a positive multiple of 4", C);
@@ -568,7 +584,7 @@ int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, in
   dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
   bn_prelu_pad_fwd_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(
       y, y_sample_stride, T, C, scale, shift, alpha, dst, dst_sample_stride, dst_row_stride, padL,
-      Tp, pool, pool_sample_stride, pool_row_stride, pool_d, pool_T);
+      Tp, pool, pool_sample_stride, pool_row_stride, pool_d, pool_T, dst_lo);
   PASE_LAUNCH_CHECK("pase_bn_prelu_pad_fwd");
   return PASE_OK;
 }
@@ -600,7 +616,8 @@ int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T,
 int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, int C,
                             const float* mean, const float* invstd, const float* gamma,
                             const double* S1, const double* S2, double count, float* dst,
-                            long dst_sample_stride, double* dbias_acc, void* stream) {
+                            long dst_sample_stride, double* dbias_acc, float* dst_lo,
+                            void* stream) {
   PASE_CHECK_ARG(y && mean && invstd && S1 && S2 && dst, "pase_bn_prelu_bwd_apply: null pointer");
   PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 8192,
                  "pase_bn_prelu_bwd_apply: bad C=%d", C);
@@ -608,7 +625,7 @@ int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, 
   dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
   bn_prelu_bwd_apply_kernel<<<grid, THREADS, C * sizeof(float), (cudaStream_t)stream>>>(
       y, y_sample_stride, T, C, mean, invstd, gamma, S1, S2, 1.0 / count, dst, dst_sample_stride,
-      dbias_acc);
+      dbias_acc, dst_lo);
   PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_apply");
   return PASE_OK;
 }

@@ -769,9 +769,23 @@ int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   const int ti = (I + BM - 1) / BM, tj = (J + BN - 1) / BN;
   const int cpg = (rows_per_group + TN_KR - 1) / TN_KR;
   const long total = (long)groups * cpg;
-  long splits = (2L * pase_num_sms() + (long)ti * tj - 1) / ((long)ti * tj);
-  if (splits > total) splits = total;
-  if (splits < 1) splits = 1;
+  // split the reduction so that the CTA count fills whole waves of the SMs (one CTA per SM):
+  // among 1..4 waves pick the split with the best fill, keeping chains >= 8 chunks
+  const long tiles = (long)ti * tj;
+  const int sms = pase_num_sms();
+  long best = 1;
+  double best_eff = -1.0;
+  for (long sp = 1; sp <= total && sp * tiles <= 4L * sms; ++sp) {
+    const long cps_try = (total + sp - 1) / sp;
+    if (cps_try < 8 && sp > 1) break;
+    const long ctas = tiles * ((total + cps_try - 1) / cps_try);
+    const long waves = (ctas + sms - 1) / sms;
+    // time ~ waves * chunks-per-cta: lower is better
+    const double cost = (double)waves * (double)(cps_try + 6);
+    const double eff = 1.0 / cost;
+    if (eff > best_eff) { best_eff = eff; best = sp; }
+  }
+  long splits = best;
   long cps = (total + splits - 1) / splits;
   splits = (total + cps - 1) / cps;
   dim3 grid(tj, ti, (unsigned)splits);

@@ -81,7 +81,7 @@ class _DecoderStackFn(torch.autograd.Function):
             C = g.Cout
             call("pase_bn_prelu_pad_fwd", plan.yfull[i][g.pad * C:], g.U * g.s * C, B, g.L, C,
                  plan.ones[:C], plan.zeros[:C], alpha.reshape(-1), dst, d_ss, C, 0, 0,
-                 None, 0, 0, 0, 0)
+                 None, 0, 0, 0, 0, None)
         ctx.plan, ctx.generation = plan, plan.generation
         ctx.save_for_backward(*params)
         return out

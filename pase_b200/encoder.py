@@ -211,12 +211,23 @@ class EncoderPlan(object):
             return buf, None
         tw = self._twins.get(name)
         if tw is None or tw[1].numel() != buf.numel():
-            tw = (torch.empty_like(buf) if weights else None, torch.empty_like(buf))
+            tw = (torch.zeros_like(buf) if weights else None, torch.zeros_like(buf))
             self._twins[name] = tw
             fresh = True
         if fresh:
             ops.call("pase_split_tf32", buf, tw[0], tw[1], buf.numel())
         return (tw[0] if weights else buf), tw[1]
+
+    def lo_of(self, name, buf):
+        """Residual twin of an activation operand, for producers that write it themselves
+        (mode 1 only; zero-initialised so halos / slack stay valid)."""
+        if self.mode != 1:
+            return None
+        tw = self._twins.get(name)
+        if tw is None or tw[1].numel() != buf.numel():
+            tw = (None, torch.zeros_like(buf))
+            self._twins[name] = tw
+        return tw[1]
 
     def nt(self, an, A, lda, afresh, bn, B, ldb, bfresh, C, ldc, M, N, K, alpha, bias,
            rows_in, t_valid, rows_out, fold, cs, cq, acc):
@@ -307,7 +318,7 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
             cs, cq = plan.stats_f[o:o + g.Nn], plan.stats_f[o + g.Nn:o + 2 * g.Nn]
         else:
             cs = cq = None
-        plan.nt(("apad", l), plan.apad[l], g.lda, True, ("Wt", l), plan.Wt[l], g.K, True,
+        plan.nt(("apad", l), plan.apad[l], g.lda, l == 0, ("Wt", l), plan.Wt[l], g.K, True,
                 plan.y[l], g.Nn, N * g.P, g.Nn, g.K, 1.0, bias, g.P, g.T_out, g.rows_out,
                 g.fold, cs, cq, 0)
         mean, invstd, scale, shift = plan.bn[l][0], plan.bn[l][1], plan.bn[l][2], plan.bn[l][3]
@@ -322,11 +333,15 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
                  buf(pre + "norm.running_var"), P(pre + "norm.weight"), P(pre + "norm.bias"),
                  g.Cout, BN_EPS, mean, invstd, scale, shift)
         C = g.Cout
+        dst_lo = None            # 3xTF32: the producer also writes the operand's tf32 residual
         if l + 1 < plan.nblk:
             nx = G[l + 1]
             dst, d_ss, d_rs, pl, pr = plan.apad[l + 1], nx.apad_floats, C, nx.padL, nx.padR
+            dst_lo = plan.lo_of(("apad", l + 1), plan.apad[l + 1])
         elif plan.rnn:
             dst, d_ss, d_rs, pl, pr = plan.xq[C:], (Tq + 1) * C, C, 0, 0
+            lo = plan.lo_of("xq", plan.xq)
+            dst_lo = None if lo is None else lo[C:]
         else:
             dst, d_ss, d_rs, pl, pr = plan.cat, Tq * Kc, Kc, 0, 0
         if plan.skips and l + 1 < plan.nblk:
@@ -334,14 +349,14 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
         else:
             pool, pd = None, 0
         call("pase_bn_prelu_pad_fwd", plan.y[l], g.Ty * C, N, g.T_out, C, scale, shift,
-             P(pre + "act.weight"), dst, d_ss, d_rs, pl, pr, pool, Tq * Kc, Kc, pd, Tq)
+             P(pre + "act.weight"), dst, d_ss, d_rs, pl, pr, pool, Tq * Kc, Kc, pd, Tq, dst_lo)
 
     if plan.rnn:
         Cq, H = plan.Clast, plan.H
         Wl = params["rnn.layers.0.linear.weight"].detach()
         Wq = torch.cat([Wl[:, Cq:], Wl[:, :Cq]], 1).contiguous()      # [x_{t-1} | x_t] order
         plan.Wq = Wq
-        plan.nt("xq", plan.xq, Cq, True, "Wq", Wq.reshape(-1), 2 * Cq, True, plan.Yg, 3 * H,
+        plan.nt("xq", plan.xq, Cq, False, "Wq", Wq.reshape(-1), 2 * Cq, True, plan.Yg, 3 * H,
                 N * (Tq + 1), 3 * H, 2 * Cq, 1.0, P("rnn.layers.0.linear.bias"),
                 Tq + 1, Tq, Tq, 1, None, None, 0)
         call("pase_qrnn_scan_fwd", plan.Yg, plan.cat, Kc, plan.Cst, N, Tq, H)
@@ -465,11 +480,13 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
             a1, a2 = S1, S2
         else:
             a1, a2 = zeros[:C], zeros[C:2 * C]
+        lo = plan.lo_of(("dyz", l), plan.dyz[l])
+        dst_lo = None if lo is None else (lo if g.sinc else lo[(g.taps - 1) * C:])
         call("pase_bn_prelu_bwd_apply", plan.y[l], g.Ty * C, N, g.T_out, C, mean, invstd,
              P(pre + "norm.weight"), a1, a2, float(N * g.T_out), dst, d_ss,
-             None if g.sinc else dbi)
+             None if g.sinc else dbi, dst_lo)
         if g.sinc:
-            plan.tn(("dyz", l), plan.dyz[l], g.Nn, g.rows_out, 0, True, ("apad", l), plan.apad[l],
+            plan.tn(("dyz", l), plan.dyz[l], g.Nn, g.rows_out, 0, False, ("apad", l), plan.apad[l],
                     g.lda, g.P, False, plan.dWt[l], g.K, g.Nn, g.K, N, g.rows_out, 1.0, 0)
             dlow = torch.empty_like(params[pre + "conv.low_hz_"])
             dband = torch.empty_like(params[pre + "conv.band_hz_"])
@@ -479,7 +496,7 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
             grads[pre + "conv.low_hz_"] = dlow
             grads[pre + "conv.band_hz_"] = dband
         else:
-            plan.tn(("dyz", l), plan.dyz[l], C, g.Pd, g.taps - 1, True, ("apad", l), plan.apad[l],
+            plan.tn(("dyz", l), plan.dyz[l], C, g.Pd, g.taps - 1, False, ("apad", l), plan.apad[l],
                     g.lda, g.P, False, plan.dWt[l], g.K, C, g.K, N, g.T_out, 1.0, 0)
             dW = torch.empty_like(params[pre + "conv.weight"])
             call("pase_conv_w_from_fwd", plan.dWt[l], dW.reshape(-1), g.Cout, g.Cin, g.k)

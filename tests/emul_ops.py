@@ -179,13 +179,19 @@ def _prelu(u, a):
     return torch.where(u > 0, u, a * u)
 
 
+def _residual(a):
+    return _tf32_rn(a - _tf32_trunc(a))
+
+
 def pase_bn_prelu_pad_fwd(y, y_ss, N, T, C, scale, shift, alpha, dst, d_ss, d_rs, padL, padR,
-                          pool, p_ss, p_rs, pool_d, pool_T):
+                          pool, p_ss, p_rs, pool_d, pool_T, dst_lo=None):
     yv = _as(y, (N, T, C), (y_ss, C, 1))
     a = _prelu(yv * scale[:C] + shift[:C], alpha[:C])
     Tp = T + padL + padR
     idx = _reflect(torch.arange(Tp) - padL, T)
     _as(dst, (N, Tp, C), (d_ss, d_rs, 1)).copy_(a[:, idx])
+    if dst_lo is not None:
+        _as(dst_lo, (N, Tp, C), (d_ss, d_rs, 1)).copy_(_residual(a[:, idx].contiguous()))
     if pool is not None and pool_d > 0:
         L = pool_T * pool_d
         pv = _as(pool, (N, pool_T, C), (p_ss, p_rs, 1))
@@ -223,7 +229,7 @@ def pase_bn_prelu_bwd_reduce(y, y_ss, N, T, C, mean, invstd, scale, shift, alpha
 
 
 def pase_bn_prelu_bwd_apply(y, y_ss, N, T, C, mean, invstd, gamma, S1, S2, count, dst, d_ss,
-                            dbias):
+                            dbias, dst_lo=None):
     yv = _as(y, (N, T, C), (y_ss, C, 1))
     dv = _as(dst, (N, T, C), (d_ss, C, 1))
     xh = (yv - mean[:C]) * invstd[:C]
@@ -231,6 +237,8 @@ def pase_bn_prelu_bwd_apply(y, y_ss, N, T, C, mean, invstd, gamma, S1, S2, count
     m1, m2 = (S1[:C] / count).float(), (S2[:C] / count).float()
     out = gi * (dv - m1 - xh * m2)
     dv.copy_(out)
+    if dst_lo is not None:
+        _as(dst_lo, (N, T, C), (d_ss, C, 1)).copy_(_residual(out.contiguous()))
     if dbias is not None:
         dbias[:C] += out.double().sum((0, 1))
 

@@ -119,9 +119,10 @@ def test_reflect_pad_and_bn_finalize():
                                      torch.zeros(C)])
 
 
+@pytest.mark.parametrize("with_lo", [False, True])
 @pytest.mark.parametrize("N,T,C,padL,padR,pool_d", [(2, 203, 64, 4, 5, 16), (3, 77, 48, 0, 0, 0),
                                                     (2, 1001, 128, 5, 5, 8), (2, 50, 512, 9, 10, 2)])
-def test_bn_prelu_pad_fwd(N, T, C, padL, padR, pool_d):
+def test_bn_prelu_pad_fwd(N, T, C, padL, padR, pool_d, with_lo):
     Tp = T + padL + padR
     y = R(N * (T + 3) * C, seed=20)
     d_rs = C + 8
@@ -130,7 +131,8 @@ def test_bn_prelu_pad_fwd(N, T, C, padL, padR, pool_d):
     pool = torch.zeros(N * max(pool_T, 1) * 200 + C) if pool_d else None
     run_both("pase_bn_prelu_pad_fwd", [y, (T + 3) * C, N, T, C, R(C, seed=21), R(C, seed=22),
                                        R(C, seed=23, scale=0.3), dst, (Tp + 2) * d_rs, d_rs, padL,
-                                       padR, pool, max(pool_T, 1) * 200, 200, pool_d, pool_T])
+                                       padR, pool, max(pool_T, 1) * 200, 200, pool_d, pool_T,
+                                       torch.zeros_like(dst) if with_lo else None])
 
 
 @pytest.mark.parametrize("N,T,C,padL,padR,pool_d,useB", [(2, 203, 64, 4, 5, 16, False),
@@ -153,8 +155,8 @@ def test_bn_prelu_bwd(N, T, C, padL, padR, pool_d, useB):
         S1, S2, dal], rtol=2e-4, atol=2e-5)
     du, s1, s2 = cpu[24], cpu[26], cpu[27]
     run_both("pase_bn_prelu_bwd_apply", [y, T * C, N, T, C, mean, invstd, R(C, seed=33), s1, s2,
-                                         float(N * T), du, T * C, torch.zeros(C, dtype=torch.float64)],
-             rtol=2e-4, atol=2e-5)
+                                         float(N * T), du, T * C, torch.zeros(C, dtype=torch.float64),
+                                         None], rtol=2e-4, atol=2e-5)
 
 
 def test_prelu_colsum_cast():
