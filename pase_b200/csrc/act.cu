@@ -153,19 +153,21 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
   __syncthreads();
   const int C4 = C >> 2;
   const int n = blockIdx.y;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int q = (int)(idx % C4);
-  const long run = idx / C4;
-  const long t0 = run * RUN;
+  // grid-stride over runs (the host only caps the grid when the stride keeps each thread on
+  // the same channel quad): fewer blocks -> far fewer same-address fp64 atomics at the end
+  const long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nthreads = (long)C4 * ((T + RUN - 1) / RUN);
+  const int q = (int)(idx0 % C4);
   const int c = q * 4;
   float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, a3[4] = {0, 0, 0, 0};
-  if (t0 < T) {
-    const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
-    const float4 mu = ld4(mean + c), is = ld4(invstd + c);
-    const float* yn = y + (long)n * y_ss;
-    float* dn = dst + (long)n * d_ss;
-    const int pool_len = s.pool_d > 0 ? s.pool_T * s.pool_d : 0;
-    const float inv_d = s.pool_d > 0 ? 1.f / (float)s.pool_d : 0.f;
+  const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
+  const float4 mu = ld4(mean + c), is = ld4(invstd + c);
+  const float* yn = y + (long)n * y_ss;
+  float* dn = dst + (long)n * d_ss;
+  const int pool_len = s.pool_d > 0 ? s.pool_T * s.pool_d : 0;
+  const float inv_d = s.pool_d > 0 ? 1.f / (float)s.pool_d : 0.f;
+  for (long idx = idx0; idx < nthreads; idx += (long)gridDim.x * blockDim.x) {
+    const long t0 = (idx / C4) * RUN;
     const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
     float4 gs[RUN], ys[RUN];
     // phase 1: issue every load of the run (gradient sources + saved pre-activation)
@@ -231,7 +233,7 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
       }
     }
   }
-  if ((pre && (threadIdx.x & 31) < C4) || (!pre && t0 < T)) {
+  if ((pre && (threadIdx.x & 31) < C4) || (!pre && idx0 < nthreads)) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       atomicAdd(&red[0 * C + c + k], a1[k]);
@@ -259,12 +261,12 @@ bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
   __syncthreads();
   const int C4 = C >> 2;
   const int n = blockIdx.y;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int q = (int)(idx % C4);
-  const long run = idx / C4;
-  const long t0 = run * RUN;
-  if (t0 < T) {
-    const int c = q * 4;
+  const long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nthreads = (long)C4 * ((T + RUN - 1) / RUN);
+  const int q = (int)(idx0 % C4);
+  const int c = q * 4;
+  float acc[4] = {0, 0, 0, 0};
+  if (idx0 < nthreads) {
     float m1[4], m2[4], gi[4], muv[4], isv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -276,7 +278,8 @@ bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
     }
     const float* yn = y + (long)n * y_ss;
     float* dn = dst + (long)n * d_ss;
-    float acc[4] = {0, 0, 0, 0};
+    for (long idx = idx0; idx < nthreads; idx += (long)gridDim.x * blockDim.x) {
+    const long t0 = (idx / C4) * RUN;
     const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
     float4 vs[RUN], ds[RUN];
 #pragma unroll
@@ -303,6 +306,7 @@ bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
         st4(dst_lo + (long)n * d_ss + (long)t * C + c,
             make_float4(tf32_residual(o[0]), tf32_residual(o[1]), tf32_residual(o[2]),
                         tf32_residual(o[3])));
+    }
     }
     if (dbias) {
 #pragma unroll
@@ -605,7 +609,13 @@ int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T,
   BwdSrc s{srcA, a_sample_stride, a_row_stride, padL, padR, srcB, b_sample_stride, b_row_stride,
            b_shift, pool, pool_sample_stride, pool_row_stride, pool ? pool_d : 0, pool_T};
   const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
-  dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
+  long gx = (threads + THREADS - 1) / THREADS;
+  if ((THREADS % (C / 4)) == 0) {          // stride keeps the channel quad: cap the grid
+    long cap = (8L * pase_num_sms() + N - 1) / N;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+  }
+  dim3 grid((unsigned)gx, N);
   bn_prelu_bwd_reduce_kernel<<<grid, THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
       y, y_sample_stride, T, C, mean, invstd, scale, shift, alpha, s, dst, dst_sample_stride, S1,
       S2, dalpha);
@@ -622,7 +632,13 @@ int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, 
   PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 8192,
                  "pase_bn_prelu_bwd_apply: bad C=%d", C);
   const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
-  dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
+  long gx = (threads + THREADS - 1) / THREADS;
+  if ((THREADS % (C / 4)) == 0) {
+    long cap = (8L * pase_num_sms() + N - 1) / N;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+  }
+  dim3 grid((unsigned)gx, N);
   bn_prelu_bwd_apply_kernel<<<grid, THREADS, C * sizeof(float), (cudaStream_t)stream>>>(
       y, y_sample_stride, T, C, mean, invstd, gamma, S1, S2, 1.0 / count, dst, dst_sample_stride,
       dbias_acc, dst_lo);

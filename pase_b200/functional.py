@@ -5,13 +5,78 @@ channels) with a leading dimension that is a multiple of 4 floats; padding
 columns are kept at zero so a padded matrix can be fed straight back as a GEMM
 operand.  Each autograd Function launches only kernels of pase_b200/csrc.
 """
+import os
+
 import torch
 
 from . import ops
 
+# GEMM numerics of the heads (same meaning as WaveFe.precision): "3xtf32" (tcgen05, fp32-
+# equivalent), "tf32", or "fp32" (FFMA kernels).
+PRECISION = os.environ.get("PASE_B200_PRECISION", "3xtf32")
+_MODES = {"fp32": None, "3xtf32": 1, "tf32": 0}
+
+
+def set_precision(p):
+    global PRECISION
+    if p not in _MODES:
+        raise ValueError("precision must be one of %s" % sorted(_MODES))
+    PRECISION = p
+
 
 def _ru4(n):
     return (n + 3) // 4 * 4
+
+
+def _ru32(n):
+    return (n + 31) // 32 * 32
+
+
+def _pad_ld(n):
+    """leading dimension of a rows-matrix with n columns: tensor-core modes pad to 32 so the
+    matrix can itself be a TMA operand (one folded row = k 128-byte boxes)."""
+    return _ru4(n) if _MODES[PRECISION] is None else _ru32(n)
+
+
+def _split_act(flat, n, mode):
+    if mode != 1:
+        return flat, None
+    lo = torch.empty(n, dtype=torch.float32, device=flat.device)
+    ops.call("pase_split_tf32", flat, None, lo, n)
+    return flat, lo
+
+
+def _split_w(flat, n, mode):
+    if mode != 1:
+        return flat, None
+    hi = torch.empty(n, dtype=torch.float32, device=flat.device)
+    lo = torch.empty(n, dtype=torch.float32, device=flat.device)
+    ops.call("pase_split_tf32", flat, hi, lo, n)
+    return hi, lo
+
+
+def gemm_nt(A, lda, a_used, B, ldb, b_used, C, ldc, M, N, K, bias):
+    """C[m,n] = sum_k A[m*lda+k] B[n*ldb+k] + bias[n]; dispatches tcgen05 / FFMA."""
+    mode = _MODES[PRECISION]
+    if mode is None or lda % 32 != 0 or K % 4 != 0 or ldb % 4 != 0:
+        return ops.call("pase_gemm_nt", A, lda, B, ldb, C, ldc, M, N, K, 1.0, bias,
+                        M, M, M, 1, None, None, 0)
+    Ah, Al = _split_act(A, a_used, mode)
+    Bh, Bl = _split_w(B, b_used, mode)
+    return ops.call("pase_tc_gemm_nt", Ah, Al, a_used // lda, lda, Bh, Bl, ldb, C, ldc, M, N, K,
+                    1.0, bias, M, M, M, 1, None, None, 0, mode)
+
+
+def gemm_tn(A, lda, a_used, B, ldb, b_used, C, ldc, I, J, rows):
+    """C[i,j] = sum_r A[r*lda+i] B[r*ldb+j]."""
+    mode = _MODES[PRECISION]
+    if mode is None or ldb % 32 != 0 or lda % 4 != 0 or I % 4 != 0 or J % 32 != 0:
+        return ops.call("pase_gemm_tn", A, lda, rows, 0, B, ldb, rows, 0, C, ldc, I, J, 1, rows,
+                        1.0, 0)
+    Ah, Al = _split_act(A, a_used, mode)
+    Bh, Bl = _split_act(B, b_used, mode)
+    return ops.call("pase_tc_gemm_tn", Ah, Al, lda, rows, 0, Bh, Bl, ldb, rows, b_used // ldb,
+                    C, ldc, I, J, 1, rows, 1.0, 0, mode)
 
 
 def _rows_ld(x):
@@ -50,38 +115,45 @@ class _LinearRows(torch.autograd.Function):
         w2 = weight.detach().reshape(N, -1)
         assert w2.shape[1] == K and K % 4 == 0, "in-features %d must match and be a multiple of 4" % K
         w2 = w2.contiguous()
-        ldo = _ru4(N)
-        out = torch.empty(rows, ldo, dtype=torch.float32, device=x.device)
+        ldo = _pad_ld(N)
+        # +32 floats of slack: the tensor-core weight-gradient kernel reads whole 32-column
+        # blocks of dY
+        buf = torch.empty(rows * ldo + 32, dtype=torch.float32, device=x.device)
+        out = buf[:rows * ldo].view(rows, ldo)
+        buf[rows * ldo:].zero_()
         if ldo != N:
             out[:, N:].zero_()
-        ops.call("pase_gemm_nt", _flat_from(x), ldx, w2.reshape(-1), K, out.reshape(-1), ldo,
-                 rows, N, K, 1.0, None if bias is None else bias.detach().reshape(-1),
-                 rows, rows, rows, 1, None, None, 0)
+        gemm_nt(_flat_from(x), ldx, rows * ldx, w2.reshape(-1), K, N * K, out.reshape(-1), ldo,
+                rows, N, K, None if bias is None else bias.detach().reshape(-1))
         ctx.save_for_backward(x, w2)
-        ctx.ldx, ctx.N, ctx.has_bias, ctx.wshape = ldx, N, bias is not None, weight.shape
+        ctx.ldx, ctx.N, ctx.has_bias, ctx.wshape, ctx.ldo = ldx, N, bias is not None, \
+            weight.shape, ldo
         return out
 
     @staticmethod
     def backward(ctx, dy):
         x, w2 = ctx.saved_tensors
         rows, K = x.shape
-        N, ldx = ctx.N, ctx.ldx
-        ldo = _ru4(N)
-        dy = dy.contiguous()
+        N, ldx, ldo = ctx.N, ctx.ldx, ctx.ldo
         assert dy.shape == (rows, ldo)
         dev = x.device
+        dyb = torch.empty(rows * ldo + 32, dtype=torch.float32, device=dev)
+        dyb[:rows * ldo].view(rows, ldo).copy_(dy)
+        dyb[rows * ldo:].zero_()
+        dyf = dyb
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             wT = torch.empty(K, ldo, dtype=torch.float32, device=dev)
             ops.call("pase_transpose_pad", w2.reshape(-1), K, wT.reshape(-1), ldo, N, K)
             dx = torch.empty(rows, K, dtype=torch.float32, device=dev)
-            ops.call("pase_gemm_nt", dy.reshape(-1), ldo, wT.reshape(-1), ldo, dx.reshape(-1), K,
-                     rows, K, ldo, 1.0, None, rows, rows, rows, 1, None, None, 0)
+            gemm_nt(dyf, ldo, rows * ldo, wT.reshape(-1), ldo, K * ldo, dx.reshape(-1), K,
+                    rows, K, ldo, None)
         if ctx.needs_input_grad[1]:
             dWp = torch.empty(ldo, K, dtype=torch.float32, device=dev)
-            ops.call("pase_gemm_tn", dy.reshape(-1), ldo, rows, 0, _flat_from(x), ldx, rows, 0,
-                     dWp.reshape(-1), K, ldo, K, 1, rows, 1.0, 0)
+            gemm_tn(dyf, ldo, rows * ldo, _flat_from(x), ldx, rows * ldx, dWp.reshape(-1), K,
+                    ldo, K, rows)
             dW = dWp[:N].reshape(ctx.wshape)
+        dy = dyb[:rows * ldo].view(rows, ldo)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             acc = torch.zeros(ldo, dtype=torch.float64, device=dev)
             ops.call("pase_colsum", dy.reshape(-1), ldo, rows, ldo, acc)

@@ -43,9 +43,10 @@ class RowsInput(object):
 
 
 def rows_to_pred(rows, B, T, ncols):
-    """(B*T, ld) rows -> reference-shaped (B, ncols, T) view, tagged with its buffer."""
-    ld = rows.shape[1]
-    pred = rows.view(B, T, ld)[:, :, :ncols].transpose(1, 2)
+    """(B*T, >=ncols) rows (row stride ld) -> reference-shaped (B, ncols, T) view, tagged with
+    its buffer."""
+    ld = rows.stride(0) if rows.shape[0] > 1 else rows.shape[1]
+    pred = torch.as_strided(rows, (B, ncols, T), (T * ld, 1, ld), rows.storage_offset())
     pred._pase_rows = (rows, ncols)
     return pred
 
@@ -85,8 +86,9 @@ class MLPMinion(Model):
     def forward_rows(self, rows):
         h = rows
         for blk in self.blocks:
+            C = blk.W.weight.shape[0]
             u = Fn.linear_rows(h, blk.W.weight, blk.W.bias)
-            h = Fn.prelu_rows(u, blk.act.weight, blk.W.weight.shape[0])
+            h = Fn.prelu_rows(u, blk.act.weight, C)[:, :C]      # drop the leading-dim padding
         return Fn.linear_rows(h, self.W.weight, self.W.bias), h
 
     def forward(self, x, alpha=1, device=None):
@@ -177,8 +179,9 @@ class DecoderMinion(Model):
         xin = RowsInput.of(x)
         h, L = _dec.decoder_stack(self, xin.rows, xin.B, xin.T)       # (B*L, C) rows
         for blk in self.blocks[self.n_deconv:]:
+            C = blk.W.weight.shape[0]
             u = Fn.linear_rows(h, blk.W.weight, blk.W.bias)
-            h = Fn.prelu_rows(u, blk.act.weight, blk.W.weight.shape[0])
+            h = Fn.prelu_rows(u, blk.act.weight, C)[:, :C]
         y = Fn.linear_rows(h, self.W.weight, self.W.bias)
         return rows_to_pred(y, xin.B, L, self.num_outputs)
 

@@ -427,8 +427,18 @@ def pase_split_tf32(x, hi, lo, n):
     lo[:n] = _tf32_rn(x[:n] - h)
 
 
+def _like(lo, hi):
+    """lo residual arrays may be shorter than the hi buffer (only the used part is split)."""
+    if lo is None or lo.numel() >= hi.numel():
+        return lo
+    out = torch.zeros(hi.numel(), dtype=lo.dtype)
+    out[:lo.numel()] = lo
+    return out
+
+
 def pase_tc_gemm_nt(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, C, ldc, M, N, K, alpha, bias, rows_in,
                     t_valid, rows_out, fold, colsum, colsumsq, accumulate, mode):
+    Alo, Blo = _like(Alo, Ahi), _like(Blo, Bhi)
     need = M * R + K
     A = torch.zeros(need)
     lim = min(a_rows * R, Ahi.numel(), need)         # TMA zero-fills rows >= a_rows
@@ -445,6 +455,7 @@ def pase_tc_gemm_nt(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, C, ldc, M, N, K, alpha, 
 
 def pase_tc_gemm_tn(Ahi, Alo, lda, pitchA, offA, Bhi, Blo, R, pitchB, b_rows_total, C, ldc, I, J,
                     groups, rows_per_group, alpha, accumulate, mode):
+    Alo, Blo = _like(Alo, Ahi), _like(Blo, Bhi)
     A = _tf32_trunc(Ahi)
     if mode == 1:
         A = A + _tf32_trunc(Alo)
