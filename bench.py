@@ -292,43 +292,45 @@ def run_native(args):
     # ---- roofline of the dominant kernel family (implicit-GEMM): CUDA events around each
     # gemm launch of one extra, untimed-for-the-headline step -------------------------------
     gemm_ms, gemm_flop, per_kernel = 0.0, 0.0, {}
-    if rank == 0:
-        recs = []
-        real_call = ops.call
+    recs = []
+    real_call = ops.call
 
-        def spy(name, *a):
-            if name in ("pase_gemm_nt", "pase_gemm_tn", "pase_tc_gemm_nt", "pase_tc_gemm_tn"):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                r = real_call(name, *a)
-                e.record()
-                if name == "pase_gemm_nt":
-                    fl = 2.0 * a[6] * a[7] * a[8]
-                elif name == "pase_gemm_tn":
-                    fl = 2.0 * a[10] * a[11] * a[12] * a[13]
-                elif name == "pase_tc_gemm_nt":
-                    fl = 2.0 * a[9] * a[10] * a[11]
-                else:
-                    fl = 2.0 * a[12] * a[13] * a[14] * a[15]
-                recs.append((name, s, e, fl))
-                return r
-            return real_call(name, *a)
+    def spy(name, *a):
+        if name in ("pase_gemm_nt", "pase_gemm_tn", "pase_tc_gemm_nt", "pase_tc_gemm_tn"):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = real_call(name, *a)
+            e.record()
+            if name == "pase_gemm_nt":
+                fl = 2.0 * a[6] * a[7] * a[8]
+            elif name == "pase_gemm_tn":
+                fl = 2.0 * a[10] * a[11] * a[12] * a[13]
+            elif name == "pase_tc_gemm_nt":
+                fl = 2.0 * a[9] * a[10] * a[11]
+            else:
+                fl = 2.0 * a[12] * a[13] * a[14] * a[15]
+            recs.append((name, s, e, fl))
+            return r
+        return real_call(name, *a)
+    # every rank runs the two instrumented steps (they contain the gradient all-reduce, a
+    # collective); only rank 0 records
+    if rank == 0:
         ops.call = spy
-        try:
-            for _ in range(2):
-                recs.clear()
-                step_resident()
-                torch.cuda.synchronize()
-        finally:
-            ops.call = real_call
-        for name, s, e, fl in recs:
-            t = s.elapsed_time(e)
-            gemm_ms += t
-            gemm_flop += fl
-            k = per_kernel.setdefault(name, [0, 0.0, 0.0])
-            k[0] += 1
-            k[1] += t
-            k[2] += fl
+    try:
+        for _ in range(2):
+            recs.clear()
+            step_resident()
+            torch.cuda.synchronize()
+    finally:
+        ops.call = real_call
+    for name, s, e, fl in recs:
+        t = s.elapsed_time(e)
+        gemm_ms += t
+        gemm_flop += fl
+        k = per_kernel.setdefault(name, [0, 0.0, 0.0])
+        k[0] += 1
+        k[1] += t
+        k[2] += fl
     if world > 1:
         dist.barrier()
 
