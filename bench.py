@@ -211,6 +211,11 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # everything runs on one non-default stream so that the eager steps and the CUDA-graph
+    # capture of the end-to-end step share their autograd (AccumulateGrad) stream
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+
     torch.manual_seed(0)                               # identical replicas
     model = wf_builder(dict(PASE_PLUS)).to(dev).train()
     model.precision = args.precision
@@ -271,19 +276,51 @@ def run_native(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # launches of OUR kernels per step, counted on eager steps (a graph replay re-issues the
+    # same kernels without going through the Python funnel)
+    n0 = ops.launch_count
+    step_resident()
+    launches_per_step = ops.launch_count - n0
+    value_fn, value_graphed = step_resident, False
+    gopt = None
+    if world == 1 and not args.no_graph:
+        try:
+            from pase_b200.graph import GraphedEncoderStep
+            gopt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
+            gres = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
+                                      (B_PER_GPU, 1, T_CHUNK), dev, stream=side, resident=True)
+            gres.x_static.copy_(x_dev)
+            value_fn, value_graphed = (lambda: gres.step()), True
+            for _ in range(3):
+                value_fn()
+        except Exception as exc:
+            sys.stderr.write("bench: CUDA-graph capture unavailable (%s); eager steps\n" % (exc,))
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     if sampler:
         sampler.start()
-    n0 = ops.launch_count
-    ms = timed(step_resident, args.steps)
-    launches = ops.launch_count - n0
+    ms = timed(value_fn, args.steps)
+    launches = launches_per_step * args.steps
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    # end-to-end: through the public API with pinned HOST waveforms; at N=1 the whole step
+    # (H2D, fwd, bwd, Adam, D2H of the loss) is captured in one CUDA graph when possible
+    graphed, e2e_fn = False, step_e2e
+    if world == 1 and not args.no_graph:
+        try:
+            from pase_b200.graph import GraphedEncoderStep
+            gopt = gopt or torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
+            gs = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
+                                    (B_PER_GPU, 1, T_CHUNK), dev, stream=side)
+            gs.x_host.copy_(x_host)                   # the loader's pinned staging buffer
+            e2e_fn = lambda: gs.step()
+            graphed = True
+        except Exception as exc:                      # report, fall back to the eager path
+            sys.stderr.write("bench: CUDA-graph capture unavailable (%s); eager e2e\n" % (exc,))
     for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+        e2e_fn()
+    ms_e2e = timed(e2e_fn, args.steps)
 
     samples_per_step = B_PER_GPU * T_CHUNK * world
     value = samples_per_step * args.steps / (ms * 1e-3)
@@ -351,9 +388,11 @@ def run_native(args):
                                    "train-mode BN, no workers (BASELINE configs[1])",
                        "global_batch": B_PER_GPU * world, "seq_len": T_CHUNK,
                        "parallelism": "dp%d" % world, "gemm_precision": args.precision,
+                       "cuda_graph": value_graphed,
                        "l2": "no flush: per-step working set (~1.7 GB activations) >> 126 MB L2",
                        "grad_allreduce_bytes": red.nbytes if red is not None else 0},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                    "cuda_graph": graphed,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
@@ -400,6 +439,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager end-to-end step (no CUDA graph)")
     ap.add_argument("--precision", default=os.environ.get("PASE_B200_PRECISION", "3xtf32"),
                     choices=["fp32", "3xtf32", "tf32"],
                     help="GEMM numerics: fp32 FFMA, 3xTF32 tcgen05 (fp32-equivalent), TF32 tcgen05")
