@@ -194,6 +194,73 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def workers_plus_cfg():
+    """cfg/workers/workers+.cfg restated programmatically (names, output sizes, r, losses)."""
+    mlp = lambda name, nout: {"num_outputs": nout, "dropout": 0, "hidden_size": 256,
+                              "hidden_layers": 1, "name": name, "context": 1, "r": 7,
+                              "loss": "MSELoss", "skip": False}
+    regr = [{"num_outputs": 1, "dropout": 0, "dropout_time": 0.0, "hidden_layers": 1,
+             "name": "cchunk", "type": "decoder", "hidden_size": 64, "fmaps": [512, 256, 128],
+             "strides": [4, 4, 10], "kwidths": [30, 30, 30], "loss": "L1Loss"}]
+    for name, nout in (("lps", 3075), ("lps_long", 3075), ("fbank", 120), ("fbank_long", 120),
+                       ("gtn", 120), ("gtn_long", 120), ("mfcc", 39), ("mfcc_long", 60),
+                       ("prosody", 12)):
+        regr.append(mlp(name, nout))
+    cls = [{"num_outputs": 1, "dropout": 0, "hidden_size": 256, "hidden_layers": 1, "name": n,
+            "loss": "BCEWithLogitsLoss", "skip": False, "augment": n == "cmi"}
+           for n in ("mi", "cmi")]
+    return {"regr": regr, "cls": cls}
+
+
+def run_workers(args):
+    """Extra workload (BASELINE configs[2-3] shape): encoder on the 3B concatenated chunks +
+    all workers+ heads + summed loss, fwd+bwd+Adam, 1 GPU, eager.  Not the contract line."""
+    from pase_b200.pase import pase, total_loss
+    from pase_b200.utils import parse_workers
+    from pase_b200 import functional as Fn
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    Fn.set_precision(args.precision)
+    torch.manual_seed(0)
+    wcfg = workers_plus_cfg()
+    model = pase(frontend_cfg=dict(PASE_PLUS), minions_cfg=parse_workers(wcfg)).to(dev).train()
+    model.frontend.precision = args.precision
+    B = args.batch
+    Tq = T_CHUNK // 160
+    batch = {k: torch.randn(B, 1, T_CHUNK, device=dev) for k in
+             ("chunk", "chunk_ctxt", "chunk_rand", "cchunk")}
+    for w in wcfg["regr"]:
+        if w["name"] != "cchunk":
+            batch[w["name"]] = torch.randn(B, w["num_outputs"], Tq, device=dev)
+    opt = torch.optim.Adam([p for p in model.parameters()], lr=1e-4, fused=True)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        h, chunk, preds, labels = model(batch, 1, dev)
+        tot, _ = total_loss(model, preds, labels)
+        tot.backward()
+        opt.step()
+        return tot
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    nparam = sum(p.numel() for p in model.parameters())
+    print(json.dumps({"metric": "waveform-samples/sec PASE+ encoder(3B chunks)+workers+ heads "
+                                "fwd+bwd+adam", "value": B * T_CHUNK / (ms * 1e-3),
+                      "unit": "chunk-samples/s", "ms_per_step": ms, "n_gpus": 1,
+                      "config": {"workload": "PASE+.cfg + workers+.cfg (12 workers), B=%d chunk "
+                                             "triplets, T=32000" % B,
+                                 "gemm_precision": args.precision, "params": nparam},
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 # ------------------------------------------------------------------ GPU arm ---
 def run_native(args):
     import torch.distributed as dist
@@ -440,12 +507,18 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager end-to-end step (no CUDA graph)")
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "workers"],
+                    help="encoder = the contract line (BASELINE configs[1]); workers = encoder + "
+                         "all workers+ heads (informational)")
+    ap.add_argument("--batch", type=int, default=32, help="chunk triplets per step (workers workload)")
     ap.add_argument("--precision", default=os.environ.get("PASE_B200_PRECISION", "3xtf32"),
                     choices=["fp32", "3xtf32", "tf32"],
                     help="GEMM numerics: fp32 FFMA, 3xTF32 tcgen05 (fp32-equivalent), TF32 tcgen05")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "workers":
+        run_workers(args)
     else:
         run_native(args)
 

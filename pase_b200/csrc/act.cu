@@ -170,32 +170,53 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
     const long t0 = (idx / C4) * RUN;
     const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
     float4 gs[RUN], ys[RUN];
-    // phase 1: issue every load of the run (gradient sources + saved pre-activation)
+    // phase 1: straight-line loads of the whole run (no branch between a load and the next
+    // one, so all DRAM requests of the run are in flight together)
+    const float* an = s.A + (long)n * s.a_ss + c;
 #pragma unroll
     for (int i = 0; i < RUN; ++i) {
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < nvalid) {
+      const int t = (int)t0 + (i < nvalid ? i : 0);
+      gs[i] = ld4(an + (long)(t + s.padL) * s.a_rs);
+      ys[i] = ld4(yn + (long)t * C + c);
+    }
+    if (s.P != nullptr) {                       // mean-pooled dense-skip gradient (broadcast)
+      const float* pn = s.P + (long)n * s.p_ss + c;
+      float4 pv[RUN];
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
+        const int t = (int)t0 + (i < nvalid ? i : 0);
+        const int tw = t < pool_len ? t / s.pool_d : 0;
+        pv[i] = ld4(pn + (long)tw * s.p_rs);
+      }
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
         const int t = (int)t0 + i;
-        auto add4 = [&](const float* p, float w) {
+        const float w = (t < pool_len) ? inv_d : 0.f;
+        gs[i].x += pv[i].x * w; gs[i].y += pv[i].y * w;
+        gs[i].z += pv[i].z * w; gs[i].w += pv[i].w * w;
+      }
+    }
+    // rare: reflect-pad fold-back at the two sequence ends, second shifted source (QRNN)
+    const bool edge = (s.padL > 0 && t0 <= s.padL) || (s.padR > 0 && t0 + RUN >= T - 1 - s.padR);
+    if (edge || s.B != nullptr) {
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
+        if (i >= nvalid) break;
+        const int t = (int)t0 + i;
+        float4 g = gs[i];
+        auto add4 = [&](const float* p) {
           const float4 v = ld4(p);
-          g.x += v.x * w; g.y += v.y * w; g.z += v.z * w; g.w += v.w * w;
+          g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
         };
-        if (s.A) {
-          const float* an = s.A + (long)n * s.a_ss + c;
-          add4(an + (long)(t + s.padL) * s.a_rs, 1.f);
-          if (s.padL > 0 && t >= 1 && t <= s.padL) add4(an + (long)(s.padL - t) * s.a_rs, 1.f);
-          if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
-            add4(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs, 1.f);
-        }
+        if (s.padL > 0 && t >= 1 && t <= s.padL) add4(an + (long)(s.padL - t) * s.a_rs);
+        if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
+          add4(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs);
         if (s.B) {
           const int tb = t + s.b_shift;
-          if (tb >= 0 && tb < T) add4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c, 1.f);
+          if (tb >= 0 && tb < T) add4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c);
         }
-        if (s.P && t < pool_len)
-          add4(s.P + (long)n * s.p_ss + (long)(t / s.pool_d) * s.p_rs + c, inv_d);
-        ys[i] = ld4(yn + (long)t * C + c);
+        gs[i] = g;
       }
-      gs[i] = g;
     }
     const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
     const float alv[4] = {al.x, al.y, al.z, al.w};
@@ -602,8 +623,9 @@ int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T,
                              long pool_row_stride, int pool_d, int pool_T, float* dst,
                              long dst_sample_stride, double* S1, double* S2, double* dalpha,
                              void* stream) {
-  PASE_CHECK_ARG(y && mean && invstd && scale && shift && alpha && dst && S1 && S2 && dalpha,
-                 "pase_bn_prelu_bwd_reduce: null pointer");
+  PASE_CHECK_ARG(y && mean && invstd && scale && shift && alpha && dst && S1 && S2 && dalpha &&
+                     srcA,
+                 "pase_bn_prelu_bwd_reduce: null pointer (srcA is mandatory)");
   PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 4096,
                  "pase_bn_prelu_bwd_reduce: C=%d must be a multiple of 4, <= 4096", C);
   BwdSrc s{srcA, a_sample_stride, a_row_stride, padL, padR, srcB, b_sample_stride, b_row_stride,

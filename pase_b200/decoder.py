@@ -12,6 +12,7 @@ weight gradient is the same TN GEMM the encoder uses.
 import torch
 
 from . import ops
+from . import functional as Fn
 
 
 def _cdiv(a, b):
@@ -69,9 +70,9 @@ class _DecoderStackFn(torch.autograd.Function):
             W, b, alpha = params[3 * i].detach(), params[3 * i + 1].detach(), \
                 params[3 * i + 2].detach()
             call("pase_deconv_w_to_fwd", W.reshape(-1), plan.Wu[i], g.Cin, g.Cout, g.k, g.s, g.taps)
-            call("pase_gemm_nt", plan.xz[i], g.Cin, plan.Wu[i], g.taps * g.Cin, plan.yfull[i],
-                 g.s * g.Cout, B * g.Pd, g.s * g.Cout, g.taps * g.Cin, 1.0,
-                 b.repeat(g.s).contiguous(), g.Pd, g.U, g.U, 1, None, None, 0)
+            Fn.gemm_nt(plan.xz[i], g.Cin, plan.xz[i].numel(), plan.Wu[i], g.taps * g.Cin,
+                       plan.Wu[i].numel(), plan.yfull[i], g.s * g.Cout, B * g.Pd, g.s * g.Cout,
+                       g.taps * g.Cin, b.repeat(g.s).contiguous(), g.Pd, g.U, g.U)
             if i + 1 < len(G):
                 nx = G[i + 1]
                 dst, d_ss = plan.xz[i + 1][(nx.taps - 1) * nx.Cin:], nx.Pd * nx.Cin
@@ -114,17 +115,18 @@ class _DecoderStackFn(torch.autograd.Function):
             call("pase_cast_d2f", acc, small, 4 * C, 1.0)
             grads[3 * i + 2] = small[2 * C:3 * C].clone().view_as(alpha)
             grads[3 * i + 1] = small[3 * C:4 * C].clone()
-            call("pase_gemm_tn", plan.dyfull[i], g.s * C, g.U, 0, plan.xz[i], g.Cin, g.Pd, 0,
-                 plan.dWu[i], g.taps * g.Cin, g.s * C, g.taps * g.Cin, B, g.U, 1.0, 0)
+            Fn.gemm_tn(plan.dyfull[i], g.s * C, plan.dyfull[i].numel(), plan.xz[i], g.Cin,
+                       plan.xz[i].numel(), plan.dWu[i], g.taps * g.Cin, g.s * C, g.taps * g.Cin,
+                       g.U, groups=B, pitchA=g.U, offA=0, pitchB=g.Pd)
             dW = torch.empty_like(W)
             call("pase_deconv_w_from_fwd", plan.dWu[i], dW.reshape(-1), g.Cin, g.Cout, g.k, g.s,
                  g.taps)
             grads[3 * i] = dW
             if i > 0 or ctx.needs_input_grad[0]:
                 call("pase_deconv_w_to_bwd", W.reshape(-1), plan.Wb[i], g.Cin, g.Cout, g.k)
-                call("pase_gemm_nt", plan.dyfull[i], g.s * C, plan.Wb[i], g.k * C, plan.dx[i],
-                     g.Cin, B * g.U, g.Cin, g.k * C, 1.0, None, g.U, g.T_in, g.T_in, 1,
-                     None, None, 0)
+                Fn.gemm_nt(plan.dyfull[i], g.s * C, plan.dyfull[i].numel(), plan.Wb[i], g.k * C,
+                           plan.Wb[i].numel(), plan.dx[i], g.Cin, B * g.U, g.Cin, g.k * C, None,
+                           g.U, g.T_in, g.T_in)
                 src = plan.dx[i]
         dx = None
         if ctx.needs_input_grad[0]:

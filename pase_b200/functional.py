@@ -55,28 +55,35 @@ def _split_w(flat, n, mode):
     return hi, lo
 
 
-def gemm_nt(A, lda, a_used, B, ldb, b_used, C, ldc, M, N, K, bias):
-    """C[m,n] = sum_k A[m*lda+k] B[n*ldb+k] + bias[n]; dispatches tcgen05 / FFMA."""
+def gemm_nt(A, lda, a_used, B, ldb, b_used, C, ldc, M, N, K, bias, rows_in=None, t_valid=None,
+            rows_out=None):
+    """C[map(m),n] = sum_k A[m*lda+k] B[n*ldb+k] + bias[n]; dispatches tcgen05 / FFMA.
+    Optional row map (rows_in, t_valid, rows_out) as in pase_gemm_nt."""
     mode = _MODES[PRECISION]
+    if rows_in is None:
+        rows_in = t_valid = rows_out = M
     if mode is None or lda % 32 != 0 or K % 4 != 0 or ldb % 4 != 0:
         return ops.call("pase_gemm_nt", A, lda, B, ldb, C, ldc, M, N, K, 1.0, bias,
-                        M, M, M, 1, None, None, 0)
+                        rows_in, t_valid, rows_out, 1, None, None, 0)
     Ah, Al = _split_act(A, a_used, mode)
     Bh, Bl = _split_w(B, b_used, mode)
     return ops.call("pase_tc_gemm_nt", Ah, Al, a_used // lda, lda, Bh, Bl, ldb, C, ldc, M, N, K,
-                    1.0, bias, M, M, M, 1, None, None, 0, mode)
+                    1.0, bias, rows_in, t_valid, rows_out, 1, None, None, 0, mode)
 
 
-def gemm_tn(A, lda, a_used, B, ldb, b_used, C, ldc, I, J, rows):
-    """C[i,j] = sum_r A[r*lda+i] B[r*ldb+j]."""
+def gemm_tn(A, lda, a_used, B, ldb, b_used, C, ldc, I, J, rows, groups=1, pitchA=None, offA=0,
+            pitchB=None):
+    """C[i,j] = sum_r A[rowA(r)*lda+i] B[rowB(r)*ldb+j] over `groups` x `rows` rows."""
     mode = _MODES[PRECISION]
+    pitchA = rows if pitchA is None else pitchA
+    pitchB = rows if pitchB is None else pitchB
     if mode is None or ldb % 32 != 0 or lda % 4 != 0 or I % 4 != 0 or J % 32 != 0:
-        return ops.call("pase_gemm_tn", A, lda, rows, 0, B, ldb, rows, 0, C, ldc, I, J, 1, rows,
-                        1.0, 0)
+        return ops.call("pase_gemm_tn", A, lda, pitchA, offA, B, ldb, pitchB, 0, C, ldc, I, J,
+                        groups, rows, 1.0, 0)
     Ah, Al = _split_act(A, a_used, mode)
     Bh, Bl = _split_act(B, b_used, mode)
-    return ops.call("pase_tc_gemm_tn", Ah, Al, lda, rows, 0, Bh, Bl, ldb, rows, b_used // ldb,
-                    C, ldc, I, J, 1, rows, 1.0, 0, mode)
+    return ops.call("pase_tc_gemm_tn", Ah, Al, lda, pitchA, offA, Bh, Bl, ldb, pitchB,
+                    b_used // ldb, C, ldc, I, J, groups, rows, 1.0, 0, mode)
 
 
 def _rows_ld(x):
