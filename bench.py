@@ -289,18 +289,15 @@ def run_native(args):
     params = list(model.parameters())
     # N>1: every .grad is a view of one flat buffer -> a single NCCL all-reduce per step.
     # N=1: no collective, gradients are handed to Adam as produced (no accumulation adds).
-    red = FlatGradAllReducer(params) if world > 1 else None
+    red = FlatGradAllReducer(params, attach=False) if world > 1 else None
     opt = torch.optim.Adam(params, lr=1e-4, fused=True)
 
     def zero_grads():
-        if red is not None:
-            red.zero()
-        else:
-            opt.zero_grad(set_to_none=True)
+        opt.zero_grad(set_to_none=True)
 
     def reduce_grads():
         if red is not None:
-            red.all_reduce()
+            red.pack_and_reduce()
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)   # distinct data per rank
     x_host = torch.randn(B_PER_GPU, 1, T_CHUNK, generator=g).pin_memory()
     x_dev = x_host.to(dev)

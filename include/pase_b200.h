@@ -46,7 +46,7 @@ int pase_device_info(int* out4);
  *   u*fold + n/(N/fold) < t_valid; it is stored at row g*rows_out + u.
  *   colsum/colsumsq (double[N], may be NULL) accumulate the per-column sum and
  *   sum of squares of the valid outputs (BatchNorm batch statistics).
- *   prec: 0 = fp32 FFMA, (tensor-core modes added by later entry points).
+ *   This entry point computes in fp32 FFMA; pase_tc_gemm_nt is the tensor-core variant.
  */
 int pase_gemm_nt(const float* A, long lda, const float* B, long ldb,
                  float* C, long ldc, int M, int N, int K,

@@ -15,9 +15,10 @@
 //           representable tf32 "hi" and "lo" parts (hi + lo == fp32 value to 2^-22),
 //           D = Ahi*Bhi + Alo*Bhi + Ahi*Blo  -> fp32-equivalent products.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
-// (one elected lane), warps 2-5 = epilogue (tcgen05.ld -> bias / row map / BatchNorm
-// column statistics -> global).  K-major tiles are 128-byte rows with the 128B swizzle.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2-17 = 16 epilogue warps (tcgen05.ld -> fp32 register sums -> bias /
+// row map / BatchNorm column statistics -> staged coalesced stores).  K-major tiles are
+// 128-byte rows with the 128B swizzle; two TMEM accumulator buffers per CTA.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -26,7 +27,6 @@ namespace {
 constexpr int BM = 128;
 constexpr int BKF = 32;                  // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                // tf32
-constexpr int NTHREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 200u * 1000u * 1000u;
 
 // ------------------------------------------------------------------ PTX helpers ----
@@ -65,23 +65,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
                                             int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar,

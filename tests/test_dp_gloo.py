@@ -31,6 +31,13 @@ def _worker(rank, world, port, out):
     assert all(p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr()
                for p in model.parameters())
     red.all_reduce()
+    first = red.flat.clone()
+    # second protocol: fresh gradients packed with one multi-tensor copy
+    red.detach()
+    model(x).square().mean().backward()
+    red.pack_and_reduce()
+    assert torch.allclose(red.flat, first, rtol=1e-6, atol=1e-8)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
     torch.save(red.flat.clone(), os.path.join(out, "g%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
