@@ -84,6 +84,10 @@ int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, in
                     float* C, long ldc, int I, int J, int groups, int rows_per_group,
                     float alpha, int accumulate, int mode, void* stream);
 
+/* hardware probe used by tools/rowshift_probe.py only (not on the product path) */
+int pase_tc_probe_rowshift(const float* W, const float* B, float* D, int wrows, int shift,
+                           int use_base_offset, void* stream);
+
 /* ---- weight re-layout (implicit-GEMM operand preparation) ---------------- */
 /* (Cout,Cin,k) -> Wt[co, j*Cin+ci]                      (forward operand)   */
 int pase_conv_w_to_fwd(const float* W, float* Wt, int Cout, int Cin, int k, void* stream);

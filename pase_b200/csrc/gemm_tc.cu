@@ -21,6 +21,7 @@
 // 128-byte rows with the 128B swizzle; two TMEM accumulator buffers per CTA.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
@@ -255,13 +256,22 @@ __device__ __forceinline__ uint64_t desc_hi_bits(uint32_t lbo_bytes, uint32_t sb
   return make_desc<LAYOUT>(0, lbo_bytes, sbo_bytes);
 }
 
-template <int BN, bool SPLIT>
+// BK = fp32 elements per k-block: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows,
+// SWIZZLE_64B; used with BN = 256 so that four pipeline stages still fit in shared memory).
+// Why BN = 256: a 128xNx8 tf32 UMMA reads (128 + N) * 32 B of shared memory in N/2 clocks --
+// 128 B/clk at N = 128, i.e. the whole shared-memory bandwidth of the SM before the TMA fills
+// are even counted (measured tensor-pipe activity ~58 %); N = 256 needs 96 B/clk.
+template <int BN, bool SPLIT, int BK>
 struct NTCfg {
-  static constexpr int A_BYTES = BM * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int ROW_BYTES = BK * 4;
+  static constexpr int A_BYTES = BM * ROW_BYTES;
+  static constexpr int B_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;      // two accumulator buffers
-  static constexpr int EPI_ACTIVE = 4 * (BN / 32);
+  static constexpr int CPW = (BN / 32 + 3) / 4; // 32-column chunks per epilogue warp
+  static constexpr int EPI_ACTIVE = BN >= 128 ? 16 : 4 * (BN / 32);
+  static constexpr int LAYOUT = BK == 32 ? 2 : 4;          // SWIZZLE_128B : SWIZZLE_64B
+  static constexpr int SBO = 8 * ROW_BYTES;                // 8-row core-matrix group
 };
 
 // ------------------------------------------------------------------ NT kernel ----
@@ -270,7 +280,7 @@ struct NTCfg {
 // TMEM buffers; the epilogue warps fold each finished buffer into fp32 register sums with
 // round-to-nearest adds (the tensor core's own accumulator rounds toward zero, which drifts
 // over long K) while the MMAs of the next chunk / next tile run.
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int BK>
 __global__ void __launch_bounds__(NTHREADS_V3, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
@@ -278,7 +288,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
                   const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
                   double* __restrict__ colsumsq, int accumulate, int flush_kb, int stages,
                   int stat_cols) {
-  using Cfg = NTCfg<BN, SPLIT>;
+  using Cfg = NTCfg<BN, SPLIT, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -294,7 +304,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
   const int total_tiles = n_tiles * m_tiles;
-  const int nkb = (K + BKF - 1) / BKF;
+  const int nkb = (K + BK - 1) / BK;
   if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
   const int nchunks = (nkb + flush_kb - 1) / flush_kb;
   const bool want_stats = colsum != nullptr;
@@ -335,7 +345,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           mbar_wait(&empty_bar[s], ph ^ 1, 1);
           uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          const int kf = kb * BKF;
+          const int kf = kb * BK;
           const int arow = m0 + kf / R, acol = kf % R;
           tma_load_2d(st, &mAhi, &full_bar[s], acol, arow);
           tma_load_2d(st + Cfg::A_BYTES, &mBhi, &full_bar[s], kf, n0);
@@ -350,7 +360,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-      const uint64_t dconst = desc_hi_bits<2>(16, 1024);
+      const uint64_t dconst = desc_hi_bits<Cfg::LAYOUT>(16, Cfg::SBO);
       const uint32_t tiles_u32 = smem_u32(tiles);
       uint32_t it = 0, c = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -373,7 +383,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
             const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
             const uint32_t first = (kb == kb_lo) ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < BKF / UMMA_K; ++k) {
+            for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t acc = (k == 0) ? first : 1u;
               if (SPLIT) {
                 umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
@@ -394,7 +404,275 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
     // ---------------- epilogue: 16 warps = 4 TMEM lane quarters x 4 column chunks ------------
     const int e = warp - 2;
     const int q = warp & 3;                      // hardware: warp w may access lanes 32*(w%4)..
-    const int cc = e >> 2;                       // this warp's 32-column chunk of the tile
+    const int cc0 = e >> 2;                      // first 32-column chunk of this warp
+    if (cc0 < BN / 32) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+      float* stg = s_out + e * OUT_STG_FLOATS;
+      uint32_t c = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        float sums[Cfg::CPW][32];
+        for (int ch = 0; ch < nchunks; ++ch, ++c) {
+          const uint32_t b = c & 1, aph = (c >> 1) & 1;
+          mbar_wait(&acc_full[b], aph, 3);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < Cfg::CPW; ++h) {
+            uint32_t raw[32];
+            tmem_ld32(lane_addr + b * BN + (cc0 + 4 * h) * 32, raw);
+            if (ch == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sums[h][j] = __uint_as_float(raw[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sums[h][j] += __uint_as_float(raw[j]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[b]);        // buffer may be overwritten now
+        }
+        // ---- output: bias, row map / validity, optional accumulate, BatchNorm statistics ----
+        const int m = m0 + q * 32 + lane;
+        long orow = 0;
+        int nlim = 0;                            // columns [0, nlim) of this row are valid
+        if (m < M) {
+          const int g = m / rm.rows_in;
+          const int u = m - g * rm.rows_in;
+          orow = (long)g * rm.rows_out + u;
+          const long lim = (long)(rm.t_valid - u * rm.fold) * rm.cols_per_fold;
+          nlim = lim <= 0 ? 0 : (lim >= N ? N : (int)lim);
+        }
+#pragma unroll
+        for (int h = 0; h < Cfg::CPW; ++h) {
+          const int nb = n0 + (cc0 + 4 * h) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = sums[h][j] * alpha;
+            if (bias != nullptr && nb + j < N) x += __ldg(bias + nb + j);
+            sums[h][j] = x;
+          }
+          store_chunk<false>(stg, sums[h], lane, C, ldc, orow, nlim, nb, vec_ok, accumulate);
+          if (want_stats) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sums[h][j] = (nb + j < nlim) ? sums[h][j] : 0.f;
+              sq[j] = sums[h][j] * sums[h][j];
+            }
+            const float s1 = colsum32(sums[h], lane);
+            const float s2 = colsum32(sq, lane);
+            if (nb + lane < N) {
+              atomicAdd(&s_stats[nb + lane], s1);
+              atomicAdd(&s_stats[stat_cols + nb + lane], s2);
+            }
+          }
+        }
+      }
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 1, 512;" ::: "memory");     // the 16 epilogue warps only
+      for (int col = threadIdx.x - 64; col < N; col += N_EPI_WARPS * 32) {
+        const float a = s_stats[col], b2 = s_stats[stat_cols + col];
+        if (a != 0.f || b2 != 0.f) {
+          atomicAdd(colsum + col, (double)a);
+          atomicAdd(colsumsq + col, (double)b2);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ NT window kernel ----
+// Same contract as tc_gemm_nt_kernel, but the A operand is fetched once per 32-float column
+// block instead of once per k-block.  With A(m, kk) = F[m + kk/R, kk%R] the k-blocks
+// kk = q*R + cb*32 (q = 0..Q-1) of one column block cb read the SAME columns of F, shifted by
+// q rows: one TMA box of (BM + Q - 1) rows serves all of them, the UMMA descriptor simply
+// starts q rows (q*128 B) further down.  (Verified on B200, tools/rowshift_probe.py: K-major
+// SWIZZLE_128B operands may start at any row with base_offset = 0 -- the swizzle is a function
+// of absolute shared-memory address bits.)  For a k-tap stride-s convolution this divides the
+// activation traffic by ~k/s; the weight tiles stream through a ring of B stages.
+template <int BN, bool SPLIT>
+struct NTWCfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_STAGE_BYTES = (SPLIT ? 2 : 1) * B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int EPI_ACTIVE = 4 * (BN / 32);
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS_V3, 1)
+tc_gemm_ntw_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
+                   int R, float* __restrict__ C, long ldc, int M, int N, int K, float alpha,
+                   const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
+                   double* __restrict__ colsumsq, int accumulate, int flush_kb, int stages,
+                   int stat_cols, int win_rows) {
+  using Cfg = NTWCfg<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int win_bytes = win_rows * 128;                       // one hi (or lo) window
+  const int win_pair = (SPLIT ? 2 : 1) * win_bytes;
+  uint8_t* wins = smem;                                       // 2 window buffers (hi [, lo])
+  uint8_t* btiles = smem + 2 * win_pair;
+  uint8_t* after = btiles + stages * Cfg::B_STAGE_BYTES;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(after);
+  uint64_t* b_empty = b_full + MAX_STAGES;
+  uint64_t* w_full = b_empty + MAX_STAGES;
+  uint64_t* w_empty = w_full + 2;
+  uint64_t* acc_full = w_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_out = reinterpret_cast<float*>(after + BAR_BYTES);
+  float* s_stats = s_out + OUT_STAGE_BYTES / 4;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
+  const int total_tiles = n_tiles * m_tiles;
+  const int nkb = K / BKF;                                    // K % 32 == 0 (host-checked)
+  const int ncb = (R < K ? R : K) / BKF;                      // column blocks of a folded row
+  if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
+  const bool want_stats = colsum != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&w_full[b], 1);
+      mbar_init(&w_empty[b], 1);
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], Cfg::EPI_ACTIVE);
+    }
+    fence_barrier_init();
+    tmap_prefetch(&mAhi);
+    tmap_prefetch(&mBhi);
+    if (SPLIT) {
+      tmap_prefetch(&mAlo);
+      tmap_prefetch(&mBlo);
+    }
+  }
+  if (want_stats)
+    for (int i = threadIdx.x; i < 2 * stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // q-steps of column block cb: kk = q*R + cb*32 < K
+  auto nq_of = [&](int cb) { return (K - cb * BKF + R - 1) / R; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t wi = 0, bi = 0;
+      auto issue_window = [&](int tile, int cb) {
+        const uint32_t w = wi & 1, wph = (wi >> 1) & 1;
+        mbar_wait(&w_empty[w], wph ^ 1, 5);
+        const int m0 = (tile / n_tiles) * BM;
+        uint8_t* dst = wins + w * win_pair;
+        mbar_expect_tx(&w_full[w], win_pair);
+        tma_load_2d(dst, &mAhi, &w_full[w], cb * BKF, m0);
+        if (SPLIT) tma_load_2d(dst + win_bytes, &mAlo, &w_full[w], cb * BKF, m0);
+        ++wi;
+      };
+      int tile = blockIdx.x, cb = 0;
+      if (tile < total_tiles) issue_window(tile, 0);
+      while (tile < total_tiles) {
+        const int n0 = (tile % n_tiles) * BN;
+        const int nq = nq_of(cb);
+        // successor (tile, cb) whose window is prefetched while this block's last B tiles load
+        int ntile = tile, ncbn = cb + 1;
+        if (ncbn == ncb) { ncbn = 0; ntile = tile + gridDim.x; }
+        const int pre_at = nq > stages ? nq - stages : 0;
+        for (int q = 0; q < nq; ++q, ++bi) {
+          if (q == pre_at && ntile < total_tiles) issue_window(ntile, ncbn);
+          const int s = bi % stages;
+          const uint32_t ph = (bi / stages) & 1;
+          mbar_wait(&b_empty[s], ph ^ 1, 1);
+          uint8_t* st = btiles + s * Cfg::B_STAGE_BYTES;
+          mbar_expect_tx(&b_full[s], Cfg::B_STAGE_BYTES);
+          const int kf = q * R + cb * BKF;
+          tma_load_2d(st, &mBhi, &b_full[s], kf, n0);
+          if (SPLIT) tma_load_2d(st + Cfg::B_BYTES, &mBlo, &b_full[s], kf, n0);
+        }
+        tile = ntile;
+        cb = ncbn;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+      const uint64_t dconst = desc_hi_bits<2>(16, 1024);
+      const uint32_t wins_u32 = smem_u32(wins), bt_u32 = smem_u32(btiles);
+      uint32_t wi = 0, bi = 0, c = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int in_chunk = 0, done_kb = 0;
+        uint32_t b = c & 1;
+        mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1, 4);
+        tc_fence_after();
+        for (int cb = 0; cb < ncb; ++cb, ++wi) {
+          const uint32_t w = wi & 1;
+          mbar_wait(&w_full[w], (wi >> 1) & 1, 6);
+          tc_fence_after();
+          const uint32_t a_hi0 = wins_u32 + w * win_pair;
+          const int nq = nq_of(cb);
+          for (int q = 0; q < nq; ++q, ++bi) {
+            const int s = bi % stages;
+            mbar_wait(&b_full[s], (bi / stages) & 1, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + b * BN;
+            // A starts q rows into the window; k-step of 8 tf32 = +32 B
+            const uint64_t dah = dconst + ((a_hi0 + q * 128) >> 4);
+            const uint64_t dal = dconst + ((a_hi0 + win_bytes + q * 128) >> 4);
+            const uint64_t dbh = dconst + ((bt_u32 + s * Cfg::B_STAGE_BYTES) >> 4);
+            const uint64_t dbl = dbh + (Cfg::B_BYTES >> 4);
+            const uint32_t first = in_chunk == 0 ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < BKF / UMMA_K; ++k) {
+              const uint32_t acc = (k == 0) ? first : 1u;
+              if (SPLIT) {
+                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
+                umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+              } else {
+                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
+              }
+            }
+            umma_commit(&b_empty[s]);
+            ++in_chunk;
+            ++done_kb;
+            if (in_chunk == flush_kb || done_kb == nkb) {
+              umma_commit(&acc_full[b]);           // chunk complete -> epilogue folds it
+              ++c;
+              in_chunk = 0;
+              if (done_kb < nkb) {
+                b = c & 1;
+                mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1, 4);
+                tc_fence_after();
+              }
+            }
+          }
+          umma_commit(&w_empty[w]);                // window free once its MMAs retire
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: identical to tc_gemm_nt_kernel ----------------
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int cc = e >> 2;
+    const int nchunks = (nkb + flush_kb - 1) / flush_kb;
     if (cc < BN / 32) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
       const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
@@ -411,7 +689,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           tmem_ld32(taddr + b * BN, raw);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[b]);        // buffer may be overwritten now
+          if (lane == 0) mbar_arrive(&acc_empty[b]);
           if (ch == 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) sums[j] = __uint_as_float(raw[j]);
@@ -420,10 +698,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
             for (int j = 0; j < 32; ++j) sums[j] += __uint_as_float(raw[j]);
           }
         }
-        // ---- output: bias, row map / validity, optional accumulate, BatchNorm statistics ----
         const int m = m0 + q * 32 + lane;
         long orow = 0;
-        int nlim = 0;                            // columns [0, nlim) of this row are valid
+        int nlim = 0;
         if (m < M) {
           const int g = m / rm.rows_in;
           const int u = m - g * rm.rows_in;
@@ -456,7 +733,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       }
     }
     if (want_stats) {
-      asm volatile("bar.sync 1, 512;" ::: "memory");     // the 16 epilogue warps only
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       for (int col = threadIdx.x - 64; col < N; col += N_EPI_WARPS * 32) {
         const float a = s_stats[col], b2 = s_stats[stat_cols + col];
         if (a != 0.f || b2 != 0.f) {
@@ -661,6 +938,17 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 }
 
 // ------------------------------------------------------------------ host side ----
+static bool pase_tc_use_window() {
+  static int v = -1;
+  if (v < 0) {
+    // off by default: measured slower than the per-k-block kernel (the GEMMs are bound by
+    // shared-memory bandwidth, not by operand traffic); PASE_B200_TC_WINDOW=1 enables it
+    const char* e = getenv("PASE_B200_TC_WINDOW");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -706,12 +994,12 @@ int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims
   return PASE_OK;
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int BK>
 int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
               const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
               const float* bias, RowMap rm, double* cs, double* cq, int accumulate, int flush_kb,
               cudaStream_t st) {
-  using Cfg = NTCfg<BN, SPLIT>;
+  using Cfg = NTCfg<BN, SPLIT, BK>;
   static bool attr = false;
   const int stat_cols = cs ? ((N + 31) / 32) * 32 : 0;
   const int stages = pick_stages(Cfg::STAGE_BYTES, 2 * stat_cols * 4);
@@ -721,7 +1009,7 @@ int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
     return PASE_ERR_UNSUPPORTED;
   }
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, SPLIT>,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, SPLIT, BK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
       pase_set_error("pase_tc_gemm_nt: smem attribute: %s", cudaGetErrorString(e));
@@ -731,10 +1019,46 @@ int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   }
   const long tiles = (long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
   const int grid = (int)(tiles < pase_num_sms() ? tiles : pase_num_sms());
-  tc_gemm_nt_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(
+  tc_gemm_nt_kernel<BN, SPLIT, BK><<<grid, NTHREADS_V3, smem, st>>>(
       ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
       stat_cols);
   PASE_LAUNCH_CHECK("pase_tc_gemm_nt");
+  return PASE_OK;
+}
+
+template <int BN, bool SPLIT>
+int launch_ntw(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+               const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
+               const float* bias, RowMap rm, double* cs, double* cq, int accumulate, int flush_kb,
+               int win_rows, cudaStream_t st) {
+  using Cfg = NTWCfg<BN, SPLIT>;
+  static bool attr = false;
+  const int stat_cols = cs ? ((N + 31) / 32) * 32 : 0;
+  const int win_total = 2 * (SPLIT ? 2 : 1) * win_rows * 128;
+  int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - OUT_STAGE_BYTES - 2 * stat_cols * 4 - win_total) /
+               Cfg::B_STAGE_BYTES;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) {
+    pase_set_error("pase_tc_gemm_nt: not enough shared memory for the window pipeline");
+    return PASE_ERR_UNSUPPORTED;
+  }
+  const int smem = win_total + stages * Cfg::B_STAGE_BYTES + 1024 + BAR_BYTES + OUT_STAGE_BYTES +
+                   2 * stat_cols * 4;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_ntw_kernel<BN, SPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      pase_set_error("pase_tc_gemm_nt(window): smem attribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr = true;
+  }
+  const long tiles = (long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const int grid = (int)(tiles < pase_num_sms() ? tiles : pase_num_sms());
+  tc_gemm_ntw_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(
+      ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
+      stat_cols, win_rows);
+  PASE_LAUNCH_CHECK("pase_tc_gemm_nt(window)");
   return PASE_OK;
 }
 
@@ -862,35 +1186,59 @@ int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, cons
   PASE_CHECK_ARG((colsum == nullptr) == (colsumsq == nullptr), "pase_tc_gemm_nt: stats pair");
   PASE_CHECK_ARG(colsum == nullptr || N <= 2048, "pase_tc_gemm_nt: stats need N <= 2048");
   PASE_CHECK_ARG(colsum == nullptr || !accumulate, "pase_tc_gemm_nt: stats + accumulate");
-  const int BN = N <= 64 ? 64 : 128;
-  // 3xTF32: fold the TMEM accumulator into fp32 register sums every 4 k-blocks (K = 128)
-  const int flush_kb = (mode == 1) ? 4 : 0;
+  // 256-wide tiles (16-element k-blocks, see NTCfg) raise the MMA rate per flop by ~1.2x but
+  // halve the tile count (wave quantisation) and double the epilogue per warp: measured on
+  // the PASE+ shapes they only pay off for long reductions (profiles/r01_history.md)
+  const bool wide = N >= 256 && (N % 256) == 0 && K >= 4096;
+  const int BN = N <= 64 ? 64 : (wide ? 256 : 128);
+  const int BKh = BN == 256 ? 16 : 32;
+  // 3xTF32: fold the TMEM accumulator into fp32 register sums every K = 128
+  const int flush_kb = (mode == 1) ? 128 / BKh : 0;
   CUtensorMap ah, al, bh, bl;
+  // window kernel: A fetched once per 32-float column block (needs K % 32 == 0); the plain
+  // per-k-block kernel remains for ragged K
+  const bool window = BN != 256 && (K % 32) == 0 && pase_tc_use_window();
+  const int qmax = (K + R - 1) / R - 1;
+  const int win_rows = ((BM + qmax + 7) / 8) * 8;
   uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
   uint64_t astr[1] = {(uint64_t)R * 4};
-  uint32_t abox[2] = {32, (uint32_t)BM};
+  uint32_t abox[2] = {(uint32_t)BKh, (uint32_t)(window ? win_rows : BM)};
   uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
   uint64_t bstr[1] = {(uint64_t)ldb * 4};
-  uint32_t bbox[2] = {32, (uint32_t)BN};
+  uint32_t bbox[2] = {(uint32_t)BKh, (uint32_t)BN};
+  const CUtensorMapSwizzle swz = BKh == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  PASE_CHECK_ARG(!window || win_rows <= 256, "pase_tc_gemm_nt: K/R=%d too large for a window",
+                 qmax + 1);
   int rc;
-  if ((rc = make_map(&ah, Ahi, 2, adims, astr, abox, "A.hi")) != 0) return rc;
-  if ((rc = make_map(&bh, Bhi, 2, bdims, bstr, bbox, "B.hi")) != 0) return rc;
+  if ((rc = make_map(&ah, Ahi, 2, adims, astr, abox, "A.hi", swz)) != 0) return rc;
+  if ((rc = make_map(&bh, Bhi, 2, bdims, bstr, bbox, "B.hi", swz)) != 0) return rc;
   if (mode == 1) {
-    if ((rc = make_map(&al, Alo, 2, adims, astr, abox, "A.lo")) != 0) return rc;
-    if ((rc = make_map(&bl, Blo, 2, bdims, bstr, bbox, "B.lo")) != 0) return rc;
+    if ((rc = make_map(&al, Alo, 2, adims, astr, abox, "A.lo", swz)) != 0) return rc;
+    if ((rc = make_map(&bl, Blo, 2, bdims, bstr, bbox, "B.lo", swz)) != 0) return rc;
   } else {
     al = ah;
     bl = bh;
   }
   RowMap rm{rows_in, t_valid, rows_out, fold, N / fold};
   cudaStream_t st = (cudaStream_t)stream;
-#define PASE_NT(BNV)                                                                             \
-  (mode == 1 ? launch_nt<BNV, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, colsum, \
-                                    colsumsq, accumulate, flush_kb, st)                          \
-             : launch_nt<BNV, false>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,        \
-                                     colsum, colsumsq, accumulate, flush_kb, st))
-  if (BN == 64) return PASE_NT(64);
-  return PASE_NT(128);
+  if (window) {
+#define PASE_NTW(BNV)                                                                          \
+  (mode == 1 ? launch_ntw<BNV, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,       \
+                                     colsum, colsumsq, accumulate, flush_kb, win_rows, st)      \
+             : launch_ntw<BNV, false>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,      \
+                                      colsum, colsumsq, accumulate, flush_kb, win_rows, st))
+    if (BN == 64) return PASE_NTW(64);
+    return PASE_NTW(128);
+#undef PASE_NTW
+  }
+#define PASE_NT(BNV, BKV)                                                                       \
+  (mode == 1 ? launch_nt<BNV, true, BKV>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,   \
+                                         colsum, colsumsq, accumulate, flush_kb, st)            \
+             : launch_nt<BNV, false, BKV>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,  \
+                                          colsum, colsumsq, accumulate, flush_kb, st))
+  if (BN == 64) return PASE_NT(64, 32);
+  if (BN == 128) return PASE_NT(128, 32);
+  return PASE_NT(256, 16);
 #undef PASE_NT
 }
 

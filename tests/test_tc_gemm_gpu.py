@@ -46,6 +46,8 @@ NT_CASES = [
     (520, 2048, 288, 32, 130, 4100, 129, 32, False, True, 0),     # folded sinc (fold 32)
     (333, 512, 5632, 1024, 111, 100, 100, 1, True, False, 1),     # long K, accumulate
     (260, 1920, 256, 256, 260, 260, 260, 1, False, False, 0),     # dcat shape, wide N
+    (300, 128, 200, 64, 300, 300, 300, 1, True, True, 0),         # K % 32 != 0: per-k-block kernel
+    (4000, 256, 2816, 256, 1000, 990, 990, 1, True, True, 0),     # many tiles / persistent loop
 ]
 
 
