@@ -38,6 +38,16 @@ BYTES_PER_CHUNK = 96.5e6         # ideal-fusion HBM traffic, fp32
 FP32_FFMA_PEAK_TF = 74.4         # 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
+def gemm_traffic(precision):
+    """DRAM bytes per GEMM launch (dram__bytes_read+write) from the committed ncu --set full
+    capture of this kernel family (profiles/r01_gemm_traffic.json); None if not captured for
+    this precision."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if precision != "3xtf32" or not os.path.exists(path):
+        return None
+    return json.load(open(path))["dram_bytes_per_launch"]
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -468,7 +478,8 @@ def run_native(args):
                            "tf32": "pase_tc_gemm_nt + pase_tc_gemm_tn (tcgen05 kind::tf32)"}[
                     args.precision],
                 "bound": "tensor", "achieved": ach_tf, "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": ach_tf / peaks["tf_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": ach_tf / peaks["tf_sustained"],
+                "traffic": gemm_traffic(args.precision),
                 "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "gemm_share_of_step": gemm_ms / step_ms if step_ms > 0 else None,
                 "gemm_ms_per_step": gemm_ms, "gemm_gflop_per_step": gemm_flop / 1e9,
