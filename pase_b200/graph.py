@@ -12,11 +12,14 @@ class GraphedEncoderStep(object):
     given at construction; `loss_fn(y) -> scalar tensor`; the optimizer must be capturable."""
 
     def __init__(self, model, optimizer, loss_fn, shape, device, pre_step=None, post_backward=None,
-                 warmup=3, stream=None, resident=False):
+                 warmup=3, stream=None, resident=False, x_init=None):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.x_static = torch.zeros(shape, dtype=torch.float32, device=device)
         self.x_host = torch.zeros(shape, dtype=torch.float32).pin_memory()
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        if x_init is not None:               # batch used by the warm-up steps
+            self.x_host.copy_(x_init)
+            self.x_static.copy_(x_init)
         self.pre_step, self.post_backward = pre_step, post_backward
         self.resident = resident        # True: input stays in HBM, no H2D / D2H in the graph
         # capture on the stream the model's autograd nodes already live on: an AccumulateGrad

@@ -21,10 +21,13 @@ def test_graphed_step_matches_eager():
     torch.cuda.set_stream(side)
     try:
         x = seeded_randn((4, 1, 6400), 5, 0.5)
-        loss_fn = lambda y: y.square().mean()
+        cot = seeded_randn((4, 256, 40), 6).cuda()
+        loss_fn = lambda y: (y * cot).mean() + y.abs().mean()     # not invariant under norm_out
         # eager: two Adam steps
         me = _model(3)
-        oe = torch.optim.Adam(me.parameters(), lr=1e-3, fused=True, capturable=True)
+        # SGD: linear in the gradients (Adam would turn the fp-noise gradients of the
+        # analytically-zero conv biases into +-lr steps of random sign)
+        oe = torch.optim.SGD(me.parameters(), lr=1e-2, momentum=0.9, foreach=True)
         eager_losses = []
         for _ in range(3 + 2):                       # same number of updates as warm-up + replays
             oe.zero_grad(set_to_none=True)
@@ -34,15 +37,16 @@ def test_graphed_step_matches_eager():
             eager_losses.append(float(l))
         # graphed: 3 warm-up updates inside the constructor, capture (1 update), then 1 replay
         mg = _model(3)
-        og = torch.optim.Adam(mg.parameters(), lr=1e-3, fused=True, capturable=True)
-        gs = GraphedEncoderStep(mg, og, loss_fn, (4, 1, 6400), "cuda", stream=side, warmup=3)
-        gs.x_host.copy_(x)
+        og = torch.optim.SGD(mg.parameters(), lr=1e-2, momentum=0.9, foreach=True)
+        gs = GraphedEncoderStep(mg, og, loss_fn, (4, 1, 6400), "cuda", stream=side, warmup=3,
+                                x_init=x)
         # the capture itself does not execute; replays do
         l1 = gs.step()
         l2 = gs.step()
-        assert abs(l1 - eager_losses[3]) <= 2e-4 * abs(eager_losses[3]) + 1e-6
-        assert abs(l2 - eager_losses[4]) <= 2e-4 * abs(eager_losses[4]) + 1e-6
+        assert abs(l1 - eager_losses[3]) <= 5e-4 * abs(eager_losses[3]) + 1e-6
+        assert abs(l2 - eager_losses[4]) <= 5e-4 * abs(eager_losses[4]) + 1e-6
+        assert abs(eager_losses[4] - eager_losses[3]) > 1e-3 * abs(eager_losses[3])   # loss moves
         for (k, pe), (_, pg) in zip(me.named_parameters(), mg.named_parameters()):
-            assert rel_l2(pg.detach().cpu(), pe.detach().cpu()) < 1e-4, k
+            assert rel_l2(pg.detach().cpu(), pe.detach().cpu()) < 2e-3, k
     finally:
         torch.cuda.set_stream(torch.cuda.default_stream())
