@@ -113,6 +113,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-convergent variants: every lane of the MMA warp executes the surrounding loop and
+// one elected lane issues.  Keeping the warp converged lets ptxas hold descriptors and TMEM
+// addresses in uniform registers; under `if (lane == 0)` every UTCHMMA is preceded by an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY sequence and the issue thread, not the tensor pipe,
+// bounds the MMA rate (profiles/r01_history.md).
+__device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
@@ -336,67 +359,79 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
+        int arow = m0, acol = 0;                 // folded-row view: k = (arow - m0) * R + acol
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1, 1);
           uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           const int kf = kb * BK;
-          const int arow = m0 + kf / R, acol = kf % R;
           tma_load_2d(st, &mAhi, &full_bar[s], acol, arow);
           tma_load_2d(st + Cfg::A_BYTES, &mBhi, &full_bar[s], kf, n0);
           if (SPLIT) {
             tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mAlo, &full_bar[s], acol, arow);
             tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mBlo, &full_bar[s], kf, n0);
           }
+          acol += BK;
+          while (acol >= R) {
+            acol -= R;
+            ++arow;
+          }
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-      const uint64_t dconst = desc_hi_bits<Cfg::LAYOUT>(16, Cfg::SBO);
-      const uint32_t tiles_u32 = smem_u32(tiles);
-      uint32_t it = 0, c = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < nchunks; ++ch, ++c) {
-          const uint32_t b = c & 1, aph = (c >> 1) & 1;
-          mbar_wait(&acc_empty[b], aph ^ 1, 4);
+    // all 32 lanes run the loop (converged); one elected lane issues each MMA / commit
+    constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+    const uint64_t dconst = desc_hi_bits<Cfg::LAYOUT>(16, Cfg::SBO);
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+    uint32_t c = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < nchunks; ++ch, ++c) {
+        const uint32_t b = c & 1, aph = (c >> 1) & 1;
+        mbar_wait(&acc_empty[b], aph ^ 1, 4);
+        tc_fence_after();
+        const uint32_t d_tmem = tm0 + b * BN;
+        const int kb_lo = ch * flush_kb;
+        const int kb_hi = (kb_lo + flush_kb < nkb) ? kb_lo + flush_kb : nkb;
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          mbar_wait(&full_bar[s], ph, 2);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + b * BN;
-          const int kb_lo = ch * flush_kb;
-          const int kb_hi = (kb_lo + flush_kb < nkb) ? kb_lo + flush_kb : nkb;
-          for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
-            const int s = it % stages;
-            const uint32_t ph = (it / stages) & 1;
-            mbar_wait(&full_bar[s], ph, 2);
-            tc_fence_after();
-            // descriptor = constant bits + (byte address >> 4); k-step of 8 tf32 = +32 B = +2
-            const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
-            const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
-            const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
-            const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
-            const uint32_t first = (kb == kb_lo) ? 0u : 1u;
+          // descriptor = constant bits + (byte address >> 4); k-step of 8 tf32 = +32 B = +2
+          const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
+          const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
+          const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
+          const uint32_t first = (kb == kb_lo) ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint32_t acc = (k == 0) ? first : 1u;
-              if (SPLIT) {
-                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
-                umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
-                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
-              } else {
-                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
-              }
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t acc = (k == 0) ? first : 1u;
+            if (SPLIT) {
+              umma_tf32_w(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
+              umma_tf32_w(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+              umma_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+            } else {
+              umma_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
             }
-            umma_commit(&empty_bar[s]);          // frees the smem stage once the MMAs retire
           }
-          umma_commit(&acc_full[b]);             // this chunk's accumulator is complete
+          umma_commit_w(&empty_bar[s]);          // frees the smem stage once the MMAs retire
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
         }
+        umma_commit_w(&acc_full[b]);             // this chunk's accumulator is complete
       }
     }
     __syncwarp();
@@ -822,9 +857,13 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
+      int s = -1;
+      uint32_t ph = 1;
       for (int it = 0; it < nch; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
+        if (++s == stages || it == 0) {
+          s = 0;
+          ph ^= 1;
+        }
         mbar_wait(&empty_bar[s], ph ^ 1, 11);
         const long ch = c_begin + it;
         const int g = (int)(ch / cpg);
@@ -858,43 +897,47 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
-      const uint64_t dconst = desc_hi_bits<1>(TN_KR * 128, 512);
-      const uint32_t tiles_u32 = smem_u32(tiles);
-      for (int f = 0; f < nflush; ++f) {
-        const uint32_t b = f & 1, aph = (f >> 1) & 1;
-        mbar_wait(&acc_empty[b], aph ^ 1, 14);
+    // converged warp, elected issue (see umma_tf32_w)
+    constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
+    const uint64_t dconst = desc_hi_bits<1>(TN_KR * 128, 512);
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int f = 0; f < nflush; ++f) {
+      const uint32_t b = f & 1, aph = (f >> 1) & 1;
+      mbar_wait(&acc_empty[b], aph ^ 1, 14);
+      tc_fence_after();
+      const uint32_t d_tmem = tm0 + b * BN;
+      const int it_lo = f * flush_ch;
+      const int it_hi = (it_lo + flush_ch < nch) ? it_lo + flush_ch : nch;
+      for (int it = it_lo; it < it_hi; ++it) {
+        mbar_wait(&full_bar[s], ph, 12);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + b * BN;
-        const int it_lo = f * flush_ch;
-        const int it_hi = (it_lo + flush_ch < nch) ? it_lo + flush_ch : nch;
-        for (int it = it_lo; it < it_hi; ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(&full_bar[s], ph, 12);
-          tc_fence_after();
-          const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
-          const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
-          const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
-          const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
-          const uint32_t first = (it == it_lo) ? 0u : 1u;
+        const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
+        const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
+        const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
+        const uint32_t first = (it == it_lo) ? 0u : 1u;
 #pragma unroll
-          for (int k = 0; k < TN_KR / UMMA_K; ++k) {
-            const uint32_t acc = (k == 0) ? first : 1u;
-            const uint32_t o = k * (1024 >> 4);          // 8 k-rows of 128 B
-            if (SPLIT) {
-              umma_tf32(d_tmem, dal + o, dbh + o, idesc, acc);
-              umma_tf32(d_tmem, dah + o, dbl + o, idesc, 1);
-              umma_tf32(d_tmem, dah + o, dbh + o, idesc, 1);
-            } else {
-              umma_tf32(d_tmem, dah + o, dbh + o, idesc, acc);
-            }
+        for (int k = 0; k < TN_KR / UMMA_K; ++k) {
+          const uint32_t acc = (k == 0) ? first : 1u;
+          const uint32_t o = k * (1024 >> 4);          // 8 k-rows of 128 B
+          if (SPLIT) {
+            umma_tf32_w(d_tmem, dal + o, dbh + o, idesc, acc);
+            umma_tf32_w(d_tmem, dah + o, dbl + o, idesc, 1);
+            umma_tf32_w(d_tmem, dah + o, dbh + o, idesc, 1);
+          } else {
+            umma_tf32_w(d_tmem, dah + o, dbh + o, idesc, acc);
           }
-          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&acc_full[b]);
+        umma_commit_w(&empty_bar[s]);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
+      umma_commit_w(&acc_full[b]);
     }
     __syncwarp();
   } else {
