@@ -15,13 +15,16 @@ for f in funcs:
         continue
     m = re.search(r"tc_gemm_\w+?_kernelILi(\d+)ELb(\d)E(?:Li(\d+)E)?", name)
     ins = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", l)]
-    ops = [re.sub(r"/\*[0-9a-f]+\*/", "", l).strip().rstrip(";") for l in ins]
+    ops = [re.sub(r"/\*[0-9a-fx ]+\*/", "", l).strip().rstrip("; ") for l in ins]
     mma = [i for i, o in enumerate(ops) if "UTCHMMA" in o]
     if not mma:
         continue
     first = mma[0]
     start = max(i for i in range(first) if "SYNCS.PHASECHK" in ops[i])
-    end = min(i for i in range(mma[-1], len(ops)) if "UTCBAR" in ops[i])
+    # fast (converged) path only: ptxas also emits a BRA.DIV fallback copy further down
+    ends = [i for i in range(first, len(ops)) if "UTCBAR" in ops[i]]
+    end = ends[0] if ends else mma[-1]
+    mma = [i for i in mma if i <= end]
     body = ops[start:end + 1]
     kinds = {}
     for o in body:
