@@ -12,7 +12,8 @@ class GraphedEncoderStep(object):
     given at construction; `loss_fn(y) -> scalar tensor`; the optimizer must be capturable."""
 
     def __init__(self, model, optimizer, loss_fn, shape, device, pre_step=None, post_backward=None,
-                 warmup=3, stream=None, resident=False, x_init=None):
+                 warmup=3, stream=None, resident=False, x_init=None,
+                 capture_error_mode="global"):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.x_static = torch.zeros(shape, dtype=torch.float32, device=device)
         self.x_host = torch.zeros(shape, dtype=torch.float32).pin_memory()
@@ -26,6 +27,9 @@ class GraphedEncoderStep(object):
         # node created on another stream invalidates the capture
         self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
         self.graph = None
+        # "thread_local" when other threads of the process issue CUDA calls during the
+        # capture (e.g. the NCCL process group's watchdog, with a collective in post_backward)
+        self.capture_error_mode = capture_error_mode
         self._capture(warmup)
 
     def _one(self):
@@ -52,7 +56,7 @@ class GraphedEncoderStep(object):
         torch.cuda.current_stream().wait_stream(self.stream)
         self.opt.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=self.stream):
+        with torch.cuda.graph(g, stream=self.stream, capture_error_mode=self.capture_error_mode):
             self._one()
         self.graph = g
 
