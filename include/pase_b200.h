@@ -96,6 +96,14 @@ int pase_conv_w_to_dgrad(const float* W, float* Wd, int Cout, int Cin, int k,
                          int s, int taps, void* stream);
 /* dWt[co, j*Cin+ci] -> dW (Cout,Cin,k)                                      */
 int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, void* stream);
+/* The three re-layouts above for EVERY conv block of a step in one launch (the per-layer
+ * calls are ~4 us each and there are 35 of them per PASE+ step).  table: device array of
+ * njobs x 12 int64 {src, dst, hi, lo, Cout, Cin, k, s, taps, start, count, 0}; start = prefix
+ * sum of count (flat element index space of size total); op 0 = to_fwd, 1 = to_dgrad,
+ * 2 = from_fwd (dst is then an element offset into dst_base).  hi/lo != 0 additionally write
+ * the 3xTF32 weight split (as pase_split_tf32 with an explicit hi).                        */
+int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* dst_base,
+                      void* stream);
 /* ConvTranspose1d weight (Cin,Cout,k) -> Wu[p*Cout+co, v*Cin+ci] =
  * W[ci,co,s*(taps-1-v)+p] or 0 (forward operand of the transposed conv)     */
 int pase_deconv_w_to_fwd(const float* W, float* Wu, int Cin, int Cout, int k,

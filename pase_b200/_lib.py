@@ -22,7 +22,7 @@ _CTYPES = {
     "double": ctypes.c_double,
 }
 _PTR_DTYPES = {"float": torch.float32, "double": torch.float64, "int": torch.int32,
-               "void": None}
+               "long": torch.int64, "void": None}
 
 
 def parse_header(path=HEADER):

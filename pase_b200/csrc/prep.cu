@@ -204,6 +204,68 @@ inline unsigned nblk(long total) {
   return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
+// ---- batched weight re-layout: every conv block of a step in ONE launch ----
+// table: njobs rows of PASE_WJOB longs {src, dst, hi, lo, Cout, Cin, k, s, taps, start, count, 0}
+// (device memory, built once per buffer plan).  op 0: to_fwd, 1: to_dgrad, 2: from_fwd (dst is
+// an element offset into dst_base, the per-call gradient buffer).  hi/lo != 0: also write the
+// 3xTF32 weight split hi = rn_tf32(v), lo = rn_tf32(v - hi) (as pase_split_tf32 does).
+constexpr int WJOB = 12;
+constexpr int WJOB_MAX = 32;
+
+__device__ __forceinline__ float w_tf32_rn(float v) {
+  uint32_t u = __float_as_uint(v);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+
+__global__ void conv_w_batch_kernel(const long* __restrict__ table, int njobs, long total, int op,
+                                    float* __restrict__ dst_base) {
+  __shared__ long jt[WJOB_MAX * WJOB];
+  for (int i = threadIdx.x; i < njobs * WJOB; i += blockDim.x) jt[i] = table[i];
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    int j = 0;
+    while (j + 1 < njobs && i >= jt[(j + 1) * WJOB + 9]) ++j;
+    const long* J = jt + j * WJOB;
+    const float* src = reinterpret_cast<const float*>(J[0]);
+    float* dst = (op == 2) ? dst_base + J[1] : reinterpret_cast<float*>(J[1]);
+    float* hi = reinterpret_cast<float*>(J[2]);
+    float* lo = reinterpret_cast<float*>(J[3]);
+    const int Cout = (int)J[4], Cin = (int)J[5], k = (int)J[6], sd = (int)J[7], taps = (int)J[8];
+    const long e = i - J[9];
+    float v;
+    if (op == 0) {                     // e indexes Wt: [co][j][ci]
+      const int ci = (int)(e % Cin);
+      const long r = e / Cin;
+      const int jj = (int)(r % k);
+      const int co = (int)(r / k);
+      v = src[((long)co * Cin + ci) * k + jj];
+    } else if (op == 1) {              // e indexes Wd: [p][ci][v][co]
+      const int co = (int)(e % Cout);
+      long r = e / Cout;
+      const int vv = (int)(r % taps);
+      r /= taps;
+      const int ci = (int)(r % Cin);
+      const int pp = (int)(r / Cin);
+      const int jj = sd * (taps - 1 - vv) + pp;
+      v = (jj < k) ? src[((long)co * Cin + ci) * k + jj] : 0.f;
+    } else {                           // e indexes dW: [co][ci][j]
+      const int jj = (int)(e % k);
+      const long r = e / k;
+      const int ci = (int)(r % Cin);
+      const int co = (int)(r / Cin);
+      v = src[((long)co * k + jj) * Cin + ci];
+    }
+    dst[e] = v;
+    if (hi != nullptr) {
+      const float h = w_tf32_rn(v);
+      hi[e] = h;
+      lo[e] = w_tf32_rn(v - h);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -221,6 +283,18 @@ int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, 
   conv_w_from_fwd_kernel<<<nblk((long)Cout * Cin * k), 256, 0, (cudaStream_t)stream>>>(
       dWt, dW, Cout, Cin, k);
   PASE_LAUNCH_CHECK("pase_conv_w_from_fwd");
+  return PASE_OK;
+}
+
+int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* dst_base,
+                      void* stream) {
+  PASE_CHECK_ARG(table && njobs > 0 && njobs <= WJOB_MAX && total > 0,
+                 "pase_conv_w_batch: bad args (njobs=%d, at most %d)", njobs, WJOB_MAX);
+  PASE_CHECK_ARG(op >= 0 && op <= 2 && (op != 2 || dst_base != nullptr),
+                 "pase_conv_w_batch: op=%d (0 to_fwd, 1 to_dgrad, 2 from_fwd + dst_base)", op);
+  conv_w_batch_kernel<<<nblk(total), 256, 0, (cudaStream_t)stream>>>(table, njobs, total, op,
+                                                                    dst_base);
+  PASE_LAUNCH_CHECK("pase_conv_w_batch");
   return PASE_OK;
 }
 

@@ -114,6 +114,7 @@ class EncoderPlan(object):
             raise ValueError("precision must be one of %s" % (sorted(PRECISIONS),))
         self.prec, self.mode = prec, PRECISIONS[prec]
         self._twins = {}
+        self._wtables = {}
         self.geoms = build_geometry(cfg, T, TC_SINC_FOLD if self.mode is not None else SINC_FOLD)
         G = self.geoms
         self.nblk = len(G)
@@ -218,6 +219,34 @@ class EncoderPlan(object):
             ops.call("pase_split_tf32", buf, tw[0], tw[1], buf.numel())
         return (tw[0] if weights else buf), tw[1]
 
+    def twins_w(self, name, buf):
+        """(hi, lo) twin buffers of a weight operand for producers that write the split
+        themselves (pase_conv_w_batch); (None, None) outside 3xTF32 mode."""
+        if self.mode != 1:
+            return None, None
+        tw = self._twins.get(name)
+        if tw is None or tw[0] is None or tw[1].numel() != buf.numel():
+            tw = (torch.zeros_like(buf), torch.zeros_like(buf))
+            self._twins[name] = tw
+        return tw
+
+    def w_batch(self, op, jobs, dst_base=None):
+        """One launch for the weight re-layouts of every conv block (pase_conv_w_batch).
+        jobs: [(src, dst tensor | element offset, hi, lo, Cout, Cin, k, s, taps, count)].
+        The device job table is rebuilt only when a pointer changed."""
+        ptr = lambda t: 0 if t is None else (t if isinstance(t, int) else t.data_ptr())
+        rows, start = [], 0
+        for (src, dst, hi, lo, Cout, Cin, k, sd, taps, count) in jobs:
+            rows.append([ptr(src), ptr(dst), ptr(hi), ptr(lo), Cout, Cin, k, sd, taps, start,
+                         count, 0])
+            start += count
+        ent = self._wtables.get(op)
+        if ent is None or ent[0] != rows:
+            table = torch.tensor(rows, dtype=torch.int64).reshape(-1).to(self.device)
+            ent = (rows, table)
+            self._wtables[op] = ent
+        ops.call("pase_conv_w_batch", ent[1], len(rows), start, op, dst_base)
+
     def lo_of(self, name, buf):
         """Residual twin of an activation operand, for producers that write it themselves
         (mode 1 only; zero-initialised so halos / slack stay valid)."""
@@ -303,6 +332,17 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
     if plan.skips:
         plan.cat.zero_()
 
+    # GEMM operands (+ 3xTF32 split) of every conv block's weight: one launch
+    jobs = []
+    for l, g in enumerate(G):
+        if not g.sinc:
+            hi, lo = plan.twins_w(("Wt", l), plan.Wt[l])
+            jobs.append((P("blocks.%d.conv.weight" % l), plan.Wt[l], hi, lo, g.Cout, g.Cin, g.k,
+                         1, 1, g.Cout * g.Cin * g.k))
+    if jobs:
+        plan.w_batch(0, jobs)
+    counters = []
+
     for l, g in enumerate(G):
         pre = "blocks.%d." % l
         if g.sinc:
@@ -311,14 +351,13 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
                  50.0, 50.0, float(cfg["sr"]))
             bias = None
         else:
-            call("pase_conv_w_to_fwd", P(pre + "conv.weight"), plan.Wt[l], g.Cout, g.Cin, g.k)
             bias = P(pre + "conv.bias")
         if training:
             o = plan.fs_off[l]
             cs, cq = plan.stats_f[o:o + g.Nn], plan.stats_f[o + g.Nn:o + 2 * g.Nn]
         else:
             cs = cq = None
-        plan.nt(("apad", l), plan.apad[l], g.lda, l == 0, ("Wt", l), plan.Wt[l], g.K, True,
+        plan.nt(("apad", l), plan.apad[l], g.lda, l == 0, ("Wt", l), plan.Wt[l], g.K, g.sinc,
                 plan.y[l], g.Nn, N * g.P, g.Nn, g.K, 1.0, bias, g.P, g.T_out, g.rows_out,
                 g.fold, cs, cq, 0)
         mean, invstd, scale, shift = plan.bn[l][0], plan.bn[l][1], plan.bn[l][2], plan.bn[l][3]
@@ -327,7 +366,7 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
                  P(pre + "norm.weight"), P(pre + "norm.bias"),
                  buf(pre + "norm.running_mean"), buf(pre + "norm.running_var"),
                  BN_MOMENTUM, BN_EPS, mean, invstd, scale, shift)
-            mod.get_buffer(pre + "norm.num_batches_tracked").add_(1)
+            counters.append(mod.get_buffer(pre + "norm.num_batches_tracked"))
         else:
             call("pase_bn_eval_affine", buf(pre + "norm.running_mean"),
                  buf(pre + "norm.running_var"), P(pre + "norm.weight"), P(pre + "norm.bias"),
@@ -381,11 +420,13 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
             call("pase_bn_finalize", cs, cq, emb, 1, float(rows), None, None,
                  buf("norm_out.running_mean"), buf("norm_out.running_var"),
                  BN_MOMENTUM, BN_EPS, bo[0], bo[1], bo[2], bo[3])
-            mod.get_buffer("norm_out.num_batches_tracked").add_(1)
+            counters.append(mod.get_buffer("norm_out.num_batches_tracked"))
         else:
             call("pase_bn_eval_affine", buf("norm_out.running_mean"),
                  buf("norm_out.running_var"), None, None, emb, BN_EPS,
                  bo[0], bo[1], bo[2], bo[3])
+    if counters:                                 # BatchNorm step counters: one launch
+        torch._foreach_add_(counters, 1)
     out = torch.empty(N, emb, Tq, dtype=torch.float32, device=x.device)
     out_ntc = torch.empty(rows, emb, dtype=torch.float32, device=x.device)
     call("pase_out_affine_nct", plan.yout, bo[2], bo[3], out.reshape(-1), out_ntc.reshape(-1),
@@ -403,6 +444,15 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
     grads = {}
     sb = plan.stats_b
     sb.zero_()
+    # dgrad operands (+ split) of every conv block with an input gradient: one launch
+    jobs = []
+    for l, g in enumerate(G):
+        if not g.sinc and l > 0:
+            hi, lo = plan.twins_w(("Wd", l), plan.Wd[l])
+            jobs.append((P("blocks.%d.conv.weight" % l), plan.Wd[l], hi, lo, g.Cout, g.Cin, g.k,
+                         g.s, g.taps, g.s * g.Cin * g.taps * g.Cout))
+    if jobs:
+        plan.w_batch(1, jobs)
     zeros = plan.zeros64
     bo = plan.bn_out
     o = plan.bs_out
@@ -498,30 +548,41 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
         else:
             plan.tn(("dyz", l), plan.dyz[l], C, g.Pd, g.taps - 1, False, ("apad", l), plan.apad[l],
                     g.lda, g.P, False, plan.dWt[l], g.K, C, g.K, N, g.T_out, 1.0, 0)
-            dW = torch.empty_like(params[pre + "conv.weight"])
-            call("pase_conv_w_from_fwd", plan.dWt[l], dW.reshape(-1), g.Cout, g.Cin, g.k)
-            grads[pre + "conv.weight"] = dW
             if l > 0:
-                call("pase_conv_w_to_dgrad", P(pre + "conv.weight"), plan.Wd[l], g.Cout, g.Cin,
-                     g.k, g.s, g.taps)
-                plan.nt(("dyz", l), plan.dyz[l], C, False, ("Wd", l), plan.Wd[l], g.taps * C, True,
+                plan.nt(("dyz", l), plan.dyz[l], C, False, ("Wd", l), plan.Wd[l], g.taps * C, False,
                         plan.dxpad[l], g.s * g.Cin, N * g.Pd, g.s * g.Cin, g.taps * C, 1.0, None,
                         g.Pd, g.P, g.P, 1, None, None, 0)
 
-    # one cast for every small reduction (double accumulators -> fp32 gradients)
-    call("pase_cast_d2f", sb, plan.grad_vec, sb.numel(), 1.0)
-    gv = plan.grad_vec
+    # conv weight gradients: GEMM layout -> parameter layout for every block in one launch,
+    # into one per-call buffer (the gradients handed to autograd are views of it)
+    jobs, off = [], 0
+    for l, g in enumerate(G):
+        if not g.sinc:
+            cnt = g.Cout * g.Cin * g.k
+            jobs.append((plan.dWt[l], off, None, None, g.Cout, g.Cin, g.k, 1, 1, cnt))
+            off += cnt
+    if jobs:
+        dWflat = torch.empty(off, dtype=torch.float32, device=plan.device)
+        plan.w_batch(2, jobs, dWflat)
+        for (_, o, _, _, Cout, Cin, k, _, _, cnt), l in zip(jobs, [l for l, g in enumerate(G)
+                                                                  if not g.sinc]):
+            grads["blocks.%d.conv.weight" % l] = dWflat[o:o + cnt].view(Cout, Cin, k)
+
+    # one cast for every small reduction (double accumulators -> fp32 gradients) into a
+    # per-call vector; the per-parameter gradients are views of it (no copies)
+    gv = torch.empty_like(plan.grad_vec)
+    call("pase_cast_d2f", sb, gv, sb.numel(), 1.0)
     for l, g in enumerate(G):
         C, o = g.Cout, plan.bs_off[l]
         pre = "blocks.%d." % l
-        grads[pre + "norm.bias"] = gv[o:o + C].clone()
-        grads[pre + "norm.weight"] = gv[o + C:o + 2 * C].clone()
-        grads[pre + "act.weight"] = gv[o + 2 * C:o + 3 * C].clone()
+        grads[pre + "norm.bias"] = gv[o:o + C]
+        grads[pre + "norm.weight"] = gv[o + C:o + 2 * C]
+        grads[pre + "act.weight"] = gv[o + 2 * C:o + 3 * C]
         if not g.sinc:
-            grads[pre + "conv.bias"] = gv[o + 3 * C:o + 4 * C].clone()
-    grads["W.bias"] = gv[plan.bs_bw:plan.bs_bw + emb].clone()
+            grads[pre + "conv.bias"] = gv[o + 3 * C:o + 4 * C]
+    grads["W.bias"] = gv[plan.bs_bw:plan.bs_bw + emb]
     if plan.rnn:
-        grads["rnn.layers.0.linear.bias"] = gv[plan.bs_bq:plan.bs_bq + 3 * plan.H].clone()
+        grads["rnn.layers.0.linear.bias"] = gv[plan.bs_bq:plan.bs_bq + 3 * plan.H]
     return grads
 
 

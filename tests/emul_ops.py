@@ -391,6 +391,35 @@ def pase_scale_dev(x, n, dev_scalar, host_coef):
     x[:n] *= (float(dev_scalar[0]) if dev_scalar is not None else 1.0) * host_coef
 
 
+def _host_view(ptr, n):
+    """Float32 view of n elements at a HOST address (the emulation's stand-in for a device
+    pointer stored in a job table); shares memory with the tensor that owns the address."""
+    import ctypes
+    import numpy as np
+    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr)))
+
+
+def pase_conv_w_batch(table, njobs, total, op, dst_base):
+    t = table.reshape(njobs, 12).tolist()
+    done = 0
+    for (src, dst, hi, lo, Cout, Cin, k, sd, taps, start, count, _) in t:
+        assert start == done
+        n_w = Cout * Cin * k
+        if op == 2:
+            out = dst_base[dst:dst + count]
+            pase_conv_w_from_fwd(_host_view(src, n_w), out, Cout, Cin, k)
+        else:
+            out = _host_view(dst, count)
+            if op == 0:
+                pase_conv_w_to_fwd(_host_view(src, n_w), out, Cout, Cin, k)
+            else:
+                pase_conv_w_to_dgrad(_host_view(src, n_w), out, Cout, Cin, k, sd, taps)
+        if hi:
+            pase_split_tf32(out, _host_view(hi, count), _host_view(lo, count), count)
+        done += count
+    assert done == total
+
+
 def call(name, *args):
     fn = globals().get(name)
     if fn is None:

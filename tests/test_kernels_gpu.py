@@ -231,3 +231,61 @@ def test_error_reporting():
                   torch.zeros(64).cuda(), 4, 4, 4, 4, 1.0, None, 4, 4, 4, 1, None, None, 0)
     with pytest.raises(RuntimeError, match="CUDA device"):
         _lib.call("pase_axpy", torch.zeros(4), torch.zeros(4).cuda(), 4, 1.0)
+
+
+@pytest.mark.gpu
+def test_conv_w_batch_matches_per_layer_ops():
+    """pase_conv_w_batch == the per-layer re-layouts (+ explicit-hi TF32 split), bit-exact."""
+    layers = [(64, 64, 20, 10), (128, 64, 11, 2), (128, 128, 11, 1), (24, 12, 5, 2)]
+    dev = torch.device("cuda")
+    Ws = [R(co, ci, k, seed=3 + i).to(dev) for i, (co, ci, k, s) in enumerate(layers)]
+
+    def table(rows):
+        out, start = [], 0
+        for r in rows:
+            out.append(r[:9] + [start, r[9], 0])
+            start += r[9]
+        return torch.tensor(out, dtype=torch.int64, device=dev).reshape(-1), start
+
+    for op in (0, 1):
+        rows, outs, his, los, refs = [], [], [], [], []
+        for W, (co, ci, k, s) in zip(Ws, layers):
+            taps = (k + s - 1) // s
+            cnt = co * ci * k if op == 0 else s * ci * taps * co
+            o, h, l = (torch.full((cnt,), 7.0, device=dev) for _ in range(3))
+            split = (co != 24)                         # last job: no split requested
+            rows.append([W.data_ptr(), o.data_ptr(), h.data_ptr() if split else 0,
+                         l.data_ptr() if split else 0, co, ci, k, s, taps, cnt])
+            ref = torch.empty(cnt, device=dev)
+            if op == 0:
+                _lib.call("pase_conv_w_to_fwd", W.reshape(-1), ref, co, ci, k)
+            else:
+                _lib.call("pase_conv_w_to_dgrad", W.reshape(-1), ref, co, ci, k, s, taps)
+            rh, rl = torch.empty(cnt, device=dev), torch.empty(cnt, device=dev)
+            _lib.call("pase_split_tf32", ref, rh, rl, cnt)
+            outs.append(o); his.append(h if split else None); los.append(l if split else None)
+            refs.append((ref, rh, rl))
+        t, total = table(rows)
+        _lib.call("pase_conv_w_batch", t, len(rows), total, op, None)
+        torch.cuda.synchronize()
+        for o, h, l, (ref, rh, rl) in zip(outs, his, los, refs):
+            assert torch.equal(o, ref)
+            if h is not None:
+                assert torch.equal(h, rh) and torch.equal(l, rl)
+
+    # op 2: GEMM-layout gradients -> parameter layout, into one flat buffer
+    rows, refs, off = [], [], 0
+    srcs = [R(co, k, ci, seed=11 + i).to(dev) for i, (co, ci, k, s) in enumerate(layers)]
+    for S, (co, ci, k, s) in zip(srcs, layers):
+        cnt = co * ci * k
+        rows.append([S.data_ptr(), off, 0, 0, co, ci, k, 1, 1, cnt])
+        ref = torch.empty(cnt, device=dev)
+        _lib.call("pase_conv_w_from_fwd", S.reshape(-1), ref, co, ci, k)
+        refs.append((off, cnt, ref))
+        off += cnt
+    t, total = table(rows)
+    flat = torch.zeros(total, device=dev)
+    _lib.call("pase_conv_w_batch", t, len(rows), total, 2, flat)
+    torch.cuda.synchronize()
+    for o, cnt, ref in refs:
+        assert torch.equal(flat[o:o + cnt], ref)
