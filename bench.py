@@ -357,12 +357,16 @@ def run_native(args):
     launches_per_step = ops.launch_count - n0
     value_fn, value_graphed = step_resident, False
     gopt = None
-    if world == 1 and not args.no_graph:
+    # N>1: two captured halves ([fwd, bwd, pack gradients] and [Adam]) with the NCCL
+    # all-reduce of the flat gradient buffer issued eagerly between the two replays
+    gkw = dict(post_backward=red.pack, between=red.all_reduce) if world > 1 else {}
+    if not args.no_graph:
         try:
             from pase_b200.graph import GraphedEncoderStep
             gopt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
             gres = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
-                                      (B_PER_GPU, 1, T_CHUNK), dev, stream=side, resident=True)
+                                      (B_PER_GPU, 1, T_CHUNK), dev, stream=side, resident=True,
+                                      **gkw)
             gres.x_static.copy_(x_dev)
             value_fn, value_graphed = (lambda: gres.step()), True
             for _ in range(3):
@@ -378,15 +382,16 @@ def run_native(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
-    # end-to-end: through the public API with pinned HOST waveforms; at N=1 the whole step
-    # (H2D, fwd, bwd, Adam, D2H of the loss) is captured in one CUDA graph when possible
+    # end-to-end: through the public API with pinned HOST waveforms; the whole step (H2D, fwd,
+    # bwd, Adam, D2H of the loss) is captured in one CUDA graph (N>1: two, around the
+    # all-reduce) when possible
     graphed, e2e_fn = False, step_e2e
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             from pase_b200.graph import GraphedEncoderStep
             gopt = gopt or torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
             gs = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
-                                    (B_PER_GPU, 1, T_CHUNK), dev, stream=side)
+                                    (B_PER_GPU, 1, T_CHUNK), dev, stream=side, **gkw)
             gs.x_host.copy_(x_host)                   # the loader's pinned staging buffer
             e2e_fn = lambda: gs.step()
             graphed = True

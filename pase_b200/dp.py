@@ -50,6 +50,22 @@ class FlatGradAllReducer(object):
         self._reduce()
         return self.flat
 
+    def pack(self):
+        """Pack freshly produced gradients into the flat buffer and re-point ``.grad`` at
+        its views, without the collective (``all_reduce()`` follows; used when the two are
+        separated by a CUDA-graph boundary)."""
+        srcs, dsts = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                srcs.append(p.grad)
+                dsts.append(v)
+        if srcs:
+            torch._foreach_copy_(dsts, srcs)
+        self.attach()
+        return self.flat
+
     def pack_and_reduce(self):
         """Pack freshly produced gradients (``.grad`` not views), reduce, re-point ``.grad``."""
         srcs, dsts = [], []

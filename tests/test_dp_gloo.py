@@ -38,6 +38,13 @@ def _worker(rank, world, port, out):
     red.pack_and_reduce()
     assert torch.allclose(red.flat, first, rtol=1e-6, atol=1e-8)
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
+    # third protocol (CUDA-graph boundary between the two): pack(), then all_reduce()
+    red.detach()
+    model(x).square().mean().backward()
+    red.pack()
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
+    red.all_reduce()
+    assert torch.allclose(red.flat, first, rtol=1e-6, atol=1e-8)
     torch.save(red.flat.clone(), os.path.join(out, "g%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()

@@ -16,7 +16,11 @@ def _model(seed):
     return m.cuda().train()
 
 
-def test_graphed_step_matches_eager():
+@pytest.mark.parametrize("split", [False, True])
+def test_graphed_step_matches_eager(split):
+    """split=True: the data-parallel form -- [forward, backward, pack gradients into the flat
+    buffer] and [optimizer] are two graphs with an eager hook (the all-reduce; a no-op
+    collective in a single process) between their replays."""
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     try:
@@ -38,8 +42,14 @@ def test_graphed_step_matches_eager():
         # graphed: 3 warm-up updates inside the constructor, capture (1 update), then 1 replay
         mg = _model(3)
         og = torch.optim.SGD(mg.parameters(), lr=1e-2, momentum=0.9, foreach=True)
+        kw = {}
+        if split:
+            from pase_b200.dp import FlatGradAllReducer
+            red = FlatGradAllReducer(list(mg.parameters()), attach=False)
+            kw = dict(post_backward=red.pack, between=red.all_reduce)
         gs = GraphedEncoderStep(mg, og, loss_fn, (4, 1, 6400), "cuda", stream=side, warmup=3,
-                                x_init=x)
+                                x_init=x, **kw)
+        assert (gs.graph_b is not None) == split
         # the capture itself does not execute; replays do
         l1 = gs.step()
         l2 = gs.step()
