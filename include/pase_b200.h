@@ -101,7 +101,10 @@ int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, 
  * njobs x 12 int64 {src, dst, hi, lo, Cout, Cin, k, s, taps, start, count, 0}; start = prefix
  * sum of count (flat element index space of size total); op 0 = to_fwd, 1 = to_dgrad,
  * 2 = from_fwd (dst is then an element offset into dst_base).  hi/lo != 0 additionally write
- * the 3xTF32 weight split (as pase_split_tf32 with an explicit hi).                        */
+ * the 3xTF32 weight split (as pase_split_tf32 with an explicit hi).  op 3..5 = the same
+ * three through shared-memory tiles (coalesced reads and writes): `total` is then the number
+ * of thread blocks, table[.., 11] the job's first block; blocks per job = Cout (ops 3, 5) or
+ * (Cout/32)*(Cin/8) (op 4); needs Cout % 32 == 0, Cin % 8 == 0 and (Cin+1)*k <= 12000.    */
 int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* dst_base,
                       void* stream);
 /* ConvTranspose1d weight (Cin,Cout,k) -> Wu[p*Cout+co, v*Cin+ci] =

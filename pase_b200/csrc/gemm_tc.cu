@@ -63,6 +63,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
   }
 }
+// Epilogue warps wait for a whole accumulator chunk (thousands of cycles): an optional
+// back-off between polls leaves the issue slots of their scheduler to the MMA / TMA warps.
+// PASE_B200_EPI_SLEEP_NS (read once on the host) sets it; 0 = plain polling.
+__constant__ int c_epi_sleep_ns = 0;
+__device__ __forceinline__ void mbar_wait_epi(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t spins = 0;
+  const int ns = c_epi_sleep_ns;
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns > 0) __nanosleep(ns);
+    if (++spins > SPIN_LIMIT) {
+      printf("pase tc gemm: mbarrier wait timed out (tag %d, block %d,%d,%d thread %d)\n", tag,
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -450,7 +466,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         float sums[Cfg::CPW][32];
         for (int ch = 0; ch < nchunks; ++ch, ++c) {
           const uint32_t b = c & 1, aph = (c >> 1) & 1;
-          mbar_wait(&acc_full[b], aph, 3);
+          mbar_wait_epi(&acc_full[b], aph, 3);
           tc_fence_after();
 #pragma unroll
           for (int h = 0; h < Cfg::CPW; ++h) {
@@ -718,7 +734,7 @@ tc_gemm_ntw_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
         float sums[32];
         for (int ch = 0; ch < nchunks; ++ch, ++c) {
           const uint32_t b = c & 1, aph = (c >> 1) & 1;
-          mbar_wait(&acc_full[b], aph, 3);
+          mbar_wait_epi(&acc_full[b], aph, 3);
           tc_fence_after();
           uint32_t raw[32];
           tmem_ld32(taddr + b * BN, raw);
@@ -949,7 +965,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       float sums[32];
       for (int f = 0; f < nflush; ++f) {
         const uint32_t b = f & 1, aph = (f >> 1) & 1;
-        mbar_wait(&acc_full[b], aph, 13);
+        mbar_wait_epi(&acc_full[b], aph, 13);
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld32(taddr + b * BN, raw);
@@ -990,6 +1006,16 @@ static bool pase_tc_use_window() {
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v != 0;
+}
+
+// one-time upload of the epilogue poll back-off (default 0 = plain polling)
+static void pase_tc_init_epi_sleep() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = getenv("PASE_B200_EPI_SLEEP_NS");
+  const int ns = e ? atoi(e) : 0;
+  if (ns > 0) cudaMemcpyToSymbol(c_epi_sleep_ns, &ns, sizeof(int));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1220,6 +1246,7 @@ int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, cons
                     int fold, double* colsum, double* colsumsq, int accumulate, int mode,
                     void* stream) {
   PASE_CHECK_ARG(Ahi && Bhi && C && M > 0 && N > 0 && K > 0, "pase_tc_gemm_nt: bad args");
+  pase_tc_init_epi_sleep();
   PASE_CHECK_ARG(mode == 0 || (Alo && Blo), "pase_tc_gemm_nt: mode 1 needs lo operands");
   PASE_CHECK_ARG(R >= 32 && (R % 32) == 0, "pase_tc_gemm_nt: R=%d must be a multiple of 32", R);
   PASE_CHECK_ARG((K % 4) == 0 && (ldb % 4) == 0 && ldb >= K, "pase_tc_gemm_nt: K/ldb alignment");
@@ -1293,6 +1320,7 @@ int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, in
                     int accumulate, int mode, void* stream) {
   PASE_CHECK_ARG(Ahi && Bhi && C && I > 0 && J > 0 && groups > 0 && rows_per_group > 0,
                  "pase_tc_gemm_tn: bad args");
+  pase_tc_init_epi_sleep();
   PASE_CHECK_ARG(mode == 0 || (Alo && Blo), "pase_tc_gemm_tn: mode 1 needs lo operands");
   PASE_CHECK_ARG(R >= 32 && (R % 32) == 0 && (lda % 4) == 0 && (I % 4) == 0 && (J % 32) == 0,
                  "pase_tc_gemm_tn: need R%%32==0, lda%%4==0, I%%4==0, J%%32==0 (R=%d lda=%ld I=%d "

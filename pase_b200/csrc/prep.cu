@@ -266,6 +266,79 @@ __global__ void conv_w_batch_kernel(const long* __restrict__ table, int njobs, l
   }
 }
 
+// Tiled variants (ops 3..5 = 0..2 through shared memory, coalesced on both sides; the gather
+// forms above read W with a stride of k floats).  table[.., 11] = first thread block of the
+// job; blocks per job: Cout (ops 3, 5: one output-channel slab of Cin*k floats each) or
+// (Cout/32)*(Cin/WB_CI) (op 4: 32 output channels x WB_CI input channels).
+constexpr int WB_CI = 8;
+constexpr int WB_SMEM_FLOATS = 12000;          // 46.9 KB (+ the static job row < 48 KB)
+
+__device__ __forceinline__ void w_store(float* dst, float* hi, float* lo, long e, float v) {
+  dst[e] = v;
+  if (hi != nullptr) {
+    const float h = w_tf32_rn(v);
+    hi[e] = h;
+    lo[e] = w_tf32_rn(v - h);
+  }
+}
+
+__global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int njobs, int op,
+                                          float* __restrict__ dst_base) {
+  extern __shared__ float tile[];
+  __shared__ long J[WJOB];
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < njobs && (long)blockIdx.x >= table[(j + 1) * WJOB + 11]) ++j;
+    for (int i = 0; i < WJOB; ++i) J[i] = table[j * WJOB + i];
+  }
+  __syncthreads();
+  const float* src = reinterpret_cast<const float*>(J[0]);
+  float* dst = (op == 5) ? dst_base + J[1] : reinterpret_cast<float*>(J[1]);
+  float* hi = reinterpret_cast<float*>(J[2]);
+  float* lo = reinterpret_cast<float*>(J[3]);
+  const int Cout = (int)J[4], Cin = (int)J[5], k = (int)J[6], sd = (int)J[7], taps = (int)J[8];
+  const int b = (int)((long)blockIdx.x - J[11]);
+  if (op == 3) {                       // Wt[co][j][ci] = W[co][ci][j]
+    const int n = Cin * k;
+    const float* w = src + (long)b * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = w[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int ci = e % Cin, jj = e / Cin;
+      w_store(dst, hi, lo, (long)b * n + e, tile[ci * k + jj]);
+    }
+  } else if (op == 5) {                // dW[co][ci][j] = dWt[co][j][ci]
+    const int n = Cin * k, pitch = Cin + 1;
+    const float* w = src + (long)b * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[(i / Cin) * pitch + (i % Cin)] = w[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int jj = e % k, ci = e / k;
+      dst[(long)b * n + e] = tile[jj * pitch + ci];
+    }
+  } else {                             // Wd[p][ci][v][co] = W[co][ci][sd*(taps-1-v)+p] | 0
+    const int nci = Cin / WB_CI;
+    const int co0 = (b / nci) * 32, ci0 = (b % nci) * WB_CI;
+    const int seg = WB_CI * k, pitch = seg + 1;
+    for (int i = threadIdx.x; i < 32 * seg; i += blockDim.x) {
+      const int col = i / seg, r = i % seg;
+      tile[col * pitch + r] = src[((long)(co0 + col) * Cin + ci0) * k + r];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int nrow = sd * WB_CI * taps;            // output rows of 32 consecutive co
+    for (int r = threadIdx.x >> 5; r < nrow; r += nwarp) {
+      const int v = r % taps;
+      const int cl = (r / taps) % WB_CI;
+      const int pp = r / (taps * WB_CI);
+      const int jj = sd * (taps - 1 - v) + pp;
+      const float val = (jj < k) ? tile[lane * pitch + cl * k + jj] : 0.f;
+      const long e = (((long)pp * Cin + ci0 + cl) * taps + v) * Cout + co0 + lane;
+      w_store(dst, hi, lo, e, val);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -290,8 +363,18 @@ int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* d
                       void* stream) {
   PASE_CHECK_ARG(table && njobs > 0 && njobs <= WJOB_MAX && total > 0,
                  "pase_conv_w_batch: bad args (njobs=%d, at most %d)", njobs, WJOB_MAX);
-  PASE_CHECK_ARG(op >= 0 && op <= 2 && (op != 2 || dst_base != nullptr),
-                 "pase_conv_w_batch: op=%d (0 to_fwd, 1 to_dgrad, 2 from_fwd + dst_base)", op);
+  PASE_CHECK_ARG(op >= 0 && op <= 5 && ((op % 3) != 2 || dst_base != nullptr),
+                 "pase_conv_w_batch: op=%d (0 to_fwd, 1 to_dgrad, 2 from_fwd + dst_base; 3..5 "
+                 "tiled)", op);
+  if (op >= 3) {
+    // tiled: `total` thread blocks, 48 KB of shared memory (the caller guarantees that a
+    // slab fits: (Cin+1)*k resp. 32*(8*k+1) floats <= 12000, Cout % 32 == 0, Cin % 8 == 0)
+    PASE_CHECK_ARG(total < (1L << 31), "pase_conv_w_batch: too many blocks");
+    conv_w_batch_tiled_kernel<<<(unsigned)total, 256, WB_SMEM_FLOATS * sizeof(float),
+                                (cudaStream_t)stream>>>(table, njobs, op, dst_base);
+    PASE_LAUNCH_CHECK("pase_conv_w_batch");
+    return PASE_OK;
+  }
   conv_w_batch_kernel<<<nblk(total), 256, 0, (cudaStream_t)stream>>>(table, njobs, total, op,
                                                                     dst_base);
   PASE_LAUNCH_CHECK("pase_conv_w_batch");

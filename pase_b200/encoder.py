@@ -235,17 +235,25 @@ class EncoderPlan(object):
         jobs: [(src, dst tensor | element offset, hi, lo, Cout, Cin, k, s, taps, count)].
         The device job table is rebuilt only when a pointer changed."""
         ptr = lambda t: 0 if t is None else (t if isinstance(t, int) else t.data_ptr())
-        rows, start = [], 0
+        # shared-memory tiled kernels (ops 3..5) when every job fits their tile shapes
+        tiled = all(Cout % 32 == 0 and Cin % 8 == 0 and (Cin + 1) * k <= 12000
+                    and 32 * (8 * k + 1) <= 12000
+                    for (_, _, _, _, Cout, Cin, k, _, _, _) in jobs)
+        rows, start, blocks = [], 0, 0
         for (src, dst, hi, lo, Cout, Cin, k, sd, taps, count) in jobs:
             rows.append([ptr(src), ptr(dst), ptr(hi), ptr(lo), Cout, Cin, k, sd, taps, start,
-                         count, 0])
+                         count, blocks])
             start += count
+            blocks += (Cout // 32) * (Cin // 8) if op == 1 else Cout
         ent = self._wtables.get(op)
         if ent is None or ent[0] != rows:
             table = torch.tensor(rows, dtype=torch.int64).reshape(-1).to(self.device)
             ent = (rows, table)
             self._wtables[op] = ent
-        ops.call("pase_conv_w_batch", ent[1], len(rows), start, op, dst_base)
+        if tiled:
+            ops.call("pase_conv_w_batch", ent[1], len(rows), blocks, op + 3, dst_base)
+        else:
+            ops.call("pase_conv_w_batch", ent[1], len(rows), start, op, dst_base)
 
     def lo_of(self, name, buf):
         """Residual twin of an activation operand, for producers that write it themselves

@@ -400,10 +400,16 @@ def _host_view(ptr, n):
 
 
 def pase_conv_w_batch(table, njobs, total, op, dst_base):
+    """ops 3..5: same results as 0..2 (shared-memory tiled kernels; `total` = thread blocks,
+    table[.., 11] = first block of the job)."""
     t = table.reshape(njobs, 12).tolist()
-    done = 0
-    for (src, dst, hi, lo, Cout, Cin, k, sd, taps, start, count, _) in t:
+    tiled, op = op >= 3, op % 3
+    done = blocks = 0
+    for (src, dst, hi, lo, Cout, Cin, k, sd, taps, start, count, bstart) in t:
         assert start == done
+        if tiled:
+            assert bstart == blocks and Cout % 32 == 0 and Cin % 8 == 0
+            blocks += (Cout // 32) * (Cin // 8) if op == 1 else Cout
         n_w = Cout * Cin * k
         if op == 2:
             out = dst_base[dst:dst + count]
@@ -417,7 +423,7 @@ def pase_conv_w_batch(table, njobs, total, op, dst_base):
         if hi:
             pase_split_tf32(out, _host_view(hi, count), _host_view(lo, count), count)
         done += count
-    assert done == total
+    assert (blocks if tiled else done) == total
 
 
 def call(name, *args):

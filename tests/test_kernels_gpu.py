@@ -234,18 +234,24 @@ def test_error_reporting():
 
 
 @pytest.mark.gpu
-def test_conv_w_batch_matches_per_layer_ops():
-    """pase_conv_w_batch == the per-layer re-layouts (+ explicit-hi TF32 split), bit-exact."""
-    layers = [(64, 64, 20, 10), (128, 64, 11, 2), (128, 128, 11, 1), (24, 12, 5, 2)]
+@pytest.mark.parametrize("tiled", [False, True])
+def test_conv_w_batch_matches_per_layer_ops(tiled):
+    """pase_conv_w_batch == the per-layer re-layouts (+ explicit-hi TF32 split), bit-exact;
+    tiled: the shared-memory variants (ops 3..5)."""
+    layers = [(64, 64, 20, 10), (128, 64, 11, 2), (128, 128, 11, 1)]
+    layers += [(512, 256, 11, 2), (32, 8, 3, 1)] if tiled else [(24, 12, 5, 2)]
+    nosplit = layers[-1][0]
     dev = torch.device("cuda")
     Ws = [R(co, ci, k, seed=3 + i).to(dev) for i, (co, ci, k, s) in enumerate(layers)]
 
-    def table(rows):
-        out, start = [], 0
+    def table(rows, op):
+        out, start, blocks = [], 0, 0
         for r in rows:
-            out.append(r[:9] + [start, r[9], 0])
+            out.append(r[:9] + [start, r[9], blocks])
             start += r[9]
-        return torch.tensor(out, dtype=torch.int64, device=dev).reshape(-1), start
+            blocks += (r[4] // 32) * (r[5] // 8) if op == 1 else r[4]
+        t = torch.tensor(out, dtype=torch.int64, device=dev).reshape(-1)
+        return (t, blocks, op + 3) if tiled else (t, start, op)
 
     for op in (0, 1):
         rows, outs, his, los, refs = [], [], [], [], []
@@ -253,7 +259,7 @@ def test_conv_w_batch_matches_per_layer_ops():
             taps = (k + s - 1) // s
             cnt = co * ci * k if op == 0 else s * ci * taps * co
             o, h, l = (torch.full((cnt,), 7.0, device=dev) for _ in range(3))
-            split = (co != 24)                         # last job: no split requested
+            split = (co != nosplit)                    # last job: no split requested
             rows.append([W.data_ptr(), o.data_ptr(), h.data_ptr() if split else 0,
                          l.data_ptr() if split else 0, co, ci, k, s, taps, cnt])
             ref = torch.empty(cnt, device=dev)
@@ -263,10 +269,12 @@ def test_conv_w_batch_matches_per_layer_ops():
                 _lib.call("pase_conv_w_to_dgrad", W.reshape(-1), ref, co, ci, k, s, taps)
             rh, rl = torch.empty(cnt, device=dev), torch.empty(cnt, device=dev)
             _lib.call("pase_split_tf32", ref, rh, rl, cnt)
-            outs.append(o); his.append(h if split else None); los.append(l if split else None)
+            outs.append(o)
+            his.append(h if split else None)
+            los.append(l if split else None)
             refs.append((ref, rh, rl))
-        t, total = table(rows)
-        _lib.call("pase_conv_w_batch", t, len(rows), total, op, None)
+        t, total, opc = table(rows, op)
+        _lib.call("pase_conv_w_batch", t, len(rows), total, opc, None)
         torch.cuda.synchronize()
         for o, h, l, (ref, rh, rl) in zip(outs, his, los, refs):
             assert torch.equal(o, ref)
@@ -283,9 +291,9 @@ def test_conv_w_batch_matches_per_layer_ops():
         _lib.call("pase_conv_w_from_fwd", S.reshape(-1), ref, co, ci, k)
         refs.append((off, cnt, ref))
         off += cnt
-    t, total = table(rows)
-    flat = torch.zeros(total, device=dev)
-    _lib.call("pase_conv_w_batch", t, len(rows), total, 2, flat)
+    t, total, opc = table(rows, 2)
+    flat = torch.zeros(off, device=dev)
+    _lib.call("pase_conv_w_batch", t, len(rows), total, opc, flat)
     torch.cuda.synchronize()
     for o, cnt, ref in refs:
         assert torch.equal(flat[o:o + cnt], ref)
