@@ -152,6 +152,74 @@ __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
           smem_u32(bar))
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers --------------------------------------------------
+// Two CTAs of a cluster (same TPC) execute ONE tcgen05.mma of M = 256: each holds its own 128
+// rows of A and one half of B's N rows; the leader (cluster rank 0) issues, accumulators land
+// in both CTAs' TMEM.  Operand bytes read from shared memory per flop drop by 25 % (N = 128)
+// against cta_group::1 -- the limiter of the 1-CTA kernel (profiles/r01_history.md).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (an address in this CTA's window) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-SM TMA load: data lands in the executing CTA's shared memory, the transaction bytes are
+// signalled on the mbarrier at `bar_cluster_addr` (the leader CTA's barrier)
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map,
+                                             uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+      "l"(0x1000000000000000ull)
+      : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(slot)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_tf32_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of all prior MMAs of this thread; arrives on the barrier at the same CTA-relative
+// offset in both CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], m;\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
@@ -538,6 +606,261 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ NT kernel, CTA pair ----
+// Same contract as tc_gemm_nt_kernel; a cluster of two CTAs computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 (EXPERIMENTAL, PASE_B200_TC_2CTA=1; see profiles/r01_history.md).
+//   * CTA rank r loads A rows [m0 + 128 r, +128) and B rows [n0 + r BN/2, + BN/2) of every
+//     k-block into ITS shared memory at the same CTA-relative offsets; both signal the
+//     transaction bytes on the LEADER's `full` barrier (rank 0), which expects 2 x STAGE_BYTES.
+//   * the leader's MMA warp issues the M = 256 MMAs and commits with a cluster multicast, so
+//     `empty` / `acc_full` flip in both CTAs; each CTA's producer waits on its own `empty`.
+//   * each CTA's 16 epilogue warps drain the CTA's own TMEM (its 128 rows x BN columns) and
+//     release the buffer on the leader's `acc_empty` (count = both CTAs' epilogue warps).
+template <int BN, bool SPLIT>
+struct NT2Cfg {
+  static constexpr int BK = 32;
+  static constexpr int ROW_BYTES = BK * 4;
+  static constexpr int A_BYTES = BM * ROW_BYTES;
+  static constexpr int BH = BN / 2;                           // B rows held by one CTA
+  static constexpr int B_BYTES = BH * ROW_BYTES;
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);   // per CTA
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int CPW = (BN / 32 + 3) / 4;
+  static constexpr int EPI_ACTIVE = BN >= 128 ? 16 : 4 * (BN / 32);
+  static constexpr int SBO = 8 * ROW_BYTES;
+};
+
+template <int BN, bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS_V3, 1)
+tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
+                   int R, float* __restrict__ C, long ldc, int M, int N, int K, float alpha,
+                   const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
+                   double* __restrict__ colsumsq, int accumulate, int flush_kb, int stages,
+                   int stat_cols) {
+  using Cfg = NT2Cfg<BN, SPLIT>;
+  constexpr int BK = Cfg::BK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_full = empty_bar + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_out = reinterpret_cast<float*>(smem + stages * Cfg::STAGE_BYTES + BAR_BYTES);
+  float* s_stats = s_out + OUT_STAGE_BYTES / 4;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int total_tiles = n_tiles * m_tiles;
+  const int nkb = (K + BK - 1) / BK;
+  if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
+  const int nchunks = (nkb + flush_kb - 1) / flush_kb;
+  const bool want_stats = colsum != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);                      // leader's: one arrive.expect_tx
+      mbar_init(&empty_bar[s], 1);                     // one multicast commit per release
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);                      // one multicast commit per chunk
+      mbar_init(&acc_empty[b], 2 * Cfg::EPI_ACTIVE);   // leader's: both CTAs' epilogue warps
+    }
+    fence_barrier_init();
+    tmap_prefetch(&mAhi);
+    tmap_prefetch(&mBhi);
+    if (SPLIT) {
+      tmap_prefetch(&mAlo);
+      tmap_prefetch(&mBlo);
+    }
+  }
+  if (want_stats)
+    for (int i = threadIdx.x; i < 2 * stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
+  if (warp == 1) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);      // same warp in both CTAs
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // barriers of both CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % n_tiles) * BN + (int)rank * Cfg::BH;
+        int arow = m0, acol = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1, 21);
+          uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);      // the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          const int kf = kb * BK;
+          tma2_load_2d(st, &mAhi, fb, acol, arow);
+          tma2_load_2d(st + Cfg::A_BYTES, &mBhi, fb, kf, n0);
+          if (SPLIT) {
+            tma2_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mAlo, fb, acol, arow);
+            tma2_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mBlo, fb, kf, n0);
+          }
+          acol += BK;
+          while (acol >= R) {
+            acol -= R;
+            ++arow;
+          }
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader) {
+      // converged warp, elected issue (see umma_tf32_w); M = 256 across the pair
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN, 0, 0);
+      const uint64_t dconst = desc_hi_bits<2>(16, Cfg::SBO);
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t c = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        for (int ch = 0; ch < nchunks; ++ch, ++c) {
+          const uint32_t b = c & 1, aph = (c >> 1) & 1;
+          mbar_wait(&acc_empty[b], aph ^ 1, 24);
+          tc_fence_after();
+          const uint32_t d_tmem = tm0 + b * BN;
+          const int kb_lo = ch * flush_kb;
+          const int kb_hi = (kb_lo + flush_kb < nkb) ? kb_lo + flush_kb : nkb;
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
+            mbar_wait(&full_bar[s], ph, 22);
+            tc_fence_after();
+            const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
+            const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
+            const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
+            const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
+            const uint32_t first = (kb == kb_lo) ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t acc = (k == 0) ? first : 1u;
+              if (SPLIT) {
+                umma2_tf32_w(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
+                umma2_tf32_w(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                umma2_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+              } else {
+                umma2_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
+              }
+            }
+            umma2_commit_mc_w(&empty_bar[s]);        // frees the stage in both CTAs
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+          umma2_commit_mc_w(&acc_full[b]);           // accumulator chunk complete in both CTAs
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: this CTA's 128 rows x BN columns ----------------
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int cc0 = e >> 2;
+    if (cc0 < BN / 32) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+      float* stg = s_out + e * OUT_STG_FLOATS;
+      uint32_t c = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % n_tiles) * BN;
+        float sums[Cfg::CPW][32];
+        for (int ch = 0; ch < nchunks; ++ch, ++c) {
+          const uint32_t b = c & 1, aph = (c >> 1) & 1;
+          mbar_wait_epi(&acc_full[b], aph, 23);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < Cfg::CPW; ++h) {
+            uint32_t raw[32];
+            tmem_ld32(lane_addr + b * BN + (cc0 + 4 * h) * 32, raw);
+            if (ch == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sums[h][j] = __uint_as_float(raw[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sums[h][j] += __uint_as_float(raw[j]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&acc_empty[b]), 0));
+        }
+        const int m = m0 + q * 32 + lane;
+        long orow = 0;
+        int nlim = 0;
+        if (m < M) {
+          const int g = m / rm.rows_in;
+          const int u = m - g * rm.rows_in;
+          orow = (long)g * rm.rows_out + u;
+          const long lim = (long)(rm.t_valid - u * rm.fold) * rm.cols_per_fold;
+          nlim = lim <= 0 ? 0 : (lim >= N ? N : (int)lim);
+        }
+#pragma unroll
+        for (int h = 0; h < Cfg::CPW; ++h) {
+          const int nb = n0 + (cc0 + 4 * h) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = sums[h][j] * alpha;
+            if (bias != nullptr && nb + j < N) x += __ldg(bias + nb + j);
+            sums[h][j] = x;
+          }
+          store_chunk<false>(stg, sums[h], lane, C, ldc, orow, nlim, nb, vec_ok, accumulate);
+          if (want_stats) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sums[h][j] = (nb + j < nlim) ? sums[h][j] : 0.f;
+              sq[j] = sums[h][j] * sums[h][j];
+            }
+            const float s1 = colsum32(sums[h], lane);
+            const float s2 = colsum32(sq, lane);
+            if (nb + lane < N) {
+              atomicAdd(&s_stats[nb + lane], s1);
+              atomicAdd(&s_stats[stat_cols + nb + lane], s2);
+            }
+          }
+        }
+      }
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 1, 512;" ::: "memory");     // the 16 epilogue warps only
+      for (int col = threadIdx.x - 64; col < N; col += N_EPI_WARPS * 32) {
+        const float a = s_stats[col], b2 = s_stats[stat_cols + col];
+        if (a != 0.f || b2 != 0.f) {
+          atomicAdd(colsum + col, (double)a);
+          atomicAdd(colsumsq + col, (double)b2);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();            // neither CTA frees TMEM / exits while the pair still uses it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -1018,6 +1341,16 @@ static void pase_tc_init_epi_sleep() {
   if (ns > 0) cudaMemcpyToSymbol(c_epi_sleep_ns, &ns, sizeof(int));
 }
 
+static bool pase_tc_use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    // EXPERIMENTAL CTA-pair kernel (tcgen05 cta_group::2), off unless PASE_B200_TC_2CTA=1
+    const char* e = getenv("PASE_B200_TC_2CTA");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1092,6 +1425,39 @@ int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
       ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
       stat_cols);
   PASE_LAUNCH_CHECK("pase_tc_gemm_nt");
+  return PASE_OK;
+}
+
+template <int BN, bool SPLIT>
+int launch_nt2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+               const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
+               const float* bias, RowMap rm, double* cs, double* cq, int accumulate, int flush_kb,
+               cudaStream_t st) {
+  using Cfg = NT2Cfg<BN, SPLIT>;
+  static bool attr = false;
+  const int stat_cols = cs ? ((N + 31) / 32) * 32 : 0;
+  const int stages = pick_stages(Cfg::STAGE_BYTES, 2 * stat_cols * 4);
+  const int smem = smem_bytes(stages, Cfg::STAGE_BYTES, 2 * stat_cols * 4);
+  if (stages < 2) {
+    pase_set_error("pase_tc_gemm_nt (2-CTA): not enough shared memory for 2 pipeline stages");
+    return PASE_ERR_UNSUPPORTED;
+  }
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, SPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      pase_set_error("pase_tc_gemm_nt (2-CTA): smem attribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr = true;
+  }
+  const long tiles = (long)((N + BN - 1) / BN) * ((M + 2 * BM - 1) / (2 * BM));
+  const long max_pairs = pase_num_sms() / 2;
+  const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);   // cluster dims (2,1,1)
+  tc_gemm_nt2_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(
+      ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
+      stat_cols);
+  PASE_LAUNCH_CHECK("pase_tc_gemm_nt(2cta)");
   return PASE_OK;
 }
 
@@ -1267,7 +1633,8 @@ int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, cons
   CUtensorMap ah, al, bh, bl;
   // window kernel: A fetched once per 32-float column block (needs K % 32 == 0); the plain
   // per-k-block kernel remains for ragged K
-  const bool window = BN != 256 && (K % 32) == 0 && pase_tc_use_window();
+  const bool pair2 = BN == 128 && (N % 128) == 0 && pase_tc_use_2cta();
+  const bool window = !pair2 && BN != 256 && (K % 32) == 0 && pase_tc_use_window();
   const int qmax = (K + R - 1) / R - 1;
   const int win_rows = ((BM + qmax + 7) / 8) * 8;
   uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
@@ -1275,7 +1642,7 @@ int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, cons
   uint32_t abox[2] = {(uint32_t)BKh, (uint32_t)(window ? win_rows : BM)};
   uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
   uint64_t bstr[1] = {(uint64_t)ldb * 4};
-  uint32_t bbox[2] = {(uint32_t)BKh, (uint32_t)BN};
+  uint32_t bbox[2] = {(uint32_t)BKh, (uint32_t)(pair2 ? BN / 2 : BN)};   // pair: half per CTA
   const CUtensorMapSwizzle swz = BKh == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   PASE_CHECK_ARG(!window || win_rows <= 256, "pase_tc_gemm_nt: K/R=%d too large for a window",
                  qmax + 1);
@@ -1291,6 +1658,12 @@ int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, cons
   }
   RowMap rm{rows_in, t_valid, rows_out, fold, N / fold};
   cudaStream_t st = (cudaStream_t)stream;
+  if (pair2) {
+    return mode == 1 ? launch_nt2<128, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,
+                                             colsum, colsumsq, accumulate, flush_kb, st)
+                     : launch_nt2<128, false>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,
+                                              colsum, colsumsq, accumulate, flush_kb, st);
+  }
   if (window) {
 #define PASE_NTW(BNV)                                                                          \
   (mode == 1 ? launch_ntw<BNV, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,       \
