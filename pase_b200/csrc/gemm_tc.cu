@@ -611,7 +611,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 
 // ------------------------------------------------------------------ NT kernel, CTA pair ----
 // Same contract as tc_gemm_nt_kernel; a cluster of two CTAs computes a 256 x BN tile with
-// tcgen05.mma.cta_group::2 (EXPERIMENTAL, PASE_B200_TC_2CTA=1; see profiles/r01_history.md).
+// tcgen05.mma.cta_group::2 (default for N % 128 == 0; PASE_B200_TC_2CTA=0 disables it).
 //   * CTA rank r loads A rows [m0 + 128 r, +128) and B rows [n0 + r BN/2, + BN/2) of every
 //     k-block into ITS shared memory at the same CTA-relative offsets; both signal the
 //     transaction bytes on the LEADER's `full` barrier (rank 0), which expects 2 x STAGE_BYTES.
@@ -1344,9 +1344,10 @@ static void pase_tc_init_epi_sleep() {
 static bool pase_tc_use_2cta() {
   static int v = -1;
   if (v < 0) {
-    // EXPERIMENTAL CTA-pair kernel (tcgen05 cta_group::2), off unless PASE_B200_TC_2CTA=1
+    // CTA-pair kernel (tcgen05 cta_group::2): on by default (NT 2.41 -> 2.16 ms per PASE+
+    // step, profiles/r01_history.md); PASE_B200_TC_2CTA=0 selects the 1-CTA kernel
     const char* e = getenv("PASE_B200_TC_2CTA");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
 }
