@@ -1,5 +1,5 @@
 #!/bin/bash
-# default-path sanity, then the experimental CTA-pair NT kernel (PASE_B200_TC_2CTA=1)
+# default-path sanity, then an A/B of the CTA-pair NT kernel (PASE_B200_TC_2CTA=0/1)
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -q -m gpu -x > gpurun_out/t_all.log 2>&1
