@@ -70,3 +70,57 @@ def test_encoder_host_logic(name, precision, emulated):
     for key, val in gold.items():
         if key.startswith("stat/"):
             assert_close(sd[key[5:]].float(), val.float(), 1e-5, 1e-6, key)
+
+
+def test_weight_batch_table_is_cached_and_rebuilt(emulated, monkeypatch):
+    """pase_conv_w_batch job tables: built once per plan, reused on the next step, rebuilt when
+    a parameter's storage moves; gradients are views of per-call buffers (never the plan's)."""
+    gold, meta = load_golden("enc_pasep_train_3200")
+    cfg = resolve_cfg(meta["cfg"])
+    model = WaveFe(**cfg)
+    model.precision = "3xtf32"
+    model.load_state_dict(fill_state_dict(model.state_dict(), meta["seed"]))
+    model.train(True)
+    x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5)
+    seen = []
+    real = emul_ops.call
+
+    def spy(name, *a):
+        if name == "pase_conv_w_batch":
+            seen.append((a[3], a[0].data_ptr(), a[1]))       # (op, table pointer, njobs)
+        return real(name, *a)
+    monkeypatch.setattr(ops, "call", spy)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        y, _ = run_encoder_cpu(model, x)
+        y.square().mean().backward()
+        return y.detach().clone(), {k: p.grad for k, p in model.named_parameters()}
+
+    y1, g1 = step()
+    first = list(seen)
+    # PASE+ has 7 non-sinc conv blocks (all of them feed an input gradient back to the
+    # block before); their shapes fit the shared-memory tiled variants (ops 3..5)
+    assert [(op, n) for op, _, n in first] == [(3, 7), (4, 7), (5, 7)]
+    seen.clear()
+    y2, g2 = step()
+    assert [t for _, t, _ in seen] == [t for _, t, _ in first]       # same device tables
+    plan = model._plan(x.shape[0], x.shape[2], x.device)
+    plan_ptrs = {t.untyped_storage().data_ptr() for v in plan.__dict__.values()
+                 for t in (v if isinstance(v, list) else [v]) if isinstance(t, torch.Tensor)}
+    for k, g in g2.items():
+        assert g.untyped_storage().data_ptr() not in plan_ptrs, k
+        assert g1[k].untyped_storage().data_ptr() != g.untyped_storage().data_ptr() or \
+            g1[k] is g, k
+    # moving one weight to new storage invalidates the forward / dgrad tables only
+    w = model.blocks[3].conv.weight
+    w.data = w.data.clone()
+    seen.clear()
+    y3, g3 = step()
+    new = {op: t for op, t, _ in seen}
+    old = {op: t for op, t, _ in first}
+    assert new[3] != old[3] and new[4] != old[4] and new[5] == old[5]
+    # BatchNorm running statistics advance between the steps, the batch statistics do not:
+    # train-mode outputs of the three steps agree
+    assert_close(y2, y1, 1e-6, 1e-7, "step 2")
+    assert_close(y3, y1, 1e-6, 1e-7, "step 3")
