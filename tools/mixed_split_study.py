@@ -7,7 +7,10 @@ keep the main product in TF32 and do the two error-compensation products of 3xTF
       + bf16(a - trunc_tf32(a)) * bf16(b)                (bf16 pass)
       + bf16(a) * bf16(b - rn_tf32(b))                   (bf16 pass)
 
-and compare its error against fp64 with today's 3xTF32 and with single-pass TF32, on operands
+and, cheaper still, three bf16 products of a two-term bf16 split of both operands
+(a1*b1 + a1*b2 + a2*b1: 1.5 TF32-pass equivalents of tensor time against 3 today, and bf16
+operand pairs instead of fp32 + residual, i.e. half the operand bytes), and compare their
+errors against fp64 with today's 3xTF32 and with single-pass TF32, on operands
 shaped like the PASE+ layers (zero-mean activations, K up to 5632).  Products are exact in
 fp32 for 8-/11-bit mantissas, accumulation is emulated in fp64 (the kernels fold K = 128
 chunks into fp32 sums; that part is common to all schemes).
@@ -41,9 +44,13 @@ def study(M, N, K, seed):
     one = d(ah, bh)
     three = one + d(al, bh) + d(ah, bl)
     mixed = one + d(bf16(a - ah), bf16(b)) + d(bf16(a), bf16(b - bh))
+    a1, b1 = bf16(a), bf16(b)
+    a2, b2 = bf16(a - a1), bf16(b - b1)
+    b3 = d(a1, b1) + d(a1, b2) + d(a2, b1)
     scale = ref.abs().max()
     out = {}
-    for name, v in (("tf32", one), ("3xtf32", three), ("tf32+2bf16", mixed)):
+    for name, v in (("tf32", one), ("3xtf32", three), ("tf32+2bf16", mixed),
+                    ("3xbf16 (2-term split)", b3)):
         e = (v - ref).abs()
         out[name] = (float(e.max() / scale), float((e.pow(2).sum() / ref.pow(2).sum()).sqrt()))
     return out
