@@ -461,7 +461,9 @@ def run_native(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "3xtf32": "f32 (3xTF32 split on tcgen05, fp32 accumulate: "
-                      "fp32-equivalent products)", "tf32": "tf32"}[args.precision],
+                      "fp32-equivalent products)",
+                      "3xf16": "f32 (3xF16 split on tcgen05, fp32 accumulate: fp32-equivalent "
+                               "products)", "tf32": "tf32", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "PASE+.cfg encoder fwd+bwd+adam, B=32/GPU, T=32000, fp32, "
                                    "train-mode BN, no workers (BASELINE configs[1])",
@@ -480,6 +482,9 @@ def run_native(args):
                                    "fwd/dgrad/wgrad)",
                            "3xtf32": "pase_tc_gemm_nt + pase_tc_gemm_tn (tcgen05 kind::tf32, 3 MMAs "
                                      "per product; FLOPs counted once)",
+                           "3xf16": "pase_tc_gemm_nt + pase_tc_gemm_tn (tcgen05 kind::f16 on fp16 "
+                                    "hi/lo pairs, 3 MMAs per product; FLOPs counted once)",
+                           "bf16": "pase_tc_gemm_nt + pase_tc_gemm_tn (tcgen05 kind::f16, bf16)",
                            "tf32": "pase_tc_gemm_nt + pase_tc_gemm_tn (tcgen05 kind::tf32)"}[
                     args.precision],
                 "bound": "tensor", "achieved": ach_tf, "peak": peaks["tf_sustained"],
@@ -525,8 +530,9 @@ def main():
                          "all workers+ heads (informational)")
     ap.add_argument("--batch", type=int, default=32, help="chunk triplets per step (workers workload)")
     ap.add_argument("--precision", default=os.environ.get("PASE_B200_PRECISION", "3xtf32"),
-                    choices=["fp32", "3xtf32", "tf32"],
-                    help="GEMM numerics: fp32 FFMA, 3xTF32 tcgen05 (fp32-equivalent), TF32 tcgen05")
+                    choices=["fp32", "3xtf32", "3xf16", "tf32", "bf16"],
+                    help="GEMM numerics: fp32 FFMA; 3xTF32 / 3xF16 tcgen05 (fp32-equivalent); TF32 "
+                         "tcgen05; bf16 tcgen05 with bf16 activation storage (BASELINE configs[2,4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -67,26 +67,46 @@ int pase_gemm_tn(const float* A, long lda, int pitchA, int offA,
 
 
 /* ---- tensor-core (tcgen05 / TMEM / TMA) GEMMs ------------------------------
- * Same contract as pase_gemm_nt / pase_gemm_tn, computed with kind::tf32 UMMA
- * instructions and fp32 accumulation in tensor memory.
- *   mode 0: single TF32 pass;  mode 1: 3xTF32 (operands pre-split by
- *   pase_split_tf32 into exactly-representable hi/lo parts) = fp32-equivalent.
- * A is a plain 2-D tensor [a_rows x R] (R floats per folded row, R % 32 == 0):
- * element (m, k) is read at row m + k/R, column k%R. */
+ * Same contract as pase_gemm_nt / pase_gemm_tn, computed with tcgen05 UMMA
+ * instructions and fp32 accumulation in tensor memory.  `mode` selects the
+ * operand element type and the numerics:
+ *   0  TF32   : fp32 operands read as tf32, one pass;
+ *   1  3xTF32 : fp32 operands pre-split by pase_split_tf32 into exactly
+ *               representable hi/lo parts = fp32-equivalent products;
+ *   2  BF16   : bf16 operands (kind::f16), one pass at twice the TF32 rate;
+ *   3  3xF16  : fp16 operand pairs x = hi + 2^-11 lo' (pase_split_f16 or the
+ *               producing kernel) = fp32-equivalent products at half the tensor
+ *               time and operand bytes of 3xTF32; operands must fit fp16's
+ *               range (gradients are pre-scaled by a power of two).
+ * Ahi/Alo/Bhi/Blo point to fp32 (modes 0,1), bf16 (2) or fp16 (3) arrays; the
+ * lo pointers are NULL outside modes 1 and 3.
+ * A is a plain 2-D tensor [a_rows x R] (R elements per folded row, R*elemsize
+ * a multiple of 128 bytes): element (m, k) is read at row m + k/R, column k%R.
+ * alpha_dev (may be NULL): device scalar multiplied into alpha (undoes the
+ * power-of-two scale of a pre-scaled gradient operand without a host sync).
+ * c_bf16 != 0: C is a bf16 array (no accumulate); otherwise fp32. */
 int pase_split_tf32(const float* x, float* hi, float* lo, long n, void* stream);
-int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R,
-                    const float* Bhi, const float* Blo, long ldb,
-                    float* C, long ldc, int M, int N, int K, float alpha, const float* bias,
+int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R,
+                    const void* Bhi, const void* Blo, long ldb,
+                    void* C, long ldc, int M, int N, int K, float alpha,
+                    const float* alpha_dev, const float* bias,
                     int rows_in, int t_valid, int rows_out, int fold,
-                    double* colsum, double* colsumsq, int accumulate, int mode, void* stream);
-int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, int offA,
-                    const float* Bhi, const float* Blo, int R, int pitchB, long b_rows_total,
+                    double* colsum, double* colsumsq, int accumulate, int mode, int c_bf16,
+                    void* stream);
+int pase_tc_gemm_tn(const void* Ahi, const void* Alo, long lda, int pitchA, int offA,
+                    const void* Bhi, const void* Blo, int R, int pitchB, long b_rows_total,
                     float* C, long ldc, int I, int J, int groups, int rows_per_group,
-                    float alpha, int accumulate, int mode, void* stream);
+                    float alpha, const float* alpha_dev, int accumulate, int mode, void* stream);
 
-/* hardware probe used by tools/rowshift_probe.py only (not on the product path) */
-int pase_tc_probe_rowshift(const float* W, const float* B, float* D, int wrows, int shift,
-                           int use_base_offset, void* stream);
+/* ---- operand-format conversions for GEMM modes 2 / 3 (small tensors) -------- */
+/* dst (bf16) = rn(x) */
+int pase_cast_bf16(const float* x, void* dst, long n, void* stream);
+/* amax[0] = max(amax[0], max|x|)  (caller zeroes amax once per use) */
+int pase_absmax(const float* x, long n, float* amax, void* stream);
+/* fp16 pair of s*x: hi = rn_f16(s x), lo = rn_f16((s x - hi) 2^11); s = 1 when amax is
+ * NULL, else the power of two placing amax[0] below 2^14; scale_out = {1/s, s} */
+int pase_split_f16(const float* x, void* hi, void* lo, long n, const float* amax,
+                   float* scale_out, void* stream);
 
 /* ---- weight re-layout (implicit-GEMM operand preparation) ---------------- */
 /* (Cout,Cin,k) -> Wt[co, j*Cin+ci]                      (forward operand)   */
@@ -104,9 +124,11 @@ int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, 
  * the 3xTF32 weight split (as pase_split_tf32 with an explicit hi).  op 3..5 = the same
  * three through shared-memory tiles (coalesced reads and writes): `total` is then the number
  * of thread blocks, table[.., 11] the job's first block; blocks per job = Cout (ops 3, 5) or
- * (Cout/32)*(Cin/8) (op 4); needs Cout % 32 == 0, Cin % 8 == 0 and (Cin+1)*k <= 12000.    */
+ * (Cout/32)*(Cin/8) (op 4); needs Cout % 32 == 0, Cin % 8 == 0 and (Cin+1)*k <= 12000.
+ * fmt selects what hi/lo receive: 0 = the 3xTF32 split (fp32), 1 = bf16 copy in hi,
+ * 2 = fp16 pair (hi, lo' = (v-hi)*2^11); dst (fp32) may be 0 when only hi/lo are wanted. */
 int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* dst_base,
-                      void* stream);
+                      int fmt, void* stream);
 /* ConvTranspose1d weight (Cin,Cout,k) -> Wu[p*Cout+co, v*Cin+ci] =
  * W[ci,co,s*(taps-1-v)+p] or 0 (forward operand of the transposed conv)     */
 int pase_deconv_w_to_fwd(const float* W, float* Wu, int Cin, int Cout, int k,
@@ -136,9 +158,14 @@ int pase_sinc_grad(const float* dWp, const float* low_hz, const float* band_hz,
 
 /* ---- padding / BatchNorm / PReLU (F.pad reflect, nn.BatchNorm1d, nn.PReLU:
  * modules.py:924-928,1071-1075,79,111-113) --------------------------------- */
-/* (N,T) waveform -> reflect-padded rows of pitch `pitch` floats */
-int pase_reflect_pad_wave(const float* x, float* dst, int N, int T, int padL, int padR,
-                          long pitch, void* stream);
+/* Storage formats of activation-sized tensors (`*_fmt` arguments; `*_bf16` flags
+ * are 0 = fp32, 1 = bf16):
+ *   0 fp32 (optionally with a tf32-residual twin `*_lo` for GEMM mode 1),
+ *   1 bf16 (GEMM mode 2),
+ *   2 fp16 pair: dst = hi = rn_f16(x), dst_lo = lo' = rn_f16((x-hi)*2^11) (GEMM mode 3). */
+/* (N,T) waveform -> reflect-padded rows of pitch `pitch` elements */
+int pase_reflect_pad_wave(const float* x, void* dst, void* dst_lo, int dst_fmt, int N, int T,
+                          int padL, int padR, long pitch, void* stream);
 /* batch statistics -> per-channel affine; updates running stats (training) */
 int pase_bn_finalize(const double* colsum, const double* colsumsq, int C, int fold,
                      double count, const float* gamma, const float* beta,
@@ -148,36 +175,40 @@ int pase_bn_eval_affine(const float* running_mean, const float* running_var,
                         const float* gamma, const float* beta, int C, float eps,
                         float* mean, float* invstd, float* scale, float* shift, void* stream);
 /* a = PReLU(y*scale+shift) written with reflect halo into the next layer's
- * padded buffer, plus mean-pooled dense-skip accumulation (frontend.py:213-232) */
-int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, int C,
+ * padded operand buffer (format dst_fmt), plus mean-pooled dense-skip
+ * accumulation into the fp32 `pool` matrix (frontend.py:213-232) */
+int pase_bn_prelu_pad_fwd(const void* y, int y_bf16, long y_sample_stride, int N, int T, int C,
                           const float* scale, const float* shift, const float* alpha,
-                          float* dst, long dst_sample_stride, long dst_row_stride,
+                          void* dst, void* dst_lo, int dst_fmt,
+                          long dst_sample_stride, long dst_row_stride,
                           int padL, int padR,
                           float* pool, long pool_sample_stride, long pool_row_stride,
-                          int pool_d, int pool_T,
-                          float* dst_lo /* optional: tf32 residual of dst, same layout */,
-                          void* stream);
-/* backward, pass 1: g = sum of gradient sources; du = PReLU'(u) g written to
- * dst; accumulates S1=sum du, S2=sum du*xhat, dalpha (double[C] each). */
-int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T, int C,
+                          int pool_d, int pool_T, void* stream);
+/* backward, pass 1: g = sum of gradient sources (srcA: fp32 or bf16 as its dgrad GEMM
+ * wrote it; srcB / pool: fp32); du = PReLU'(u) g written to dst (same type as y);
+ * accumulates S1=sum du, S2=sum du*xhat, dalpha (double[C] each).  amax (float[2],
+ * optional, caller-zeroed): max|du|, max|xhat| for the fp16-pair gradient scale. */
+int pase_bn_prelu_bwd_reduce(const void* y, int y_bf16, long y_sample_stride, int N, int T, int C,
                              const float* mean, const float* invstd,
                              const float* scale, const float* shift, const float* alpha,
-                             const float* srcA, long a_sample_stride, long a_row_stride,
-                             int padL, int padR,
+                             const void* srcA, int a_bf16, long a_sample_stride,
+                             long a_row_stride, int padL, int padR,
                              const float* srcB, long b_sample_stride, long b_row_stride,
                              int b_shift,
                              const float* pool, long pool_sample_stride, long pool_row_stride,
                              int pool_d, int pool_T,
-                             float* dst, long dst_sample_stride,
-                             double* S1, double* S2, double* dalpha, void* stream);
-/* backward, pass 2 (in place on dst): dy = gamma*invstd*(du - S1/M - xhat*S2/M);
- * also finalises dgamma=S2, dbeta=S1, dalpha and db = sum dy.  */
-int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, int C,
+                             void* dst, long dst_sample_stride,
+                             double* S1, double* S2, double* dalpha, float* amax, void* stream);
+/* backward, pass 2: dy = gamma*invstd*(du - S1/M - xhat*S2/M) read from `du` (same type
+ * as y; may alias dst when the formats agree) and written as the next GEMMs' operand in
+ * format dst_fmt; also finalises db = sum dy.  dst_fmt 2 (fp16 pair): dy is scaled by a
+ * power of two s derived from amax (so that it fits fp16) and scale_out = {1/s, s}. */
+int pase_bn_prelu_bwd_apply(const void* y, int y_bf16, long y_sample_stride, int N, int T, int C,
                             const float* mean, const float* invstd, const float* gamma,
                             const double* S1, const double* S2, double count,
-                            float* dst, long dst_sample_stride,
-                            double* dbias_acc,
-                            float* dst_lo /* optional: tf32 residual of dst */, void* stream);
+                            const void* du, void* dst, void* dst_lo, int dst_fmt,
+                            long dst_sample_stride, double* dbias_acc,
+                            const float* amax, float* scale_out, void* stream);
 /* plain per-channel PReLU on (rows,C) (MLPBlock / GDeconv1DBlock act) */
 int pase_prelu_fwd(const float* u, float* h, const float* alpha, long rows, int C,
                    long ldu, long ldh, void* stream);

@@ -7,11 +7,27 @@ namespace {
 constexpr int RUN = 8;      // consecutive time steps handled by one thread
 constexpr int THREADS = 256;
 
-__global__ void reflect_pad_wave_kernel(const float* __restrict__ x, float* __restrict__ dst,
-                                        int T, int padL, int Tp, long pitch) {
+// DF: operand format of the padded waveform (block 0's GEMM operand)
+template <int DF>
+__global__ void reflect_pad_wave_kernel(const float* __restrict__ x, void* __restrict__ dst_v,
+                                        void* __restrict__ dst_lo_v, int T, int padL, int Tp,
+                                        long pitch) {
   const int n = blockIdx.y;
-  for (int tau = blockIdx.x * blockDim.x + threadIdx.x; tau < Tp; tau += gridDim.x * blockDim.x)
-    dst[(long)n * pitch + tau] = x[(long)n * T + reflect_idx(tau - padL, T)];
+  for (int tau = blockIdx.x * blockDim.x + threadIdx.x; tau < Tp; tau += gridDim.x * blockDim.x) {
+    const float v = x[(long)n * T + reflect_idx(tau - padL, T)];
+    const long o = (long)n * pitch + tau;
+    if constexpr (DF == PASE_FMT_F32) {
+      reinterpret_cast<float*>(dst_v)[o] = v;
+      if (dst_lo_v != nullptr) reinterpret_cast<float*>(dst_lo_v)[o] = tf32_residual(v);
+    } else if constexpr (DF == PASE_FMT_BF16) {
+      reinterpret_cast<__nv_bfloat16*>(dst_v)[o] = __float2bfloat16_rn(v);
+    } else {
+      __half h, l;
+      f16_split(v, h, l);
+      reinterpret_cast<__half*>(dst_v)[o] = h;
+      reinterpret_cast<__half*>(dst_lo_v)[o] = l;
+    }
+  }
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ colsum,
@@ -62,20 +78,19 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ rm, const float*
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float prelu1(float u, float a) { return u > 0.f ? u : a * u; }
-// lo = rn_tf32(x - trunc_tf32(x)): the part of x the tensor core drops when it reads x as tf32
-__device__ __forceinline__ float tf32_residual(float x) {
-  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  uint32_t u = __float_as_uint(r);
-  u += 0xFFFu + ((u >> 13) & 1u);
-  return __uint_as_float(u & 0xFFFFE000u);
-}
 
+// Forward: a = PReLU(y*scale+shift) with reflect halo into the next layer's padded operand.
+//   YT  storage type of y (float / bf16);  DF  operand format of dst:
+//   PASE_FMT_F32 (+ optional tf32-residual twin dst_lo), PASE_FMT_BF16, PASE_FMT_F16X2
+//   (dst = hi, dst_lo = lo').  The dense-skip pool accumulates the value the next layer
+//   reads (i.e. after rounding to bf16 in the bf16 format).
+template <typename YT, int DF>
 __global__ void __launch_bounds__(THREADS)
-bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
+bn_prelu_pad_fwd_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
                         const float* __restrict__ scale, const float* __restrict__ shift,
-                        const float* __restrict__ alpha, float* __restrict__ dst, long d_ss,
+                        const float* __restrict__ alpha, void* __restrict__ dst_v, long d_ss,
                         long d_rs, int padL, int Tp, float* __restrict__ pool, long p_ss,
-                        long p_rs, int pool_d, int pool_T, float* __restrict__ dst_lo) {
+                        long p_rs, int pool_d, int pool_T, void* __restrict__ dst_lo_v) {
   const int C4 = C >> 2;
   const int n = blockIdx.y;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,8 +100,7 @@ bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
   if (tau0 >= Tp) return;
   const int c = q * 4;
   const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
-  const float* yn = y + (long)n * y_ss;
-  float* dn = dst + (long)n * d_ss;
+  const YT* yn = y + (long)n * y_ss;
   const int pool_len = pool_d > 0 ? pool_T * pool_d : 0;
   const float inv_d = pool_d > 0 ? 1.f / (float)pool_d : 0.f;
   float4 pacc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -105,7 +119,7 @@ bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
   float4 vals[RUN];
 #pragma unroll
   for (int i = 0; i < RUN; ++i)
-    if (i < nvalid) vals[i] = ld4(yn + (long)reflect_idx((int)tau0 + i - padL, T) * C + c);
+    if (i < nvalid) vals[i] = ld4t(yn + (long)reflect_idx((int)tau0 + i - padL, T) * C + c);
 #pragma unroll
   for (int i = 0; i < RUN; ++i) {
     if (i >= nvalid) break;
@@ -117,11 +131,20 @@ bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
     a.y = prelu1(fmaf(v.y, sc.y, sh.y), al.y);
     a.z = prelu1(fmaf(v.z, sc.z, sh.z), al.z);
     a.w = prelu1(fmaf(v.w, sc.w, sh.w), al.w);
-    st4(dn + tau * d_rs + c, a);
-    if (dst_lo != nullptr)      // 3xTF32 residual of the operand just written (see gemm_tc.cu)
-      st4(dst_lo + (long)n * d_ss + tau * d_rs + c,
-          make_float4(tf32_residual(a.x), tf32_residual(a.y), tf32_residual(a.z),
-                      tf32_residual(a.w)));
+    const long o = (long)n * d_ss + tau * d_rs + c;
+    if constexpr (DF == PASE_FMT_F32) {
+      st4(reinterpret_cast<float*>(dst_v) + o, a);
+      if (dst_lo_v != nullptr)      // 3xTF32 residual of the operand just written
+        st4(reinterpret_cast<float*>(dst_lo_v) + o,
+            make_float4(tf32_residual(a.x), tf32_residual(a.y), tf32_residual(a.z),
+                        tf32_residual(a.w)));
+    } else if constexpr (DF == PASE_FMT_BF16) {
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_v) + o;
+      st4t(d, a);
+      a = rt4t(d, a);
+    } else {
+      st4_f16x2(reinterpret_cast<__half*>(dst_v) + o, reinterpret_cast<__half*>(dst_lo_v) + o, a);
+    }
     if (tr >= 0 && tr < pool_len) {
       const int w = tr / pool_d;
       if (w != pw) {
@@ -136,20 +159,25 @@ bn_prelu_pad_fwd_kernel(const float* __restrict__ y, long y_ss, int T, int C,
 
 // ---- backward pass 1: du + reductions ----
 struct BwdSrc {
-  const float* A; long a_ss, a_rs; int padL, padR;
+  const void* A; long a_ss, a_rs; int padL, padR;
   const float* B; long b_ss, b_rs; int b_shift;
   const float* P; long p_ss, p_rs; int pool_d, pool_T;
 };
 
+// YT: storage type of y and of du (dst); GT: storage type of the gradient source A (the
+// next layer's input gradient as its dgrad GEMM wrote it).  amax (optional, float[2]):
+// running maxima of |du| and |xhat| (bit-pattern atomicMax), from which pass 2 derives the
+// power-of-two scale of the fp16 gradient operand (3xF16 mode).
+template <typename YT, typename GT>
 __global__ void __launch_bounds__(THREADS)
-bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
+bn_prelu_bwd_reduce_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
                            const float* __restrict__ mean, const float* __restrict__ invstd,
                            const float* __restrict__ scale, const float* __restrict__ shift,
-                           const float* __restrict__ alpha, BwdSrc s, float* __restrict__ dst,
+                           const float* __restrict__ alpha, BwdSrc s, YT* __restrict__ dst,
                            long d_ss, double* __restrict__ S1, double* __restrict__ S2,
-                           double* __restrict__ dalpha) {
-  extern __shared__ float red[];      // [3][C]
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+                           double* __restrict__ dalpha, float* __restrict__ amax) {
+  extern __shared__ float red[];      // [3][C] (+ [2] maxima)
+  for (int i = threadIdx.x; i < 3 * C + 2; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int C4 = C >> 2;
   const int n = blockIdx.y;
@@ -160,10 +188,11 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
   const int q = (int)(idx0 % C4);
   const int c = q * 4;
   float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, a3[4] = {0, 0, 0, 0};
+  float mx_du = 0.f, mx_xh = 0.f;
   const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
   const float4 mu = ld4(mean + c), is = ld4(invstd + c);
-  const float* yn = y + (long)n * y_ss;
-  float* dn = dst + (long)n * d_ss;
+  const YT* yn = y + (long)n * y_ss;
+  YT* dn = dst + (long)n * d_ss;
   const int pool_len = s.pool_d > 0 ? s.pool_T * s.pool_d : 0;
   const float inv_d = s.pool_d > 0 ? 1.f / (float)s.pool_d : 0.f;
   for (long idx = idx0; idx < nthreads; idx += (long)gridDim.x * blockDim.x) {
@@ -172,12 +201,12 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
     float4 gs[RUN], ys[RUN];
     // phase 1: straight-line loads of the whole run (no branch between a load and the next
     // one, so all DRAM requests of the run are in flight together)
-    const float* an = s.A + (long)n * s.a_ss + c;
+    const GT* an = reinterpret_cast<const GT*>(s.A) + (long)n * s.a_ss + c;
 #pragma unroll
     for (int i = 0; i < RUN; ++i) {
       const int t = (int)t0 + (i < nvalid ? i : 0);
-      gs[i] = ld4(an + (long)(t + s.padL) * s.a_rs);
-      ys[i] = ld4(yn + (long)t * C + c);
+      gs[i] = ld4t(an + (long)(t + s.padL) * s.a_rs);
+      ys[i] = ld4t(yn + (long)t * C + c);
     }
     if (s.P != nullptr) {                       // mean-pooled dense-skip gradient (broadcast)
       const float* pn = s.P + (long)n * s.p_ss + c;
@@ -204,16 +233,13 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
         if (i >= nvalid) break;
         const int t = (int)t0 + i;
         float4 g = gs[i];
-        auto add4 = [&](const float* p) {
-          const float4 v = ld4(p);
-          g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
-        };
-        if (s.padL > 0 && t >= 1 && t <= s.padL) add4(an + (long)(s.padL - t) * s.a_rs);
+        auto add4 = [&](float4 v) { g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w; };
+        if (s.padL > 0 && t >= 1 && t <= s.padL) add4(ld4t(an + (long)(s.padL - t) * s.a_rs));
         if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
-          add4(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs);
+          add4(ld4t(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs));
         if (s.B) {
           const int tb = t + s.b_shift;
-          if (tb >= 0 && tb < T) add4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c);
+          if (tb >= 0 && tb < T) add4(ld4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c));
         }
         gs[i] = g;
       }
@@ -237,8 +263,10 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
         const float xh = (vv[k] - muv[k]) * isv[k];
         a1[k] += du[k];
         a2[k] += du[k] * xh;
+        mx_du = fmaxf(mx_du, fabsf(du[k]));
+        mx_xh = fmaxf(mx_xh, fabsf(xh));
       }
-      st4(dn + (long)t * C + c, make_float4(du[0], du[1], du[2], du[3]));
+      st4t(dn + (long)t * C + c, make_float4(du[0], du[1], du[2], du[3]));
     }
   }
   // lanes that own the same channel quad (C/4 < 32, power of two) combine before the
@@ -262,24 +290,66 @@ bn_prelu_bwd_reduce_kernel(const float* __restrict__ y, long y_ss, int T, int C,
       atomicAdd(&red[2 * C + c + k], a3[k]);
     }
   }
+  if (amax != nullptr) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      mx_du = fmaxf(mx_du, __shfl_xor_sync(0xffffffffu, mx_du, off));
+      mx_xh = fmaxf(mx_xh, __shfl_xor_sync(0xffffffffu, mx_xh, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomic_max_pos(&red[3 * C], mx_du);
+      atomic_max_pos(&red[3 * C + 1], mx_xh);
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     atomicAdd(S1 + i, (double)red[0 * C + i]);
     atomicAdd(S2 + i, (double)red[1 * C + i]);
     atomicAdd(dalpha + i, (double)red[2 * C + i]);
   }
+  if (amax != nullptr && threadIdx.x == 0) {
+    atomic_max_pos(amax, red[3 * C]);
+    atomic_max_pos(amax + 1, red[3 * C + 1]);
+  }
 }
 
+// Backward pass 2: dy = gamma*invstd*(du - S1/M - xhat*S2/M), du read from `du` (may alias
+// dst), dy written as the NEXT GEMMs' A operand in format DF.  PASE_FMT_F16X2: dy is scaled
+// by the power of two derived from the bound
+//     |dy| <= max_c |gamma_c invstd_c| (max|du| + |S1_c/M| + max|xhat| |S2_c/M|)
+// (amax from pass 1), every block computes the same scale; block (0,0) publishes
+// scale_out = {1/s, s} for the consuming GEMMs (alpha_dev).
+template <typename YT, int DF>
 __global__ void __launch_bounds__(THREADS)
-bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
+bn_prelu_bwd_apply_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ gamma, const double* __restrict__ S1,
                           const double* __restrict__ S2, double inv_count,
-                          float* __restrict__ dst, long d_ss, double* __restrict__ dbias,
-                          float* __restrict__ dst_lo) {
-  extern __shared__ float red[];      // [C]
-  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+                          const YT* du, void* dst_v, long d_ss,
+                          double* __restrict__ dbias, void* dst_lo_v,
+                          const float* __restrict__ amax, float* __restrict__ scale_out) {
+  extern __shared__ float red[];      // [C] + [1]
+  for (int i = threadIdx.x; i < C + 1; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
+  float gs_scale = 1.f;
+  if constexpr (DF == PASE_FMT_F16X2) {
+    const float mdu = amax[0], mxh = amax[1];
+    float b = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      const float gi = fabsf((gamma ? gamma[i] : 1.f) * invstd[i]);
+      const float m1 = fabsf((float)(S1[i] * inv_count)), m2 = fabsf((float)(S2[i] * inv_count));
+      b = fmaxf(b, gi * (mdu + m1 + mxh * m2));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, off));
+    if ((threadIdx.x & 31) == 0) atomic_max_pos(&red[C], b);
+    __syncthreads();
+    gs_scale = f16_grad_scale(red[C] * 1.0001f);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      scale_out[0] = 1.f / gs_scale;
+      scale_out[1] = gs_scale;
+    }
+  }
   const int C4 = C >> 2;
   const int n = blockIdx.y;
   const long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,37 +367,47 @@ bn_prelu_bwd_apply_kernel(const float* __restrict__ y, long y_ss, int T, int C,
       isv[k] = invstd[c + k];
       gi[k] = (gamma ? gamma[c + k] : 1.f) * isv[k];
     }
-    const float* yn = y + (long)n * y_ss;
-    float* dn = dst + (long)n * d_ss;
+    const YT* yn = y + (long)n * y_ss;
+    const YT* un = du + (long)n * d_ss;
     for (long idx = idx0; idx < nthreads; idx += (long)gridDim.x * blockDim.x) {
-    const long t0 = (idx / C4) * RUN;
-    const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
-    float4 vs[RUN], ds[RUN];
+      const long t0 = (idx / C4) * RUN;
+      const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
+      float4 vs[RUN], ds[RUN];
 #pragma unroll
-    for (int i = 0; i < RUN; ++i)
-      if (i < nvalid) {
-        vs[i] = ld4(yn + (long)((int)t0 + i) * C + c);
-        ds[i] = ld4(dn + (long)((int)t0 + i) * C + c);
+      for (int i = 0; i < RUN; ++i)
+        if (i < nvalid) {
+          vs[i] = ld4t(yn + (long)((int)t0 + i) * C + c);
+          ds[i] = ld4t(un + (long)((int)t0 + i) * C + c);
+        }
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
+        if (i >= nvalid) break;
+        const int t = (int)t0 + i;
+        const float vv[4] = {vs[i].x, vs[i].y, vs[i].z, vs[i].w};
+        const float dd[4] = {ds[i].x, ds[i].y, ds[i].z, ds[i].w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float xh = (vv[k] - muv[k]) * isv[k];
+          o[k] = gi[k] * (dd[k] - m1[k] - xh * m2[k]);
+          acc[k] += o[k];
+        }
+        const long off = (long)n * d_ss + (long)t * C + c;
+        if constexpr (DF == PASE_FMT_F32) {
+          st4(reinterpret_cast<float*>(dst_v) + off, make_float4(o[0], o[1], o[2], o[3]));
+          if (dst_lo_v != nullptr)
+            st4(reinterpret_cast<float*>(dst_lo_v) + off,
+                make_float4(tf32_residual(o[0]), tf32_residual(o[1]), tf32_residual(o[2]),
+                            tf32_residual(o[3])));
+        } else if constexpr (DF == PASE_FMT_BF16) {
+          st4t(reinterpret_cast<__nv_bfloat16*>(dst_v) + off, make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+          st4_f16x2(reinterpret_cast<__half*>(dst_v) + off,
+                    reinterpret_cast<__half*>(dst_lo_v) + off,
+                    make_float4(o[0] * gs_scale, o[1] * gs_scale, o[2] * gs_scale,
+                                o[3] * gs_scale));
+        }
       }
-#pragma unroll
-    for (int i = 0; i < RUN; ++i) {
-      if (i >= nvalid) break;
-      const int t = (int)t0 + i;
-      const float vv[4] = {vs[i].x, vs[i].y, vs[i].z, vs[i].w};
-      const float dd[4] = {ds[i].x, ds[i].y, ds[i].z, ds[i].w};
-      float o[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float xh = (vv[k] - muv[k]) * isv[k];
-        o[k] = gi[k] * (dd[k] - m1[k] - xh * m2[k]);
-        acc[k] += o[k];
-      }
-      st4(dn + (long)t * C + c, make_float4(o[0], o[1], o[2], o[3]));
-      if (dst_lo != nullptr)
-        st4(dst_lo + (long)n * d_ss + (long)t * C + c,
-            make_float4(tf32_residual(o[0]), tf32_residual(o[1]), tf32_residual(o[2]),
-                        tf32_residual(o[3])));
-    }
     }
     if (dbias) {
 #pragma unroll
@@ -551,15 +631,23 @@ inline unsigned blocks_for(long total, int threads, int cap_mult = 8) {
 
 extern "C" {
 
-int pase_reflect_pad_wave(const float* x, float* dst, int N, int T, int padL, int padR,
-                          long pitch, void* stream) {
+int pase_reflect_pad_wave(const float* x, void* dst, void* dst_lo, int dst_fmt, int N, int T,
+                          int padL, int padR, long pitch, void* stream) {
   PASE_CHECK_ARG(x && dst && N > 0 && T > 0, "pase_reflect_pad_wave: bad args");
   PASE_CHECK_ARG(padL < T && padR < T, "pase_reflect_pad_wave: reflect pad (%d,%d) >= T=%d", padL,
                  padR, T);
+  PASE_CHECK_ARG(dst_fmt >= 0 && dst_fmt <= 2 && (dst_fmt != PASE_FMT_F16X2 || dst_lo),
+                 "pase_reflect_pad_wave: bad dst_fmt %d / missing lo", dst_fmt);
   const int Tp = T + padL + padR;
   PASE_CHECK_ARG(pitch >= Tp, "pase_reflect_pad_wave: pitch %ld < padded length %d", pitch, Tp);
   dim3 grid(blocks_for(Tp, 256, 4), N);
-  reflect_pad_wave_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dst, T, padL, Tp, pitch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dst_fmt == PASE_FMT_F32)
+    reflect_pad_wave_kernel<PASE_FMT_F32><<<grid, 256, 0, st>>>(x, dst, dst_lo, T, padL, Tp, pitch);
+  else if (dst_fmt == PASE_FMT_BF16)
+    reflect_pad_wave_kernel<PASE_FMT_BF16><<<grid, 256, 0, st>>>(x, dst, dst_lo, T, padL, Tp, pitch);
+  else
+    reflect_pad_wave_kernel<PASE_FMT_F16X2><<<grid, 256, 0, st>>>(x, dst, dst_lo, T, padL, Tp, pitch);
   PASE_LAUNCH_CHECK("pase_reflect_pad_wave");
   return PASE_OK;
 }
@@ -589,11 +677,11 @@ int pase_bn_eval_affine(const float* running_mean, const float* running_var, con
   return PASE_OK;
 }
 
-int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, int C,
-                          const float* scale, const float* shift, const float* alpha, float* dst,
-                          long dst_sample_stride, long dst_row_stride, int padL, int padR,
-                          float* pool, long pool_sample_stride, long pool_row_stride, int pool_d,
-                          int pool_T, float* dst_lo, void* stream) {
+int pase_bn_prelu_pad_fwd(const void* y, int y_bf16, long y_sample_stride, int N, int T, int C,
+                          const float* scale, const float* shift, const float* alpha, void* dst,
+                          void* dst_lo, int dst_fmt, long dst_sample_stride, long dst_row_stride,
+                          int padL, int padR, float* pool, long pool_sample_stride,
+                          long pool_row_stride, int pool_d, int pool_T, void* stream) {
   PASE_CHECK_ARG(y && dst && scale && shift && alpha, "pase_bn_prelu_pad_fwd: null pointer");
   PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0,
                  "pase_bn_prelu_pad_fwd: C=%d must be a positive multiple of 4", C);
@@ -601,28 +689,42 @@ int pase_bn_prelu_pad_fwd(const float* y, long y_sample_stride, int N, int T, in
                  "pase_bn_prelu_pad_fwd: reflect pad (%d,%d) >= T=%d", padL, padR, T);
   PASE_CHECK_ARG((dst_row_stride % 4) == 0 && (dst_sample_stride % 4) == 0 &&
                      (y_sample_stride % 4) == 0 && aligned16(y) && aligned16(dst),
-                 "pase_bn_prelu_pad_fwd: strides/pointers must be float4 aligned");
-  if (pool_d <= 1 && pool == nullptr) pool_d = 0;
+                 "pase_bn_prelu_pad_fwd: strides/pointers must be 4-element aligned");
+  PASE_CHECK_ARG(dst_fmt >= 0 && dst_fmt <= 2 && (dst_fmt != PASE_FMT_F16X2 || dst_lo),
+                 "pase_bn_prelu_pad_fwd: bad dst_fmt %d / missing lo", dst_fmt);
   if (pool == nullptr) pool_d = 0;
   const int Tp = T + padL + padR;
   const long threads = (long)(C / 4) * ((Tp + RUN - 1) / RUN);
   dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
-  bn_prelu_pad_fwd_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(
-      y, y_sample_stride, T, C, scale, shift, alpha, dst, dst_sample_stride, dst_row_stride, padL,
-      Tp, pool, pool_sample_stride, pool_row_stride, pool_d, pool_T, dst_lo);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PASE_FWD(YT, DF)                                                                       \
+  bn_prelu_pad_fwd_kernel<YT, DF><<<grid, THREADS, 0, st>>>(                                   \
+      reinterpret_cast<const YT*>(y), y_sample_stride, T, C, scale, shift, alpha, dst,         \
+      dst_sample_stride, dst_row_stride, padL, Tp, pool, pool_sample_stride, pool_row_stride, \
+      pool_d, pool_T, dst_lo)
+  if (y_bf16) {
+    if (dst_fmt == PASE_FMT_F32) PASE_FWD(__nv_bfloat16, PASE_FMT_F32);
+    else if (dst_fmt == PASE_FMT_BF16) PASE_FWD(__nv_bfloat16, PASE_FMT_BF16);
+    else PASE_FWD(__nv_bfloat16, PASE_FMT_F16X2);
+  } else {
+    if (dst_fmt == PASE_FMT_F32) PASE_FWD(float, PASE_FMT_F32);
+    else if (dst_fmt == PASE_FMT_BF16) PASE_FWD(float, PASE_FMT_BF16);
+    else PASE_FWD(float, PASE_FMT_F16X2);
+  }
+#undef PASE_FWD
   PASE_LAUNCH_CHECK("pase_bn_prelu_pad_fwd");
   return PASE_OK;
 }
 
-int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T, int C,
+int pase_bn_prelu_bwd_reduce(const void* y, int y_bf16, long y_sample_stride, int N, int T, int C,
                              const float* mean, const float* invstd, const float* scale,
-                             const float* shift, const float* alpha, const float* srcA,
-                             long a_sample_stride, long a_row_stride, int padL, int padR,
-                             const float* srcB, long b_sample_stride, long b_row_stride,
-                             int b_shift, const float* pool, long pool_sample_stride,
-                             long pool_row_stride, int pool_d, int pool_T, float* dst,
-                             long dst_sample_stride, double* S1, double* S2, double* dalpha,
-                             void* stream) {
+                             const float* shift, const float* alpha, const void* srcA,
+                             int a_bf16, long a_sample_stride, long a_row_stride, int padL,
+                             int padR, const float* srcB, long b_sample_stride,
+                             long b_row_stride, int b_shift, const float* pool,
+                             long pool_sample_stride, long pool_row_stride, int pool_d,
+                             int pool_T, void* dst, long dst_sample_stride, double* S1,
+                             double* S2, double* dalpha, float* amax, void* stream) {
   PASE_CHECK_ARG(y && mean && invstd && scale && shift && alpha && dst && S1 && S2 && dalpha &&
                      srcA,
                  "pase_bn_prelu_bwd_reduce: null pointer (srcA is mandatory)");
@@ -638,21 +740,40 @@ int pase_bn_prelu_bwd_reduce(const float* y, long y_sample_stride, int N, int T,
     if (gx > cap) gx = cap;
   }
   dim3 grid((unsigned)gx, N);
-  bn_prelu_bwd_reduce_kernel<<<grid, THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
-      y, y_sample_stride, T, C, mean, invstd, scale, shift, alpha, s, dst, dst_sample_stride, S1,
-      S2, dalpha);
+  const size_t sm = (3 * C + 2) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PASE_RED(YT, GT)                                                                     \
+  bn_prelu_bwd_reduce_kernel<YT, GT><<<grid, THREADS, sm, st>>>(                             \
+      reinterpret_cast<const YT*>(y), y_sample_stride, T, C, mean, invstd, scale, shift,     \
+      alpha, s, reinterpret_cast<YT*>(dst), dst_sample_stride, S1, S2, dalpha, amax)
+  if (y_bf16) {
+    if (a_bf16) PASE_RED(__nv_bfloat16, __nv_bfloat16);
+    else PASE_RED(__nv_bfloat16, float);
+  } else {
+    if (a_bf16) PASE_RED(float, __nv_bfloat16);
+    else PASE_RED(float, float);
+  }
+#undef PASE_RED
   PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_reduce");
   return PASE_OK;
 }
 
-int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, int C,
+int pase_bn_prelu_bwd_apply(const void* y, int y_bf16, long y_sample_stride, int N, int T, int C,
                             const float* mean, const float* invstd, const float* gamma,
-                            const double* S1, const double* S2, double count, float* dst,
-                            long dst_sample_stride, double* dbias_acc, float* dst_lo,
+                            const double* S1, const double* S2, double count, const void* du,
+                            void* dst, void* dst_lo, int dst_fmt, long dst_sample_stride,
+                            double* dbias_acc, const float* amax, float* scale_out,
                             void* stream) {
-  PASE_CHECK_ARG(y && mean && invstd && S1 && S2 && dst, "pase_bn_prelu_bwd_apply: null pointer");
+  PASE_CHECK_ARG(y && mean && invstd && S1 && S2 && du && dst,
+                 "pase_bn_prelu_bwd_apply: null pointer");
   PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 8192,
                  "pase_bn_prelu_bwd_apply: bad C=%d", C);
+  PASE_CHECK_ARG(dst_fmt >= 0 && dst_fmt <= 2, "pase_bn_prelu_bwd_apply: bad dst_fmt %d", dst_fmt);
+  PASE_CHECK_ARG(dst_fmt != PASE_FMT_F16X2 || (dst_lo && amax && scale_out && !y_bf16),
+                 "pase_bn_prelu_bwd_apply: the fp16-pair format needs dst_lo, amax, scale_out "
+                 "and fp32 y/du");
+  PASE_CHECK_ARG((dst_fmt == PASE_FMT_BF16) == (y_bf16 != 0),
+                 "pase_bn_prelu_bwd_apply: bf16 y/du goes with bf16 dst (and only with it)");
   const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
   long gx = (threads + THREADS - 1) / THREADS;
   if ((THREADS % (C / 4)) == 0) {
@@ -661,9 +782,17 @@ int pase_bn_prelu_bwd_apply(const float* y, long y_sample_stride, int N, int T, 
     if (gx > cap) gx = cap;
   }
   dim3 grid((unsigned)gx, N);
-  bn_prelu_bwd_apply_kernel<<<grid, THREADS, C * sizeof(float), (cudaStream_t)stream>>>(
-      y, y_sample_stride, T, C, mean, invstd, gamma, S1, S2, 1.0 / count, dst, dst_sample_stride,
-      dbias_acc, dst_lo);
+  const size_t sm = (C + 1) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PASE_APP(YT, DF)                                                                      \
+  bn_prelu_bwd_apply_kernel<YT, DF><<<grid, THREADS, sm, st>>>(                               \
+      reinterpret_cast<const YT*>(y), y_sample_stride, T, C, mean, invstd, gamma, S1, S2,     \
+      1.0 / count, reinterpret_cast<const YT*>(du), dst, dst_sample_stride, dbias_acc,        \
+      dst_lo, amax, scale_out)
+  if (dst_fmt == PASE_FMT_BF16) PASE_APP(__nv_bfloat16, PASE_FMT_BF16);
+  else if (dst_fmt == PASE_FMT_F16X2) PASE_APP(float, PASE_FMT_F16X2);
+  else PASE_APP(float, PASE_FMT_F32);
+#undef PASE_APP
   PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_apply");
   return PASE_OK;
 }

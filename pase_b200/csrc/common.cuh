@@ -1,6 +1,8 @@
 // Shared helpers for the pase_b200 CUDA library (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdint>
 #include "../../include/pase_b200.h"
@@ -53,4 +55,76 @@ __device__ __forceinline__ int reflect_idx(int t, int T) {
   if (t < 0) t = -t;
   if (t >= T) t = 2 * (T - 1) - t;
   return t;
+}
+
+// ---- storage formats of activation-sized tensors (C-ABI `*_fmt` / `*_bf16` arguments) ----
+//   PASE_FMT_F32     fp32 (optionally with a tf32-residual twin for the 3xTF32 GEMM mode)
+//   PASE_FMT_BF16    bf16
+//   PASE_FMT_F16X2   fp16 pair x = hi + 2^-11 lo' (3xF16 GEMM mode), two arrays
+#define PASE_FMT_F32 0
+#define PASE_FMT_BF16 1
+#define PASE_FMT_F16X2 2
+#define PASE_F16_LO_MUL 2048.0f        // lo' = rn_f16((x - hi) * 2^11)
+
+// 4 consecutive elements <-> float4 (fp32: 16-byte, bf16: 8-byte accesses)
+__device__ __forceinline__ float4 ld4t(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ float4 ld4t(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4t(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4t(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+// round-trip through the storage type (what a later reader of the stored value sees)
+__device__ __forceinline__ float4 rt4t(const float*, float4 v) { return v; }
+__device__ __forceinline__ float4 rt4t(const __nv_bfloat16*, float4 v) {
+  return make_float4(__bfloat162float(__float2bfloat16_rn(v.x)),
+                     __bfloat162float(__float2bfloat16_rn(v.y)),
+                     __bfloat162float(__float2bfloat16_rn(v.z)),
+                     __bfloat162float(__float2bfloat16_rn(v.w)));
+}
+// fp16 pair of the 3xF16 GEMM mode: hi = rn_f16(x), lo' = rn_f16((x - hi) * 2^11)
+__device__ __forceinline__ void f16_split(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * PASE_F16_LO_MUL);
+}
+__device__ __forceinline__ void st4_f16x2(__half* hi, __half* lo, float4 v) {
+  __half h[4], l[4];
+  f16_split(v.x, h[0], l[0]);
+  f16_split(v.y, h[1], l[1]);
+  f16_split(v.z, h[2], l[2]);
+  f16_split(v.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<const uint2*>(l);
+}
+// lo = rn_tf32(x - trunc_tf32(x)): the part of x the tensor core drops when it reads x as tf32
+__device__ __forceinline__ float tf32_residual(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  uint32_t u = __float_as_uint(r);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+// Power-of-two scale that places values bounded by `bound` (> 0) below 2^14 in fp16 (3xF16
+// gradient operands): s = 2^(14 - ceil(log2(bound))), clamped to a finite range; 1 for 0.
+__device__ __forceinline__ float f16_grad_scale(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(bound, &e);                    // bound = m * 2^e, m in [0.5, 1)  ->  bound <= 2^e
+  int k = 14 - e;
+  k = k > 100 ? 100 : (k < -100 ? -100 : k);
+  return ldexpf(1.f, k);
+}
+// max over non-negative floats through their bit patterns (order-preserving for x >= 0)
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v) {
+  atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }

@@ -9,11 +9,17 @@
 //       both operands MN-major in shared memory (transpose bits set in the UMMA
 //       instruction descriptor); split over the reduction, fp32 red.add epilogue.
 //
-// Numerics: kind::tf32 MMAs with fp32 accumulation in TMEM.
-//   mode 0: single TF32 pass (10-bit mantissa operands);
-//   mode 1: 3xTF32 error-compensated: operands are pre-split into exactly
-//           representable tf32 "hi" and "lo" parts (hi + lo == fp32 value to 2^-22),
-//           D = Ahi*Bhi + Alo*Bhi + Ahi*Blo  -> fp32-equivalent products.
+// Numerics (`mode`), fp32 accumulation in TMEM in every mode:
+//   0  TF32    kind::tf32, fp32 operands read as tf32 (10-bit mantissa);
+//   1  3xTF32  error-compensated: operands pre-split into exactly representable tf32 "hi"
+//              and "lo" parts, D = Ahi*Bhi + Alo*Bhi + Ahi*Blo -> fp32-equivalent products;
+//   2  BF16    kind::f16 with bf16 operands (one pass at twice the TF32 rate, half the bytes);
+//   3  3xF16   error-compensated fp16: x = hi + 2^-11 lo', hi = rn_f16(x),
+//              lo' = rn_f16((x - hi) 2^11) (both 11-bit significands -> 22-bit products like
+//              3xTF32, at half the tensor time and half the operand bytes).  The scaled
+//              correction products go to a SECOND TMEM accumulator:
+//              D = [Ahi*Bhi] + 2^-11 [Alo'*Bhi + Ahi*Blo'].  Operands must fit fp16's range
+//              (gradients are pre-scaled by a power of two; `alpha_dev` undoes it).
 //
 // Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
 // elected lane), warps 2-17 = 16 epilogue warps (tcgen05.ld -> fp32 register sums -> bias /
@@ -21,14 +27,27 @@
 // 128-byte rows with the 128B swizzle; two TMEM accumulator buffers per CTA.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace {
 
 constexpr int BM = 128;
-constexpr int BKF = 32;                  // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int UMMA_K = 8;                // tf32
-constexpr uint32_t SPIN_LIMIT = 200u * 1000u * 1000u;
+constexpr uint32_t SPIN_LIMIT = 16u * 1000u * 1000u;   // >> any legitimate wait (each poll suspends)
+constexpr float F16_LO_SCALE = 1.0f / 2048.0f;       // 2^-11, see pase_split_f16
+
+// ---- numerics modes ------------------------------------------------------------------
+template <int MODE>
+struct ModeT {
+  static constexpr int ESZ = MODE >= 2 ? 2 : 4;            // operand element size
+  static constexpr bool K16 = MODE >= 2;                   // kind::f16 (else kind::tf32)
+  static constexpr bool SPLIT = (MODE == 1 || MODE == 3);  // hi/lo operands, 3 MMAs / product
+  static constexpr int NACC = MODE == 3 ? 2 : 1;           // TMEM accumulators per buffer
+  static constexpr int UMMA_K = 32 / ESZ;                  // 8 (tf32) / 16 (bf16, f16)
+  static constexpr int EB = 128 / ESZ;                     // elements per 128-byte row
+  // operand format of the instruction descriptor: kind::tf32 -> 2; kind::f16: f16 0, bf16 1
+  static constexpr uint32_t FMT = MODE <= 1 ? 2u : (MODE == 2 ? 1u : 0u);
+};
 
 // ------------------------------------------------------------------ PTX helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -53,30 +72,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// A wait that never completes is a pipeline bug or a bad tensor map: record (tag, block,
+// thread) in a mapped host word (survives the trap; read back into pase_last_error()).
+__device__ unsigned int* g_tc_diag = nullptr;
+__device__ __noinline__ void mbar_timeout(int tag) {
+  unsigned int* d = g_tc_diag;
+  if (d != nullptr && atomicCAS(d, 0u, (unsigned)tag) == 0u) {
+    d[1] = blockIdx.x + (blockIdx.y << 12) + (blockIdx.z << 24);
+    d[2] = threadIdx.x;
+    __threadfence_system();
+  }
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SPIN_LIMIT) {
-      printf("pase tc gemm: mbarrier wait timed out (tag %d, block %d,%d,%d thread %d)\n", tag,
-             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-// Epilogue warps wait for a whole accumulator chunk (thousands of cycles): an optional
-// back-off between polls leaves the issue slots of their scheduler to the MMA / TMA warps.
-// PASE_B200_EPI_SLEEP_NS (read once on the host) sets it; 0 = plain polling.
-__constant__ int c_epi_sleep_ns = 0;
-__device__ __forceinline__ void mbar_wait_epi(uint64_t* bar, uint32_t parity, int tag) {
-  uint32_t spins = 0;
-  const int ns = c_epi_sleep_ns;
-  while (!mbar_try_wait(bar, parity)) {
-    if (ns > 0) __nanosleep(ns);
-    if (++spins > SPIN_LIMIT) {
-      printf("pase tc gemm: mbarrier wait timed out (tag %d, block %d,%d,%d thread %d)\n", tag,
-             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
+    if (++spins > SPIN_LIMIT) mbar_timeout(tag);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -120,29 +131,49 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
                : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Warp-convergent variants: every lane of the MMA warp executes the surrounding loop and
+// Warp-convergent MMA issue: every lane of the MMA warp executes the surrounding loop and
 // one elected lane issues.  Keeping the warp converged lets ptxas hold descriptors and TMEM
 // addresses in uniform registers; under `if (lane == 0)` every UTCHMMA is preceded by an
 // ELECT / R2UR.BROADCAST / BRA.U.ANY sequence and the issue thread, not the tensor pipe,
 // bounds the MMA rate (profiles/r01_history.md).
-__device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+//   K16: kind::f16 (bf16 / fp16 operands, format in the instruction descriptor), else
+//   kind::tf32.  CG: cta_group (2 = CTA pair, M = 256, issued by the leader only).
+template <bool K16, int CG>
+__device__ __forceinline__ void umma_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  if constexpr (!K16 && CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if constexpr (!K16 && CG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if constexpr (K16 && CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
   asm volatile(
@@ -199,16 +230,6 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
                : "memory");
 }
-__device__ __forceinline__ void umma2_tf32_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // commit of all prior MMAs of this thread; arrives on the barrier at the same CTA-relative
 // offset in both CTAs of the pair
 __device__ __forceinline__ void umma2_commit_mc_w(uint64_t* bar) {
@@ -219,11 +240,6 @@ __device__ __forceinline__ void umma2_commit_mc_w(uint64_t* bar) {
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
       "[%0], m;\n\t}" ::"r"(smem_u32(bar))
       : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -240,12 +256,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128B swizzle.
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
 //   K-major : rows of 128 B, 8-row atoms of 1024 B -> SBO = 1024 B, LBO unused.
-//   MN-major: 128 B (32 fp32) along MN per row, 8 k-rows per 1024 B atom; SBO = 1024 B
-//             (next 8 k), LBO = byte distance between consecutive 32-element MN blocks.
+//   MN-major: 128 B along MN per row, 8 k-rows per 1024 B atom; SBO = 1024 B (next 8 k),
+//             LBO = byte distance between consecutive 128-byte MN blocks.
 //   MN-major fp32/tf32 operands must use the 32-byte-base 128B swizzle (layout type 1,
-//   TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 128 B (MN) x 4 k-rows, SBO = 512 B.
+//   TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 128 B (MN) x 4 k-rows, SBO = 512 B;
+//   16-bit MN-major operands use the plain 128B swizzle (layout type 2).
 template <int LAYOUT = 2>
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
                                               uint32_t sbo_bytes) {
@@ -257,9 +274,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)LAYOUT << 61;                 // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
-// Instruction descriptor: D=f32, A=B=tf32 (cute::UMMA::InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+// Instruction descriptor (cute::UMMA::InstrDescriptor bit layout): D = f32 (bit 4), A / B
+// format at bits 7 / 10, transpose bits 15 / 16, N >> 3 at 17, M >> 4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn,
+                                                  uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -286,7 +305,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Thread layout shared by both kernels: warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// Thread layout shared by all kernels: warp 0 = TMA producer, warp 1 = TMEM owner + MMA
 // issuer, warps 2..17 = 16 epilogue warps.  Epilogue warp w reads TMEM lanes 32*(w%4)..
 // (hardware restriction) and owns column chunk (w-2)/4 of the tile, so every warp folds /
 // stores only 32 columns: short per-warp instruction streams, 4 warps per scheduler.
@@ -357,29 +376,198 @@ __device__ __forceinline__ void store_chunk(float* stg, const float (&v)[32], in
   }
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// bf16 output: the same transpose with rows of 16 bf16 (32 B) -- two passes of 16 columns;
+// after the transpose a lane owns 16 B (8 columns) of a row, 2 lanes cover a 32 B sector.
+__device__ __forceinline__ void store_chunk_bf16(float* stg_f, const float (&v)[32], int lane,
+                                                 __nv_bfloat16* __restrict__ C, long ldc,
+                                                 long orow, int nlim, int nb, bool vec_ok) {
+  uint4* stg = reinterpret_cast<uint4*>(stg_f);          // 64 chunks of 16 B
+  const int sw = (lane >> 2) & 1;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c = pass * 16;
+    stg[lane * 2 + (0 ^ sw)] = make_uint4(pack_bf16(v[c + 0], v[c + 1]), pack_bf16(v[c + 2], v[c + 3]),
+                                          pack_bf16(v[c + 4], v[c + 5]), pack_bf16(v[c + 6], v[c + 7]));
+    stg[lane * 2 + (1 ^ sw)] = make_uint4(pack_bf16(v[c + 8], v[c + 9]), pack_bf16(v[c + 10], v[c + 11]),
+                                          pack_bf16(v[c + 12], v[c + 13]), pack_bf16(v[c + 14], v[c + 15]));
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = it * 16 + (lane >> 1), h = lane & 1;
+      const uint4 val = stg[r * 2 + (h ^ ((r >> 2) & 1))];
+      const long orow_r = __shfl_sync(0xffffffffu, orow, r);
+      const int nlim_r = __shfl_sync(0xffffffffu, nlim, r);
+      const int n = nb + c + h * 8;
+      __nv_bfloat16* cp = C + orow_r * ldc + n;
+      if (n + 7 < nlim_r && vec_ok) {
+        *reinterpret_cast<uint4*>(cp) = val;
+      } else {
+        const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n + j < nlim_r) {
+            const uint16_t bits = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
+            *reinterpret_cast<uint16_t*>(cp + j) = bits;
+          }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // one 64-bit shared-memory descriptor = constant bits | (address >> 4)
 template <int LAYOUT>
 __device__ __forceinline__ uint64_t desc_hi_bits(uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return make_desc<LAYOUT>(0, lbo_bytes, sbo_bytes);
 }
 
-// BK = fp32 elements per k-block: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows,
-// SWIZZLE_64B; used with BN = 256 so that four pipeline stages still fit in shared memory).
-// Why BN = 256: a 128xNx8 tf32 UMMA reads (128 + N) * 32 B of shared memory in N/2 clocks --
+// ROWB = bytes per k-block row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B; used with BN = 256 so
+// that four pipeline stages still fit in shared memory).
+// Why BN = 256: a 128xNx(32 B) UMMA reads (128 + N) * 32 B of shared memory in N/2 clocks --
 // 128 B/clk at N = 128, i.e. the whole shared-memory bandwidth of the SM before the TMA fills
 // are even counted (measured tensor-pipe activity ~58 %); N = 256 needs 96 B/clk.
-template <int BN, bool SPLIT, int BK>
+template <int BN, int MODE, int ROWB>
 struct NTCfg {
-  static constexpr int ROW_BYTES = BK * 4;
-  static constexpr int A_BYTES = BM * ROW_BYTES;
-  static constexpr int B_BYTES = BN * ROW_BYTES;
-  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int TMEM_COLS = 2 * BN;      // two accumulator buffers
-  static constexpr int CPW = (BN / 32 + 3) / 4; // 32-column chunks per epilogue warp
+  using MT = ModeT<MODE>;
+  static constexpr int BK = ROWB / MT::ESZ;                // elements per k-block
+  static constexpr int A_BYTES = BM * ROWB;
+  static constexpr int B_BYTES = BN * ROWB;
+  static constexpr int STAGE_BYTES = (MT::SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int ACC_COLS = MT::NACC * BN;           // TMEM columns of one buffer
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;           // two accumulator buffers
+  static constexpr int CPW = (BN / 32 + 3) / 4;            // 32-column chunks per epilogue warp
   static constexpr int EPI_ACTIVE = BN >= 128 ? 16 : 4 * (BN / 32);
-  static constexpr int LAYOUT = BK == 32 ? 2 : 4;          // SWIZZLE_128B : SWIZZLE_64B
-  static constexpr int SBO = 8 * ROW_BYTES;                // 8-row core-matrix group
+  static constexpr int LAYOUT = ROWB == 128 ? 2 : 4;       // SWIZZLE_128B : SWIZZLE_64B
+  static constexpr int SBO = 8 * ROWB;                     // 8-row core-matrix group
+  static constexpr int KSTEPS = ROWB / 32;                 // UMMA k-steps (32 B each) per block
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
+
+// The MMAs of one k-block (all lanes converged; elected issue inside umma_w).
+//   plain : D += A*B;   3xTF32: D += Al*Bh + Ah*Bl + Ah*Bh (one accumulator);
+//   3xF16 : Dc (+BN columns) += Al'*Bh + Ah*Bl',  D += Ah*Bh.
+template <int MODE, int CG, int KSTEPS, int KSTEP_DESC>
+__device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t corr_off, uint64_t dah,
+                                             uint64_t dbh, uint64_t dal, uint64_t dbl,
+                                             uint32_t idesc, uint32_t first) {
+  using MT = ModeT<MODE>;
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) {
+    const uint32_t acc = (k == 0) ? first : 1u;
+    const uint64_t o = (uint64_t)(k * KSTEP_DESC);
+    if constexpr (MODE == 1) {
+      umma_w<MT::K16, CG>(d_tmem, dal + o, dbh + o, idesc, acc);
+      umma_w<MT::K16, CG>(d_tmem, dah + o, dbl + o, idesc, 1);
+      umma_w<MT::K16, CG>(d_tmem, dah + o, dbh + o, idesc, 1);
+    } else if constexpr (MODE == 3) {
+      umma_w<MT::K16, CG>(d_tmem + corr_off, dal + o, dbh + o, idesc, acc);
+      umma_w<MT::K16, CG>(d_tmem + corr_off, dah + o, dbl + o, idesc, 1);
+      umma_w<MT::K16, CG>(d_tmem, dah + o, dbh + o, idesc, acc);
+    } else {
+      umma_w<MT::K16, CG>(d_tmem, dah + o, dbh + o, idesc, acc);
+    }
+  }
+}
+
+// Epilogue: fold one finished TMEM buffer (32 columns at `taddr`) into fp32 register sums.
+template <int MODE>
+__device__ __forceinline__ void fold_chunk(uint32_t taddr, uint32_t corr_off, float (&sums)[32],
+                                           bool first) {
+  uint32_t raw[32];
+  tmem_ld32(taddr, raw);
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sums[j] = __uint_as_float(raw[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sums[j] += __uint_as_float(raw[j]);
+  }
+  if constexpr (MODE == 3) {          // scaled correction accumulator
+    tmem_ld32(taddr + corr_off, raw);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sums[j] = fmaf(__uint_as_float(raw[j]), F16_LO_SCALE, sums[j]);
+  }
+}
+
+struct NTArgs {
+  int R;
+  void* C;
+  long ldc;
+  int M, N, K;
+  float alpha;
+  const float* alpha_dev;          // optional device scalar multiplied into alpha
+  const float* bias;
+  RowMap rm;
+  double* colsum;
+  double* colsumsq;
+  int accumulate, flush_kb, stages, stat_cols;
+};
+
+// Output stage shared by the 1-CTA and CTA-pair NT kernels: alpha / bias, row map and
+// validity, store (fp32 or bf16), BatchNorm column statistics of the fp32 values.
+template <int CPW, bool OUT16>
+__device__ __forceinline__ void nt_output(float (&sums)[CPW][32], const NTArgs& a, float alpha,
+                                          int m0, int n0, int cc0, int q, int lane, float* stg,
+                                          float* s_stats, bool vec_ok) {
+  const int M = a.M, N = a.N;
+  const int m = m0 + q * 32 + lane;
+  long orow = 0;
+  int nlim = 0;                            // columns [0, nlim) of this row are valid
+  if (m < M) {
+    const int g = m / a.rm.rows_in;
+    const int u = m - g * a.rm.rows_in;
+    orow = (long)g * a.rm.rows_out + u;
+    const long lim = (long)(a.rm.t_valid - u * a.rm.fold) * a.rm.cols_per_fold;
+    nlim = lim <= 0 ? 0 : (lim >= N ? N : (int)lim);
+  }
+  const bool want_stats = a.colsum != nullptr;
+#pragma unroll
+  for (int h = 0; h < CPW; ++h) {
+    const int nb = n0 + (cc0 + 4 * h) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = sums[h][j] * alpha;
+      if (a.bias != nullptr && nb + j < N) x += __ldg(a.bias + nb + j);
+      sums[h][j] = x;
+    }
+    if constexpr (OUT16)
+      store_chunk_bf16(stg, sums[h], lane, reinterpret_cast<__nv_bfloat16*>(a.C), a.ldc, orow,
+                       nlim, nb, vec_ok);
+    else
+      store_chunk<false>(stg, sums[h], lane, reinterpret_cast<float*>(a.C), a.ldc, orow, nlim, nb,
+                         vec_ok, a.accumulate);
+    if (want_stats) {
+      float sq[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sums[h][j] = (nb + j < nlim) ? sums[h][j] : 0.f;
+        sq[j] = sums[h][j] * sums[h][j];
+      }
+      const float s1 = colsum32(sums[h], lane);
+      const float s2 = colsum32(sq, lane);
+      if (nb + lane < N) {
+        atomicAdd(&s_stats[nb + lane], s1);
+        atomicAdd(&s_stats[a.stat_cols + nb + lane], s2);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void flush_stats(const NTArgs& a, const float* s_stats) {
+  asm volatile("bar.sync 1, 512;" ::: "memory");     // the 16 epilogue warps only
+  for (int col = threadIdx.x - 64; col < a.N; col += N_EPI_WARPS * 32) {
+    const float s = s_stats[col], b2 = s_stats[a.stat_cols + col];
+    if (s != 0.f || b2 != 0.f) {
+      atomicAdd(a.colsum + col, (double)s);
+      atomicAdd(a.colsumsq + col, (double)b2);
+    }
+  }
+}
 
 // ------------------------------------------------------------------ NT kernel ----
 // Persistent: CTA b processes tiles b, b+grid, ... (n-tile fastest so concurrently running
@@ -387,18 +575,18 @@ struct NTCfg {
 // TMEM buffers; the epilogue warps fold each finished buffer into fp32 register sums with
 // round-to-nearest adds (the tensor core's own accumulator rounds toward zero, which drifts
 // over long K) while the MMAs of the next chunk / next tile run.
-template <int BN, bool SPLIT, int BK>
+template <int BN, int MODE, int ROWB, bool OUT16>
 __global__ void __launch_bounds__(NTHREADS_V3, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-                  int R, float* __restrict__ C, long ldc, int M, int N, int K, float alpha,
-                  const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
-                  double* __restrict__ colsumsq, int accumulate, int flush_kb, int stages,
-                  int stat_cols) {
-  using Cfg = NTCfg<BN, SPLIT, BK>;
+                  const NTArgs a) {
+  using Cfg = NTCfg<BN, MODE, ROWB>;
+  using MT = ModeT<MODE>;
+  constexpr int BK = Cfg::BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int stages = a.stages;
   uint8_t* tiles = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -409,12 +597,14 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   float* s_stats = s_out + OUT_STAGE_BYTES / 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = a.M, N = a.N, K = a.K, R = a.R;
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
   const int total_tiles = n_tiles * m_tiles;
   const int nkb = (K + BK - 1) / BK;
+  int flush_kb = a.flush_kb;
   if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
   const int nchunks = (nkb + flush_kb - 1) / flush_kb;
-  const bool want_stats = colsum != nullptr;
+  const bool want_stats = a.colsum != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -428,13 +618,13 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
     fence_barrier_init();
     tmap_prefetch(&mAhi);
     tmap_prefetch(&mBhi);
-    if (SPLIT) {
+    if (MT::SPLIT) {
       tmap_prefetch(&mAlo);
       tmap_prefetch(&mBlo);
     }
   }
   if (want_stats)
-    for (int i = threadIdx.x; i < 2 * stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * a.stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -455,7 +645,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           const int kf = kb * BK;
           tma_load_2d(st, &mAhi, &full_bar[s], acol, arow);
           tma_load_2d(st + Cfg::A_BYTES, &mBhi, &full_bar[s], kf, n0);
-          if (SPLIT) {
+          if (MT::SPLIT) {
             tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mAlo, &full_bar[s], acol, arow);
             tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mBlo, &full_bar[s], kf, n0);
           }
@@ -474,7 +664,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // all 32 lanes run the loop (converged); one elected lane issues each MMA / commit
-    constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0, MT::FMT);
     const uint64_t dconst = desc_hi_bits<Cfg::LAYOUT>(16, Cfg::SBO);
     const uint32_t tiles_u32 = smem_u32(tiles);
     const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -486,29 +676,19 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         const uint32_t b = c & 1, aph = (c >> 1) & 1;
         mbar_wait(&acc_empty[b], aph ^ 1, 4);
         tc_fence_after();
-        const uint32_t d_tmem = tm0 + b * BN;
+        const uint32_t d_tmem = tm0 + b * Cfg::ACC_COLS;
         const int kb_lo = ch * flush_kb;
         const int kb_hi = (kb_lo + flush_kb < nkb) ? kb_lo + flush_kb : nkb;
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[s], ph, 2);
           tc_fence_after();
-          // descriptor = constant bits + (byte address >> 4); k-step of 8 tf32 = +32 B = +2
+          // descriptor = constant bits + (byte address >> 4); k-step of 32 B = +2
           const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
           const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
           const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
           const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
-          const uint32_t first = (kb == kb_lo) ? 0u : 1u;
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t acc = (k == 0) ? first : 1u;
-            if (SPLIT) {
-              umma_tf32_w(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
-              umma_tf32_w(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
-              umma_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
-            } else {
-              umma_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
-            }
-          }
+          issue_kblock<MODE, 1, Cfg::KSTEPS, 2>(d_tmem, BN, dah, dbh, dal, dbl, idesc,
+                                                (kb == kb_lo) ? 0u : 1u);
           umma_commit_w(&empty_bar[s]);          // frees the smem stage once the MMAs retire
           if (++s == stages) {
             s = 0;
@@ -526,7 +706,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
     const int cc0 = e >> 2;                      // first 32-column chunk of this warp
     if (cc0 < BN / 32) {
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+      const bool vec_ok = OUT16 ? (((a.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0))
+                                : (((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0));
+      const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
       float* stg = s_out + e * OUT_STG_FLOATS;
       uint32_t c = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -534,72 +716,20 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         float sums[Cfg::CPW][32];
         for (int ch = 0; ch < nchunks; ++ch, ++c) {
           const uint32_t b = c & 1, aph = (c >> 1) & 1;
-          mbar_wait_epi(&acc_full[b], aph, 3);
+          mbar_wait(&acc_full[b], aph, 3);
           tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < Cfg::CPW; ++h) {
-            uint32_t raw[32];
-            tmem_ld32(lane_addr + b * BN + (cc0 + 4 * h) * 32, raw);
-            if (ch == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sums[h][j] = __uint_as_float(raw[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sums[h][j] += __uint_as_float(raw[j]);
-            }
-          }
+          for (int h = 0; h < Cfg::CPW; ++h)
+            fold_chunk<MODE>(lane_addr + b * Cfg::ACC_COLS + (cc0 + 4 * h) * 32, BN, sums[h],
+                             ch == 0);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[b]);        // buffer may be overwritten now
         }
-        // ---- output: bias, row map / validity, optional accumulate, BatchNorm statistics ----
-        const int m = m0 + q * 32 + lane;
-        long orow = 0;
-        int nlim = 0;                            // columns [0, nlim) of this row are valid
-        if (m < M) {
-          const int g = m / rm.rows_in;
-          const int u = m - g * rm.rows_in;
-          orow = (long)g * rm.rows_out + u;
-          const long lim = (long)(rm.t_valid - u * rm.fold) * rm.cols_per_fold;
-          nlim = lim <= 0 ? 0 : (lim >= N ? N : (int)lim);
-        }
-#pragma unroll
-        for (int h = 0; h < Cfg::CPW; ++h) {
-          const int nb = n0 + (cc0 + 4 * h) * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = sums[h][j] * alpha;
-            if (bias != nullptr && nb + j < N) x += __ldg(bias + nb + j);
-            sums[h][j] = x;
-          }
-          store_chunk<false>(stg, sums[h], lane, C, ldc, orow, nlim, nb, vec_ok, accumulate);
-          if (want_stats) {
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sums[h][j] = (nb + j < nlim) ? sums[h][j] : 0.f;
-              sq[j] = sums[h][j] * sums[h][j];
-            }
-            const float s1 = colsum32(sums[h], lane);
-            const float s2 = colsum32(sq, lane);
-            if (nb + lane < N) {
-              atomicAdd(&s_stats[nb + lane], s1);
-              atomicAdd(&s_stats[stat_cols + nb + lane], s2);
-            }
-          }
-        }
+        nt_output<Cfg::CPW, OUT16>(sums, a, alpha, m0, n0, cc0, q, lane, stg, s_stats, vec_ok);
       }
     }
-    if (want_stats) {
-      asm volatile("bar.sync 1, 512;" ::: "memory");     // the 16 epilogue warps only
-      for (int col = threadIdx.x - 64; col < N; col += N_EPI_WARPS * 32) {
-        const float a = s_stats[col], b2 = s_stats[stat_cols + col];
-        if (a != 0.f || b2 != 0.f) {
-          atomicAdd(colsum + col, (double)a);
-          atomicAdd(colsumsq + col, (double)b2);
-        }
-      }
-    }
+    if (want_stats) flush_stats(a, s_stats);
     tc_fence_before();
   }
   __syncthreads();
@@ -619,33 +749,36 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 //     `empty` / `acc_full` flip in both CTAs; each CTA's producer waits on its own `empty`.
 //   * each CTA's 16 epilogue warps drain the CTA's own TMEM (its 128 rows x BN columns) and
 //     release the buffer on the leader's `acc_empty` (count = both CTAs' epilogue warps).
-template <int BN, bool SPLIT>
+template <int BN, int MODE>
 struct NT2Cfg {
-  static constexpr int BK = 32;
-  static constexpr int ROW_BYTES = BK * 4;
-  static constexpr int A_BYTES = BM * ROW_BYTES;
+  using MT = ModeT<MODE>;
+  static constexpr int ROWB = 128;
+  static constexpr int BK = ROWB / MT::ESZ;
+  static constexpr int A_BYTES = BM * ROWB;
   static constexpr int BH = BN / 2;                           // B rows held by one CTA
-  static constexpr int B_BYTES = BH * ROW_BYTES;
-  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);   // per CTA
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int B_BYTES = BH * ROWB;
+  static constexpr int STAGE_BYTES = (MT::SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);   // per CTA
+  static constexpr int ACC_COLS = MT::NACC * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int CPW = (BN / 32 + 3) / 4;
   static constexpr int EPI_ACTIVE = BN >= 128 ? 16 : 4 * (BN / 32);
-  static constexpr int SBO = 8 * ROW_BYTES;
+  static constexpr int SBO = 8 * ROWB;
+  static constexpr int KSTEPS = ROWB / 32;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
 
-template <int BN, bool SPLIT>
+template <int BN, int MODE, bool OUT16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS_V3, 1)
 tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                    const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-                   int R, float* __restrict__ C, long ldc, int M, int N, int K, float alpha,
-                   const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
-                   double* __restrict__ colsumsq, int accumulate, int flush_kb, int stages,
-                   int stat_cols) {
-  using Cfg = NT2Cfg<BN, SPLIT>;
+                   const NTArgs a) {
+  using Cfg = NT2Cfg<BN, MODE>;
+  using MT = ModeT<MODE>;
   constexpr int BK = Cfg::BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int stages = a.stages;
   uint8_t* tiles = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -659,12 +792,14 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int M = a.M, N = a.N, K = a.K, R = a.R;
   const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + 2 * BM - 1) / (2 * BM);
   const int total_tiles = n_tiles * m_tiles;
   const int nkb = (K + BK - 1) / BK;
+  int flush_kb = a.flush_kb;
   if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
   const int nchunks = (nkb + flush_kb - 1) / flush_kb;
-  const bool want_stats = colsum != nullptr;
+  const bool want_stats = a.colsum != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -678,13 +813,13 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
     fence_barrier_init();
     tmap_prefetch(&mAhi);
     tmap_prefetch(&mBhi);
-    if (SPLIT) {
+    if (MT::SPLIT) {
       tmap_prefetch(&mAlo);
       tmap_prefetch(&mBlo);
     }
   }
   if (want_stats)
-    for (int i = threadIdx.x; i < 2 * stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * a.stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
   if (warp == 1) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);      // same warp in both CTAs
   tc_fence_before();
   __syncthreads();
@@ -708,7 +843,7 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
           const int kf = kb * BK;
           tma2_load_2d(st, &mAhi, fb, acol, arow);
           tma2_load_2d(st + Cfg::A_BYTES, &mBhi, fb, kf, n0);
-          if (SPLIT) {
+          if (MT::SPLIT) {
             tma2_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mAlo, fb, acol, arow);
             tma2_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mBlo, fb, kf, n0);
           }
@@ -727,8 +862,8 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     if (leader) {
-      // converged warp, elected issue (see umma_tf32_w); M = 256 across the pair
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN, 0, 0);
+      // converged warp, elected issue (see umma_w); M = 256 across the pair
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN, 0, 0, MT::FMT);
       const uint64_t dconst = desc_hi_bits<2>(16, Cfg::SBO);
       const uint32_t tiles_u32 = smem_u32(tiles);
       const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -740,7 +875,7 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
           const uint32_t b = c & 1, aph = (c >> 1) & 1;
           mbar_wait(&acc_empty[b], aph ^ 1, 24);
           tc_fence_after();
-          const uint32_t d_tmem = tm0 + b * BN;
+          const uint32_t d_tmem = tm0 + b * Cfg::ACC_COLS;
           const int kb_lo = ch * flush_kb;
           const int kb_hi = (kb_lo + flush_kb < nkb) ? kb_lo + flush_kb : nkb;
           for (int kb = kb_lo; kb < kb_hi; ++kb) {
@@ -750,18 +885,8 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
             const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
             const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
-            const uint32_t first = (kb == kb_lo) ? 0u : 1u;
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint32_t acc = (k == 0) ? first : 1u;
-              if (SPLIT) {
-                umma2_tf32_w(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
-                umma2_tf32_w(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
-                umma2_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
-              } else {
-                umma2_tf32_w(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
-              }
-            }
+            issue_kblock<MODE, 2, Cfg::KSTEPS, 2>(d_tmem, BN, dah, dbh, dal, dbl, idesc,
+                                                  (kb == kb_lo) ? 0u : 1u);
             umma2_commit_mc_w(&empty_bar[s]);        // frees the stage in both CTAs
             if (++s == stages) {
               s = 0;
@@ -780,8 +905,11 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
     const int cc0 = e >> 2;
     if (cc0 < BN / 32) {
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+      const bool vec_ok = OUT16 ? (((a.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0))
+                                : (((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0));
+      const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
       float* stg = s_out + e * OUT_STG_FLOATS;
+      const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
       uint32_t c = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
@@ -789,71 +917,20 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
         float sums[Cfg::CPW][32];
         for (int ch = 0; ch < nchunks; ++ch, ++c) {
           const uint32_t b = c & 1, aph = (c >> 1) & 1;
-          mbar_wait_epi(&acc_full[b], aph, 23);
+          mbar_wait(&acc_full[b], aph, 23);
           tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < Cfg::CPW; ++h) {
-            uint32_t raw[32];
-            tmem_ld32(lane_addr + b * BN + (cc0 + 4 * h) * 32, raw);
-            if (ch == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sums[h][j] = __uint_as_float(raw[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sums[h][j] += __uint_as_float(raw[j]);
-            }
-          }
+          for (int h = 0; h < Cfg::CPW; ++h)
+            fold_chunk<MODE>(lane_addr + b * Cfg::ACC_COLS + (cc0 + 4 * h) * 32, BN, sums[h],
+                             ch == 0);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&acc_empty[b]), 0));
+          if (lane == 0) mbar_arrive_remote(acc_empty0 + b * 8);
         }
-        const int m = m0 + q * 32 + lane;
-        long orow = 0;
-        int nlim = 0;
-        if (m < M) {
-          const int g = m / rm.rows_in;
-          const int u = m - g * rm.rows_in;
-          orow = (long)g * rm.rows_out + u;
-          const long lim = (long)(rm.t_valid - u * rm.fold) * rm.cols_per_fold;
-          nlim = lim <= 0 ? 0 : (lim >= N ? N : (int)lim);
-        }
-#pragma unroll
-        for (int h = 0; h < Cfg::CPW; ++h) {
-          const int nb = n0 + (cc0 + 4 * h) * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = sums[h][j] * alpha;
-            if (bias != nullptr && nb + j < N) x += __ldg(bias + nb + j);
-            sums[h][j] = x;
-          }
-          store_chunk<false>(stg, sums[h], lane, C, ldc, orow, nlim, nb, vec_ok, accumulate);
-          if (want_stats) {
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sums[h][j] = (nb + j < nlim) ? sums[h][j] : 0.f;
-              sq[j] = sums[h][j] * sums[h][j];
-            }
-            const float s1 = colsum32(sums[h], lane);
-            const float s2 = colsum32(sq, lane);
-            if (nb + lane < N) {
-              atomicAdd(&s_stats[nb + lane], s1);
-              atomicAdd(&s_stats[stat_cols + nb + lane], s2);
-            }
-          }
-        }
+        nt_output<Cfg::CPW, OUT16>(sums, a, alpha, m0, n0, cc0, q, lane, stg, s_stats, vec_ok);
       }
     }
-    if (want_stats) {
-      asm volatile("bar.sync 1, 512;" ::: "memory");     // the 16 epilogue warps only
-      for (int col = threadIdx.x - 64; col < N; col += N_EPI_WARPS * 32) {
-        const float a = s_stats[col], b2 = s_stats[stat_cols + col];
-        if (a != 0.f || b2 != 0.f) {
-          atomicAdd(colsum + col, (double)a);
-          atomicAdd(colsumsq + col, (double)b2);
-        }
-      }
-    }
+    if (want_stats) flush_stats(a, s_stats);
     tc_fence_before();
   }
   __syncthreads();
@@ -864,292 +941,53 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------ NT window kernel ----
-// Same contract as tc_gemm_nt_kernel, but the A operand is fetched once per 32-float column
-// block instead of once per k-block.  With A(m, kk) = F[m + kk/R, kk%R] the k-blocks
-// kk = q*R + cb*32 (q = 0..Q-1) of one column block cb read the SAME columns of F, shifted by
-// q rows: one TMA box of (BM + Q - 1) rows serves all of them, the UMMA descriptor simply
-// starts q rows (q*128 B) further down.  (Verified on B200, tools/rowshift_probe.py: K-major
-// SWIZZLE_128B operands may start at any row with base_offset = 0 -- the swizzle is a function
-// of absolute shared-memory address bits.)  For a k-tap stride-s convolution this divides the
-// activation traffic by ~k/s; the weight tiles stream through a ring of B stages.
-template <int BN, bool SPLIT>
-struct NTWCfg {
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int B_STAGE_BYTES = (SPLIT ? 2 : 1) * B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int EPI_ACTIVE = 4 * (BN / 32);
-};
-
-template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(NTHREADS_V3, 1)
-tc_gemm_ntw_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
-                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-                   int R, float* __restrict__ C, long ldc, int M, int N, int K, float alpha,
-                   const float* __restrict__ bias, RowMap rm, double* __restrict__ colsum,
-                   double* __restrict__ colsumsq, int accumulate, int flush_kb, int stages,
-                   int stat_cols, int win_rows) {
-  using Cfg = NTWCfg<BN, SPLIT>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  const int win_bytes = win_rows * 128;                       // one hi (or lo) window
-  const int win_pair = (SPLIT ? 2 : 1) * win_bytes;
-  uint8_t* wins = smem;                                       // 2 window buffers (hi [, lo])
-  uint8_t* btiles = smem + 2 * win_pair;
-  uint8_t* after = btiles + stages * Cfg::B_STAGE_BYTES;
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(after);
-  uint64_t* b_empty = b_full + MAX_STAGES;
-  uint64_t* w_full = b_empty + MAX_STAGES;
-  uint64_t* w_empty = w_full + 2;
-  uint64_t* acc_full = w_empty + 2;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_out = reinterpret_cast<float*>(after + BAR_BYTES);
-  float* s_stats = s_out + OUT_STAGE_BYTES / 4;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
-  const int total_tiles = n_tiles * m_tiles;
-  const int nkb = K / BKF;                                    // K % 32 == 0 (host-checked)
-  const int ncb = (R < K ? R : K) / BKF;                      // column blocks of a folded row
-  if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
-  const bool want_stats = colsum != nullptr;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&w_full[b], 1);
-      mbar_init(&w_empty[b], 1);
-      mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], Cfg::EPI_ACTIVE);
-    }
-    fence_barrier_init();
-    tmap_prefetch(&mAhi);
-    tmap_prefetch(&mBhi);
-    if (SPLIT) {
-      tmap_prefetch(&mAlo);
-      tmap_prefetch(&mBlo);
-    }
-  }
-  if (want_stats)
-    for (int i = threadIdx.x; i < 2 * stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // q-steps of column block cb: kk = q*R + cb*32 < K
-  auto nq_of = [&](int cb) { return (K - cb * BKF + R - 1) / R; };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t wi = 0, bi = 0;
-      auto issue_window = [&](int tile, int cb) {
-        const uint32_t w = wi & 1, wph = (wi >> 1) & 1;
-        mbar_wait(&w_empty[w], wph ^ 1, 5);
-        const int m0 = (tile / n_tiles) * BM;
-        uint8_t* dst = wins + w * win_pair;
-        mbar_expect_tx(&w_full[w], win_pair);
-        tma_load_2d(dst, &mAhi, &w_full[w], cb * BKF, m0);
-        if (SPLIT) tma_load_2d(dst + win_bytes, &mAlo, &w_full[w], cb * BKF, m0);
-        ++wi;
-      };
-      int tile = blockIdx.x, cb = 0;
-      if (tile < total_tiles) issue_window(tile, 0);
-      while (tile < total_tiles) {
-        const int n0 = (tile % n_tiles) * BN;
-        const int nq = nq_of(cb);
-        // successor (tile, cb) whose window is prefetched while this block's last B tiles load
-        int ntile = tile, ncbn = cb + 1;
-        if (ncbn == ncb) { ncbn = 0; ntile = tile + gridDim.x; }
-        const int pre_at = nq > stages ? nq - stages : 0;
-        for (int q = 0; q < nq; ++q, ++bi) {
-          if (q == pre_at && ntile < total_tiles) issue_window(ntile, ncbn);
-          const int s = bi % stages;
-          const uint32_t ph = (bi / stages) & 1;
-          mbar_wait(&b_empty[s], ph ^ 1, 1);
-          uint8_t* st = btiles + s * Cfg::B_STAGE_BYTES;
-          mbar_expect_tx(&b_full[s], Cfg::B_STAGE_BYTES);
-          const int kf = q * R + cb * BKF;
-          tma_load_2d(st, &mBhi, &b_full[s], kf, n0);
-          if (SPLIT) tma_load_2d(st + Cfg::B_BYTES, &mBlo, &b_full[s], kf, n0);
-        }
-        tile = ntile;
-        cb = ncbn;
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-      const uint64_t dconst = desc_hi_bits<2>(16, 1024);
-      const uint32_t wins_u32 = smem_u32(wins), bt_u32 = smem_u32(btiles);
-      uint32_t wi = 0, bi = 0, c = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int in_chunk = 0, done_kb = 0;
-        uint32_t b = c & 1;
-        mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1, 4);
-        tc_fence_after();
-        for (int cb = 0; cb < ncb; ++cb, ++wi) {
-          const uint32_t w = wi & 1;
-          mbar_wait(&w_full[w], (wi >> 1) & 1, 6);
-          tc_fence_after();
-          const uint32_t a_hi0 = wins_u32 + w * win_pair;
-          const int nq = nq_of(cb);
-          for (int q = 0; q < nq; ++q, ++bi) {
-            const int s = bi % stages;
-            mbar_wait(&b_full[s], (bi / stages) & 1, 2);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + b * BN;
-            // A starts q rows into the window; k-step of 8 tf32 = +32 B
-            const uint64_t dah = dconst + ((a_hi0 + q * 128) >> 4);
-            const uint64_t dal = dconst + ((a_hi0 + win_bytes + q * 128) >> 4);
-            const uint64_t dbh = dconst + ((bt_u32 + s * Cfg::B_STAGE_BYTES) >> 4);
-            const uint64_t dbl = dbh + (Cfg::B_BYTES >> 4);
-            const uint32_t first = in_chunk == 0 ? 0u : 1u;
-#pragma unroll
-            for (int k = 0; k < BKF / UMMA_K; ++k) {
-              const uint32_t acc = (k == 0) ? first : 1u;
-              if (SPLIT) {
-                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, acc);
-                umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
-                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
-              } else {
-                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, acc);
-              }
-            }
-            umma_commit(&b_empty[s]);
-            ++in_chunk;
-            ++done_kb;
-            if (in_chunk == flush_kb || done_kb == nkb) {
-              umma_commit(&acc_full[b]);           // chunk complete -> epilogue folds it
-              ++c;
-              in_chunk = 0;
-              if (done_kb < nkb) {
-                b = c & 1;
-                mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1, 4);
-                tc_fence_after();
-              }
-            }
-          }
-          umma_commit(&w_empty[w]);                // window free once its MMAs retire
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ---------------- epilogue: identical to tc_gemm_nt_kernel ----------------
-    const int e = warp - 2;
-    const int q = warp & 3;
-    const int cc = e >> 2;
-    const int nchunks = (nkb + flush_kb - 1) / flush_kb;
-    if (cc < BN / 32) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
-      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
-      float* stg = s_out + e * OUT_STG_FLOATS;
-      uint32_t c = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-        float sums[32];
-        for (int ch = 0; ch < nchunks; ++ch, ++c) {
-          const uint32_t b = c & 1, aph = (c >> 1) & 1;
-          mbar_wait_epi(&acc_full[b], aph, 3);
-          tc_fence_after();
-          uint32_t raw[32];
-          tmem_ld32(taddr + b * BN, raw);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[b]);
-          if (ch == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sums[j] = __uint_as_float(raw[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sums[j] += __uint_as_float(raw[j]);
-          }
-        }
-        const int m = m0 + q * 32 + lane;
-        long orow = 0;
-        int nlim = 0;
-        if (m < M) {
-          const int g = m / rm.rows_in;
-          const int u = m - g * rm.rows_in;
-          orow = (long)g * rm.rows_out + u;
-          const long lim = (long)(rm.t_valid - u * rm.fold) * rm.cols_per_fold;
-          nlim = lim <= 0 ? 0 : (lim >= N ? N : (int)lim);
-        }
-        const int nb = n0 + cc * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = sums[j] * alpha;
-          if (bias != nullptr && nb + j < N) x += __ldg(bias + nb + j);
-          sums[j] = x;
-        }
-        store_chunk<false>(stg, sums, lane, C, ldc, orow, nlim, nb, vec_ok, accumulate);
-        if (want_stats) {
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            sums[j] = (nb + j < nlim) ? sums[j] : 0.f;
-            sq[j] = sums[j] * sums[j];
-          }
-          const float s1 = colsum32(sums, lane);
-          const float s2 = colsum32(sq, lane);
-          if (nb + lane < N) {
-            atomicAdd(&s_stats[nb + lane], s1);
-            atomicAdd(&s_stats[stat_cols + nb + lane], s2);
-          }
-        }
-      }
-    }
-    if (want_stats) {
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      for (int col = threadIdx.x - 64; col < N; col += N_EPI_WARPS * 32) {
-        const float a = s_stats[col], b2 = s_stats[stat_cols + col];
-        if (a != 0.f || b2 != 0.f) {
-          atomicAdd(colsum + col, (double)a);
-          atomicAdd(colsumsq + col, (double)b2);
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-  }
-}
-
 // ------------------------------------------------------------------ TN kernel ----
-// C[i,j] += alpha * sum_r A[r,i] B[r,j].  A: 3-D tensor (I inner, rows-per-group, groups);
-// B addressed through the folded-row trick: (r, j) -> row u + j/R of group g, column j % R.
-constexpr int TN_KR = 32;                // reduction rows per stage (4 UMMA k-steps of 8)
-
-template <int BN, bool SPLIT>
+// C[i,j] += alpha * sum_r A[r,i] B[r,j].  A: 4-D tensor (128 B inner, rows-per-group, column
+// blocks, groups); B addressed through the folded-row trick: (r, j) -> row u + j/R of group g,
+// column j % R.  One stage = KR reduction rows (4 UMMA k-steps): 32 rows of fp32, 64 of 16-bit.
+template <int BN, int MODE>
 struct TNCfg {
-  static constexpr int A_BYTES = TN_KR * BM * 4;          // 4 MN-blocks of [32 rows x 128 B]
-  static constexpr int B_BYTES = TN_KR * BN * 4;
-  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int TMEM_COLS = 2 * BN;
+  using MT = ModeT<MODE>;
+  static constexpr int EB = MT::EB;                        // elements per 128-byte MN block
+  static constexpr int KR = 4 * MT::UMMA_K;                // reduction rows per stage
+  static constexpr int A_BYTES = KR * BM * MT::ESZ;        // BM/EB MN-blocks of [KR rows x 128 B]
+  static constexpr int B_BYTES = KR * BN * MT::ESZ;
+  static constexpr int STAGE_BYTES = (MT::SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int ACC_COLS = MT::NACC * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int EPI_ACTIVE = 4 * (BN / 32);
+  // MN-major descriptors: fp32 -> 128B swizzle with 32-byte base (4 k-rows per atom);
+  // 16-bit -> plain 128B swizzle (8 k-rows per atom)
+  static constexpr int LAYOUT = MT::ESZ == 4 ? 1 : 2;
+  static constexpr int SBO = MT::ESZ == 4 ? 512 : 1024;
+  static constexpr int LBO = KR * 128;                     // next MN block
+  static constexpr int KSTEP_DESC = (MT::UMMA_K * 128) >> 4;   // UMMA_K k-rows of 128 B
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
 
-template <int BN, bool SPLIT>
+struct TNArgs {
+  int R;
+  float* C;
+  long ldc;
+  int I, J, groups, rows_per_group;
+  float alpha;
+  const float* alpha_dev;
+  int chunks_per_split, flush_ch, stages, b_blocked;
+  int lbo, sbo;                    // MN-major descriptor strides (TNCfg defaults)
+};
+
+template <int BN, int MODE>
 __global__ void __launch_bounds__(NTHREADS_V3, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-                  int R, float* __restrict__ C, long ldc, int I, int J, int groups,
-                  int rows_per_group, float alpha, int chunks_per_split, int flush_ch,
-                  int stages, int b_blocked) {
-  using Cfg = TNCfg<BN, SPLIT>;
+                  const TNArgs a) {
+  using Cfg = TNCfg<BN, MODE>;
+  using MT = ModeT<MODE>;
+  constexpr int KR = Cfg::KR, EB = Cfg::EB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int stages = a.stages;
   uint8_t* tiles = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -1159,13 +997,15 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   float* s_out = reinterpret_cast<float*>(smem + stages * Cfg::STAGE_BYTES + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = a.R;
   const int j0 = blockIdx.x * BN, i0 = blockIdx.y * BM;
-  const int cpg = (rows_per_group + TN_KR - 1) / TN_KR;       // chunks per group
-  const long total_chunks = (long)groups * cpg;
-  const long c_begin = (long)blockIdx.z * chunks_per_split;
-  long c_end = c_begin + chunks_per_split;
+  const int cpg = (a.rows_per_group + KR - 1) / KR;           // chunks per group
+  const long total_chunks = (long)a.groups * cpg;
+  const long c_begin = (long)blockIdx.z * a.chunks_per_split;
+  long c_end = c_begin + a.chunks_per_split;
   if (c_end > total_chunks) c_end = total_chunks;
   const int nch = (int)(c_end - c_begin);
+  int flush_ch = a.flush_ch;
   if (flush_ch <= 0 || flush_ch > nch) flush_ch = nch > 0 ? nch : 1;
   const int nflush = (nch + flush_ch - 1) / flush_ch;
 
@@ -1206,39 +1046,39 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         mbar_wait(&empty_bar[s], ph ^ 1, 11);
         const long ch = c_begin + it;
         const int g = (int)(ch / cpg);
-        const int u0 = (int)(ch - (long)g * cpg) * TN_KR;
+        const int u0 = (int)(ch - (long)g * cpg) * KR;
         uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         uint8_t* a_hi = st;
         uint8_t* b_hi = st + Cfg::A_BYTES;
         uint8_t* a_lo = b_hi + Cfg::B_BYTES;
         uint8_t* b_lo = a_lo + Cfg::A_BYTES;
-        // A: one 4-D box = (32 floats, 32 rows, BM/32 column blocks, 1 group) lands as
-        // BM/32 consecutive [32 rows x 128 B] MN-blocks
-        tma_load_4d(a_hi, &mAhi, &full_bar[s], 0, u0, i0 / 32, g);
-        if (SPLIT) tma_load_4d(a_lo, &mAlo, &full_bar[s], 0, u0, i0 / 32, g);
-        if (b_blocked) {
+        // A: one 4-D box = (128 B, KR rows, BM/EB column blocks, 1 group) lands as
+        // BM/EB consecutive [KR rows x 128 B] MN-blocks
+        tma_load_4d(a_hi, &mAhi, &full_bar[s], 0, u0, i0 / EB, g);
+        if (MT::SPLIT) tma_load_4d(a_lo, &mAlo, &full_bar[s], 0, u0, i0 / EB, g);
+        if (a.b_blocked) {
           // the BN columns of this tile lie inside one folded row (R % BN == 0)
-          tma_load_4d(b_hi, &mBhi, &full_bar[s], 0, u0 + jq, jc / 32, g);
-          if (SPLIT) tma_load_4d(b_lo, &mBlo, &full_bar[s], 0, u0 + jq, jc / 32, g);
+          tma_load_4d(b_hi, &mBhi, &full_bar[s], 0, u0 + jq, jc / EB, g);
+          if (MT::SPLIT) tma_load_4d(b_lo, &mBlo, &full_bar[s], 0, u0 + jq, jc / EB, g);
         } else {
 #pragma unroll
-          for (int nb = 0; nb < BN / 32; ++nb) {
-            // 32 consecutive columns never straddle a folded row (R % 32 == 0)
-            const int col = jc + nb * 32;
+          for (int nb = 0; nb < BN / EB; ++nb) {
+            // EB consecutive columns never straddle a folded row (R % EB == 0)
+            const int col = jc + nb * EB;
             const int qq = jq + col / R, cc = col % R;
-            tma_load_4d(b_hi + nb * TN_KR * 128, &mBhi, &full_bar[s], 0, u0 + qq, cc / 32, g);
-            if (SPLIT)
-              tma_load_4d(b_lo + nb * TN_KR * 128, &mBlo, &full_bar[s], 0, u0 + qq, cc / 32, g);
+            tma_load_4d(b_hi + nb * KR * 128, &mBhi, &full_bar[s], 0, u0 + qq, cc / EB, g);
+            if (MT::SPLIT)
+              tma_load_4d(b_lo + nb * KR * 128, &mBlo, &full_bar[s], 0, u0 + qq, cc / EB, g);
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // converged warp, elected issue (see umma_tf32_w)
-    constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
-    const uint64_t dconst = desc_hi_bits<1>(TN_KR * 128, 512);
+    // converged warp, elected issue (see umma_w)
+    constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1, MT::FMT);
+    const uint64_t dconst = desc_hi_bits<Cfg::LAYOUT>((uint32_t)a.lbo, (uint32_t)a.sbo);
     const uint32_t tiles_u32 = smem_u32(tiles);
     const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
     int s = 0;
@@ -1247,7 +1087,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       const uint32_t b = f & 1, aph = (f >> 1) & 1;
       mbar_wait(&acc_empty[b], aph ^ 1, 14);
       tc_fence_after();
-      const uint32_t d_tmem = tm0 + b * BN;
+      const uint32_t d_tmem = tm0 + b * Cfg::ACC_COLS;
       const int it_lo = f * flush_ch;
       const int it_hi = (it_lo + flush_ch < nch) ? it_lo + flush_ch : nch;
       for (int it = it_lo; it < it_hi; ++it) {
@@ -1257,19 +1097,8 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
         const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
         const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
-        const uint32_t first = (it == it_lo) ? 0u : 1u;
-#pragma unroll
-        for (int k = 0; k < TN_KR / UMMA_K; ++k) {
-          const uint32_t acc = (k == 0) ? first : 1u;
-          const uint32_t o = k * (1024 >> 4);          // 8 k-rows of 128 B
-          if (SPLIT) {
-            umma_tf32_w(d_tmem, dal + o, dbh + o, idesc, acc);
-            umma_tf32_w(d_tmem, dah + o, dbl + o, idesc, 1);
-            umma_tf32_w(d_tmem, dah + o, dbh + o, idesc, 1);
-          } else {
-            umma_tf32_w(d_tmem, dah + o, dbh + o, idesc, acc);
-          }
-        }
+        issue_kblock<MODE, 1, 4, Cfg::KSTEP_DESC>(d_tmem, BN, dah, dbh, dal, dbl, idesc,
+                                                  (it == it_lo) ? 0u : 1u);
         umma_commit_w(&empty_bar[s]);
         if (++s == stages) {
           s = 0;
@@ -1288,27 +1117,20 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       float sums[32];
       for (int f = 0; f < nflush; ++f) {
         const uint32_t b = f & 1, aph = (f >> 1) & 1;
-        mbar_wait_epi(&acc_full[b], aph, 13);
+        mbar_wait(&acc_full[b], aph, 13);
         tc_fence_after();
-        uint32_t raw[32];
-        tmem_ld32(taddr + b * BN, raw);
+        fold_chunk<MODE>(taddr + b * Cfg::ACC_COLS, BN, sums, f == 0);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[b]);
-        if (f == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sums[j] = __uint_as_float(raw[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sums[j] += __uint_as_float(raw[j]);
-        }
       }
       const int i = i0 + q * 32 + lane;
-      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+      const bool vec_ok = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0);
+      const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
 #pragma unroll
       for (int j = 0; j < 32; ++j) sums[j] *= alpha;
-      store_chunk<true>(s_out + e * OUT_STG_FLOATS, sums, lane, C, ldc, (long)i, i < I ? J : 0,
-                        j0 + cc * 32, vec_ok, 0);
+      store_chunk<true>(s_out + e * OUT_STG_FLOATS, sums, lane, a.C, a.ldc, (long)i,
+                        i < a.I ? a.J : 0, j0 + cc * 32, vec_ok, 0);
     }
     tc_fence_before();
   }
@@ -1320,27 +1142,6 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 }
 
 // ------------------------------------------------------------------ host side ----
-static bool pase_tc_use_window() {
-  static int v = -1;
-  if (v < 0) {
-    // off by default: measured slower than the per-k-block kernel (the GEMMs are bound by
-    // shared-memory bandwidth, not by operand traffic); PASE_B200_TC_WINDOW=1 enables it
-    const char* e = getenv("PASE_B200_TC_WINDOW");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
-
-// one-time upload of the epilogue poll back-off (default 0 = plain polling)
-static void pase_tc_init_epi_sleep() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  const char* e = getenv("PASE_B200_EPI_SLEEP_NS");
-  const int ns = e ? atoi(e) : 0;
-  if (ns > 0) cudaMemcpyToSymbol(c_epi_sleep_ns, &ns, sizeof(int));
-}
-
 static bool pase_tc_use_2cta() {
   static int v = -1;
   if (v < 0) {
@@ -1350,6 +1151,35 @@ static bool pase_tc_use_2cta() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
+}
+
+// A timed-out mbarrier wait traps the kernel; the (tag, block, thread) it recorded in the
+// mapped host diagnostics word is appended to the error message of the failing call.
+static unsigned int* h_tc_diag = nullptr;
+static void pase_tc_init_diag() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  unsigned int* h = nullptr;
+  unsigned int* d = nullptr;
+  // 16 bytes of mapped pinned memory, allocated once per process (diagnostics only)
+  if (cudaHostAlloc((void**)&h, 4 * sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  h[0] = h[1] = h[2] = h[3] = 0;
+  if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess ||
+      cudaMemcpyToSymbol(g_tc_diag, &d, sizeof(d)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeHost(h);
+    return;
+  }
+  h_tc_diag = h;
+}
+static void pase_tc_report_timeout() {
+  if (h_tc_diag != nullptr && h_tc_diag[0] != 0)
+    pase_set_error("pase tc gemm: mbarrier wait timed out (tag %u, block code 0x%x, thread %u)",
+                   h_tc_diag[0], h_tc_diag[1], h_tc_diag[2]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1369,8 +1199,8 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// rank-2 or rank-3 fp32 tensor map, 128B swizzle, zero OOB fill.
-int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims,
+// rank-2 .. rank-4 tensor map (element type by mode), zero OOB fill.
+int make_map(CUtensorMap* map, const void* base, int mode, int rank, const uint64_t* dims,
              const uint64_t* strides_bytes, const uint32_t* box, const char* what,
              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
@@ -1378,8 +1208,11 @@ int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims
     pase_set_error("pase tc gemm: cuTensorMapEncodeTiled not available");
     return PASE_ERR_UNSUPPORTED;
   }
+  const CUtensorMapDataType dt = mode <= 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (mode == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base,
+  CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base),
                    (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes,
                    (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1397,22 +1230,30 @@ int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims
   return PASE_OK;
 }
 
-template <int BN, bool SPLIT, int BK>
+#define PASE_TC_LAUNCH_CHECK(name)                                         \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) {                                              \
+      pase_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      pase_tc_report_timeout();                                            \
+      return (int)e__;                                                     \
+    }                                                                      \
+  } while (0)
+
+template <int BN, int MODE, int ROWB, bool OUT16>
 int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-              const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
-              const float* bias, RowMap rm, double* cs, double* cq, int accumulate, int flush_kb,
-              cudaStream_t st) {
-  using Cfg = NTCfg<BN, SPLIT, BK>;
+              const CUtensorMap& bl, NTArgs a, cudaStream_t st) {
+  using Cfg = NTCfg<BN, MODE, ROWB>;
   static bool attr = false;
-  const int stat_cols = cs ? ((N + 31) / 32) * 32 : 0;
-  const int stages = pick_stages(Cfg::STAGE_BYTES, 2 * stat_cols * 4);
-  const int smem = smem_bytes(stages, Cfg::STAGE_BYTES, 2 * stat_cols * 4);
-  if (stages < 2) {
+  a.stat_cols = a.colsum ? ((a.N + 31) / 32) * 32 : 0;
+  a.stages = pick_stages(Cfg::STAGE_BYTES, 2 * a.stat_cols * 4);
+  const int smem = smem_bytes(a.stages, Cfg::STAGE_BYTES, 2 * a.stat_cols * 4);
+  if (a.stages < 2) {
     pase_set_error("pase_tc_gemm_nt: not enough shared memory for 2 pipeline stages");
     return PASE_ERR_UNSUPPORTED;
   }
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, SPLIT, BK>,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, MODE, ROWB, OUT16>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
       pase_set_error("pase_tc_gemm_nt: smem attribute: %s", cudaGetErrorString(e));
@@ -1420,31 +1261,27 @@ int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
     }
     attr = true;
   }
-  const long tiles = (long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const long tiles = (long)((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM);
   const int grid = (int)(tiles < pase_num_sms() ? tiles : pase_num_sms());
-  tc_gemm_nt_kernel<BN, SPLIT, BK><<<grid, NTHREADS_V3, smem, st>>>(
-      ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
-      stat_cols);
-  PASE_LAUNCH_CHECK("pase_tc_gemm_nt");
+  tc_gemm_nt_kernel<BN, MODE, ROWB, OUT16><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_TC_LAUNCH_CHECK("pase_tc_gemm_nt");
   return PASE_OK;
 }
 
-template <int BN, bool SPLIT>
+template <int BN, int MODE, bool OUT16>
 int launch_nt2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-               const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
-               const float* bias, RowMap rm, double* cs, double* cq, int accumulate, int flush_kb,
-               cudaStream_t st) {
-  using Cfg = NT2Cfg<BN, SPLIT>;
+               const CUtensorMap& bl, NTArgs a, cudaStream_t st) {
+  using Cfg = NT2Cfg<BN, MODE>;
   static bool attr = false;
-  const int stat_cols = cs ? ((N + 31) / 32) * 32 : 0;
-  const int stages = pick_stages(Cfg::STAGE_BYTES, 2 * stat_cols * 4);
-  const int smem = smem_bytes(stages, Cfg::STAGE_BYTES, 2 * stat_cols * 4);
-  if (stages < 2) {
+  a.stat_cols = a.colsum ? ((a.N + 31) / 32) * 32 : 0;
+  a.stages = pick_stages(Cfg::STAGE_BYTES, 2 * a.stat_cols * 4);
+  const int smem = smem_bytes(a.stages, Cfg::STAGE_BYTES, 2 * a.stat_cols * 4);
+  if (a.stages < 2) {
     pase_set_error("pase_tc_gemm_nt (2-CTA): not enough shared memory for 2 pipeline stages");
     return PASE_ERR_UNSUPPORTED;
   }
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, SPLIT>,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, MODE, OUT16>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
       pase_set_error("pase_tc_gemm_nt (2-CTA): smem attribute: %s", cudaGetErrorString(e));
@@ -1452,62 +1289,34 @@ int launch_nt2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
     }
     attr = true;
   }
-  const long tiles = (long)((N + BN - 1) / BN) * ((M + 2 * BM - 1) / (2 * BM));
+  const long tiles = (long)((a.N + BN - 1) / BN) * ((a.M + 2 * BM - 1) / (2 * BM));
   const long max_pairs = pase_num_sms() / 2;
   const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);   // cluster dims (2,1,1)
-  tc_gemm_nt2_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(
-      ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
-      stat_cols);
-  PASE_LAUNCH_CHECK("pase_tc_gemm_nt(2cta)");
+  tc_gemm_nt2_kernel<BN, MODE, OUT16><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_TC_LAUNCH_CHECK("pase_tc_gemm_nt(2cta)");
   return PASE_OK;
 }
 
-template <int BN, bool SPLIT>
-int launch_ntw(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-               const CUtensorMap& bl, int R, float* C, long ldc, int M, int N, int K, float alpha,
-               const float* bias, RowMap rm, double* cs, double* cq, int accumulate, int flush_kb,
-               int win_rows, cudaStream_t st) {
-  using Cfg = NTWCfg<BN, SPLIT>;
-  static bool attr = false;
-  const int stat_cols = cs ? ((N + 31) / 32) * 32 : 0;
-  const int win_total = 2 * (SPLIT ? 2 : 1) * win_rows * 128;
-  int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - OUT_STAGE_BYTES - 2 * stat_cols * 4 - win_total) /
-               Cfg::B_STAGE_BYTES;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) {
-    pase_set_error("pase_tc_gemm_nt: not enough shared memory for the window pipeline");
-    return PASE_ERR_UNSUPPORTED;
-  }
-  const int smem = win_total + stages * Cfg::B_STAGE_BYTES + 1024 + BAR_BYTES + OUT_STAGE_BYTES +
-                   2 * stat_cols * 4;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_ntw_kernel<BN, SPLIT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) {
-      pase_set_error("pase_tc_gemm_nt(window): smem attribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr = true;
-  }
-  const long tiles = (long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
-  const int grid = (int)(tiles < pase_num_sms() ? tiles : pase_num_sms());
-  tc_gemm_ntw_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(
-      ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm, cs, cq, accumulate, flush_kb, stages,
-      stat_cols, win_rows);
-  PASE_LAUNCH_CHECK("pase_tc_gemm_nt(window)");
-  return PASE_OK;
-}
-
-template <int BN, bool SPLIT>
+template <int BN, int MODE>
 int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-              const CUtensorMap& bl, int R, float* C, long ldc, int I, int J, int groups,
-              int rows_per_group, float alpha, int flush_ch, int b_blocked, cudaStream_t st) {
-  using Cfg = TNCfg<BN, SPLIT>;
+              const CUtensorMap& bl, TNArgs a, cudaStream_t st) {
+  using Cfg = TNCfg<BN, MODE>;
   static bool attr = false;
-  const int stages = pick_stages(Cfg::STAGE_BYTES, 0);
-  const int smem = smem_bytes(stages, Cfg::STAGE_BYTES, 0);
+  a.stages = pick_stages(Cfg::STAGE_BYTES, 0);
+  a.lbo = Cfg::LBO;
+  a.sbo = Cfg::SBO;
+  if (MODE >= 2) {                 // bring-up aid: PASE_B200_TN16_DESC="lbo,sbo" (bytes)
+    static int o_lbo = -1, o_sbo = -1;
+    if (o_lbo == -1) {
+      o_lbo = 0;
+      const char* e = getenv("PASE_B200_TN16_DESC");
+      if (e) sscanf(e, "%d,%d", &o_lbo, &o_sbo);
+    }
+    if (o_lbo > 0) { a.lbo = o_lbo; a.sbo = o_sbo; }
+  }
+  const int smem = smem_bytes(a.stages, Cfg::STAGE_BYTES, 0);
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, SPLIT>,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
       pase_set_error("pase_tc_gemm_tn: smem attribute: %s", cudaGetErrorString(e));
@@ -1515,9 +1324,9 @@ int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
     }
     attr = true;
   }
-  const int ti = (I + BM - 1) / BM, tj = (J + BN - 1) / BN;
-  const int cpg = (rows_per_group + TN_KR - 1) / TN_KR;
-  const long total = (long)groups * cpg;
+  const int ti = (a.I + BM - 1) / BM, tj = (a.J + BN - 1) / BN;
+  const int cpg = (a.rows_per_group + Cfg::KR - 1) / Cfg::KR;
+  const long total = (long)a.groups * cpg;
   // split the reduction so that the CTA count fills whole waves of the SMs (one CTA per SM):
   // among 1..4 waves pick the split with the best fill, keeping chains >= 8 chunks
   const long tiles = (long)ti * tj;
@@ -1537,11 +1346,10 @@ int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   long splits = best;
   long cps = (total + splits - 1) / splits;
   splits = (total + cps - 1) / cps;
+  a.chunks_per_split = (int)cps;
   dim3 grid(tj, ti, (unsigned)splits);
-  tc_gemm_tn_kernel<BN, SPLIT><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, R, C, ldc, I, J, groups,
-                                                            rows_per_group, alpha, (int)cps,
-                                                            flush_ch, stages, b_blocked);
-  PASE_LAUNCH_CHECK("pase_tc_gemm_tn");
+  tc_gemm_tn_kernel<BN, MODE><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_TC_LAUNCH_CHECK("pase_tc_gemm_tn");
   return PASE_OK;
 }
 
@@ -1606,99 +1414,115 @@ int pase_split_tf32(const float* x, float* hi, float* lo, long n, void* stream) 
   return PASE_OK;
 }
 
-// A: [a_rows x R] fp32 (hi / lo parts, lo may be NULL for mode 0); B: [N x K] (ldb = K).
-int pase_tc_gemm_nt(const float* Ahi, const float* Alo, long a_rows, int R, const float* Bhi,
-                    const float* Blo, long ldb, float* C, long ldc, int M, int N, int K,
-                    float alpha, const float* bias, int rows_in, int t_valid, int rows_out,
-                    int fold, double* colsum, double* colsumsq, int accumulate, int mode,
-                    void* stream) {
+// A: [a_rows x R] elements (hi / lo parts; lo NULL outside the split modes); B: [N x K]
+// (ldb >= K).  Element type by mode: fp32 (0, 1), bf16 (2), fp16 (3).
+int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const void* Bhi,
+                    const void* Blo, long ldb, void* C, long ldc, int M, int N, int K,
+                    float alpha, const float* alpha_dev, const float* bias, int rows_in,
+                    int t_valid, int rows_out, int fold, double* colsum, double* colsumsq,
+                    int accumulate, int mode, int c_bf16, void* stream) {
   PASE_CHECK_ARG(Ahi && Bhi && C && M > 0 && N > 0 && K > 0, "pase_tc_gemm_nt: bad args");
-  pase_tc_init_epi_sleep();
-  PASE_CHECK_ARG(mode == 0 || (Alo && Blo), "pase_tc_gemm_nt: mode 1 needs lo operands");
-  PASE_CHECK_ARG(R >= 32 && (R % 32) == 0, "pase_tc_gemm_nt: R=%d must be a multiple of 32", R);
-  PASE_CHECK_ARG((K % 4) == 0 && (ldb % 4) == 0 && ldb >= K, "pase_tc_gemm_nt: K/ldb alignment");
+  PASE_CHECK_ARG(mode >= 0 && mode <= 3, "pase_tc_gemm_nt: mode %d (0 tf32, 1 3xtf32, 2 bf16, "
+                 "3 3xf16)", mode);
+  pase_tc_init_diag();
+  const bool split = mode == 1 || mode == 3;
+  const int esz = mode >= 2 ? 2 : 4;
+  const int eb = 128 / esz;                       // elements per 128-byte row
+  PASE_CHECK_ARG(!split || (Alo && Blo), "pase_tc_gemm_nt: split modes need lo operands");
+  PASE_CHECK_ARG(R >= eb && (R % eb) == 0, "pase_tc_gemm_nt: R=%d must be a multiple of %d", R,
+                 eb);
+  PASE_CHECK_ARG((K * esz) % 16 == 0 && (ldb * esz) % 16 == 0 && ldb >= K,
+                 "pase_tc_gemm_nt: K/ldb alignment");
   PASE_CHECK_ARG(aligned16(Ahi) && aligned16(Bhi), "pase_tc_gemm_nt: operand alignment");
   PASE_CHECK_ARG(rows_in > 0 && rows_out > 0 && fold > 0 && (N % fold) == 0,
                  "pase_tc_gemm_nt: bad row map");
   PASE_CHECK_ARG((colsum == nullptr) == (colsumsq == nullptr), "pase_tc_gemm_nt: stats pair");
-  PASE_CHECK_ARG(colsum == nullptr || N <= 2048, "pase_tc_gemm_nt: stats need N <= 2048");
+  PASE_CHECK_ARG(colsum == nullptr || N <= 4096, "pase_tc_gemm_nt: stats need N <= 4096");
   PASE_CHECK_ARG(colsum == nullptr || !accumulate, "pase_tc_gemm_nt: stats + accumulate");
-  // 256-wide tiles (16-element k-blocks, see NTCfg) raise the MMA rate per flop by ~1.2x but
+  PASE_CHECK_ARG(!c_bf16 || !accumulate, "pase_tc_gemm_nt: bf16 output cannot accumulate");
+  // 256-wide tiles (64-byte k-blocks, see NTCfg) raise the MMA rate per flop by ~1.2x but
   // halve the tile count (wave quantisation) and double the epilogue per warp: measured on
-  // the PASE+ shapes they only pay off for long reductions (profiles/r01_history.md)
-  const bool wide = N >= 256 && (N % 256) == 0 && K >= 4096;
+  // the PASE+ shapes they only pay off for long reductions (profiles/r01_history.md);
+  // not available with the two-accumulator 3xF16 mode (TMEM budget)
+  const bool wide = N >= 256 && (N % 256) == 0 && K >= 4096 && mode != 3;
   const int BN = N <= 64 ? 64 : (wide ? 256 : 128);
-  const int BKh = BN == 256 ? 16 : 32;
-  // 3xTF32: fold the TMEM accumulator into fp32 register sums every K = 128
-  const int flush_kb = (mode == 1) ? 128 / BKh : 0;
+  const int rowb = BN == 256 ? 64 : 128;
+  const int bk = rowb / esz;
+  // split modes: fold the TMEM accumulator into fp32 register sums every K = 128
+  const int flush_kb = split ? (128 / bk > 0 ? 128 / bk : 1) : 0;
   CUtensorMap ah, al, bh, bl;
-  // window kernel: A fetched once per 32-float column block (needs K % 32 == 0); the plain
-  // per-k-block kernel remains for ragged K
   const bool pair2 = BN == 128 && (N % 128) == 0 && pase_tc_use_2cta();
-  const bool window = !pair2 && BN != 256 && (K % 32) == 0 && pase_tc_use_window();
-  const int qmax = (K + R - 1) / R - 1;
-  const int win_rows = ((BM + qmax + 7) / 8) * 8;
   uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
-  uint64_t astr[1] = {(uint64_t)R * 4};
-  uint32_t abox[2] = {(uint32_t)BKh, (uint32_t)(window ? win_rows : BM)};
+  uint64_t astr[1] = {(uint64_t)R * esz};
+  uint32_t abox[2] = {(uint32_t)bk, (uint32_t)BM};
   uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
-  uint64_t bstr[1] = {(uint64_t)ldb * 4};
-  uint32_t bbox[2] = {(uint32_t)BKh, (uint32_t)(pair2 ? BN / 2 : BN)};   // pair: half per CTA
-  const CUtensorMapSwizzle swz = BKh == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  PASE_CHECK_ARG(!window || win_rows <= 256, "pase_tc_gemm_nt: K/R=%d too large for a window",
-                 qmax + 1);
+  uint64_t bstr[1] = {(uint64_t)ldb * esz};
+  uint32_t bbox[2] = {(uint32_t)bk, (uint32_t)(pair2 ? BN / 2 : BN)};   // pair: half per CTA
+  const CUtensorMapSwizzle swz = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   int rc;
-  if ((rc = make_map(&ah, Ahi, 2, adims, astr, abox, "A.hi", swz)) != 0) return rc;
-  if ((rc = make_map(&bh, Bhi, 2, bdims, bstr, bbox, "B.hi", swz)) != 0) return rc;
-  if (mode == 1) {
-    if ((rc = make_map(&al, Alo, 2, adims, astr, abox, "A.lo", swz)) != 0) return rc;
-    if ((rc = make_map(&bl, Blo, 2, bdims, bstr, bbox, "B.lo", swz)) != 0) return rc;
+  if ((rc = make_map(&ah, Ahi, mode, 2, adims, astr, abox, "A.hi", swz)) != 0) return rc;
+  if ((rc = make_map(&bh, Bhi, mode, 2, bdims, bstr, bbox, "B.hi", swz)) != 0) return rc;
+  if (split) {
+    if ((rc = make_map(&al, Alo, mode, 2, adims, astr, abox, "A.lo", swz)) != 0) return rc;
+    if ((rc = make_map(&bl, Blo, mode, 2, bdims, bstr, bbox, "B.lo", swz)) != 0) return rc;
   } else {
     al = ah;
     bl = bh;
   }
-  RowMap rm{rows_in, t_valid, rows_out, fold, N / fold};
+  NTArgs a;
+  a.R = R; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.alpha = alpha;
+  a.alpha_dev = alpha_dev; a.bias = bias;
+  a.rm = RowMap{rows_in, t_valid, rows_out, fold, N / fold};
+  a.colsum = colsum; a.colsumsq = colsumsq; a.accumulate = accumulate; a.flush_kb = flush_kb;
+  a.stages = 0; a.stat_cols = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pair2) {
-    return mode == 1 ? launch_nt2<128, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,
-                                             colsum, colsumsq, accumulate, flush_kb, st)
-                     : launch_nt2<128, false>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,
-                                              colsum, colsumsq, accumulate, flush_kb, st);
+#define PASE_NT_MODES(FN, ...)                                                           \
+  switch (mode * 2 + (c_bf16 ? 1 : 0)) {                                                 \
+    case 0: return FN(0, false, __VA_ARGS__);                                            \
+    case 1: return FN(0, true, __VA_ARGS__);                                             \
+    case 2: return FN(1, false, __VA_ARGS__);                                            \
+    case 3: return FN(1, true, __VA_ARGS__);                                             \
+    case 4: return FN(2, false, __VA_ARGS__);                                            \
+    case 5: return FN(2, true, __VA_ARGS__);                                             \
+    case 6: return FN(3, false, __VA_ARGS__);                                            \
+    default: return FN(3, true, __VA_ARGS__);                                            \
   }
-  if (window) {
-#define PASE_NTW(BNV)                                                                          \
-  (mode == 1 ? launch_ntw<BNV, true>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,       \
-                                     colsum, colsumsq, accumulate, flush_kb, win_rows, st)      \
-             : launch_ntw<BNV, false>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,      \
-                                      colsum, colsumsq, accumulate, flush_kb, win_rows, st))
-    if (BN == 64) return PASE_NTW(64);
-    return PASE_NTW(128);
-#undef PASE_NTW
+#define PASE_NT2(MODEV, O16, BNV) launch_nt2<BNV, MODEV, O16>(ah, al, bh, bl, a, st)
+#define PASE_NT1(MODEV, O16, BNV, RB) launch_nt<BNV, MODEV, RB, O16>(ah, al, bh, bl, a, st)
+  if (pair2) { PASE_NT_MODES(PASE_NT2, 128) }
+  if (BN == 64) { PASE_NT_MODES(PASE_NT1, 64, 128) }
+  if (BN == 128) { PASE_NT_MODES(PASE_NT1, 128, 128) }
+  switch (mode * 2 + (c_bf16 ? 1 : 0)) {       // BN == 256 (never mode 3)
+    case 0: return PASE_NT1(0, false, 256, 64);
+    case 1: return PASE_NT1(0, true, 256, 64);
+    case 2: return PASE_NT1(1, false, 256, 64);
+    case 3: return PASE_NT1(1, true, 256, 64);
+    case 4: return PASE_NT1(2, false, 256, 64);
+    default: return PASE_NT1(2, true, 256, 64);
   }
-#define PASE_NT(BNV, BKV)                                                                       \
-  (mode == 1 ? launch_nt<BNV, true, BKV>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,   \
-                                         colsum, colsumsq, accumulate, flush_kb, st)            \
-             : launch_nt<BNV, false, BKV>(ah, al, bh, bl, R, C, ldc, M, N, K, alpha, bias, rm,  \
-                                          colsum, colsumsq, accumulate, flush_kb, st))
-  if (BN == 64) return PASE_NT(64, 32);
-  if (BN == 128) return PASE_NT(128, 32);
-  return PASE_NT(256, 16);
-#undef PASE_NT
+#undef PASE_NT1
+#undef PASE_NT2
+#undef PASE_NT_MODES
 }
 
 // A: groups x [rows_per_group x lda] starting `offA` rows into each group of pitch `pitchA`
-// rows (columns 0..I-1 used); B: folded rows of R floats, group pitch `pitchB` rows.
-int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, int offA,
-                    const float* Bhi, const float* Blo, int R, int pitchB, long b_rows_total,
+// rows (columns 0..I-1 used); B: folded rows of R elements, group pitch `pitchB` rows.
+int pase_tc_gemm_tn(const void* Ahi, const void* Alo, long lda, int pitchA, int offA,
+                    const void* Bhi, const void* Blo, int R, int pitchB, long b_rows_total,
                     float* C, long ldc, int I, int J, int groups, int rows_per_group, float alpha,
-                    int accumulate, int mode, void* stream) {
+                    const float* alpha_dev, int accumulate, int mode, void* stream) {
   PASE_CHECK_ARG(Ahi && Bhi && C && I > 0 && J > 0 && groups > 0 && rows_per_group > 0,
                  "pase_tc_gemm_tn: bad args");
-  pase_tc_init_epi_sleep();
-  PASE_CHECK_ARG(mode == 0 || (Alo && Blo), "pase_tc_gemm_tn: mode 1 needs lo operands");
-  PASE_CHECK_ARG(R >= 32 && (R % 32) == 0 && (lda % 4) == 0 && (I % 4) == 0 && (J % 32) == 0,
-                 "pase_tc_gemm_tn: need R%%32==0, lda%%4==0, I%%4==0, J%%32==0 (R=%d lda=%ld I=%d "
-                 "J=%d)", R, lda, I, J);
+  PASE_CHECK_ARG(mode >= 0 && mode <= 3, "pase_tc_gemm_tn: mode %d", mode);
+  pase_tc_init_diag();
+  const bool split = mode == 1 || mode == 3;
+  const int esz = mode >= 2 ? 2 : 4;
+  const int eb = 128 / esz;
+  PASE_CHECK_ARG(!split || (Alo && Blo), "pase_tc_gemm_tn: split modes need lo operands");
+  PASE_CHECK_ARG(R >= eb && (R % eb) == 0 && (lda * esz) % 16 == 0 && (I % 4) == 0 &&
+                     (J % eb) == 0,
+                 "pase_tc_gemm_tn: need R%%%d==0, lda*%d%%16==0, I%%4==0, J%%%d==0 (R=%d lda=%ld "
+                 "I=%d J=%d)", eb, esz, eb, R, lda, I, J);
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) {
     cudaError_t e =
@@ -1709,43 +1533,53 @@ int pase_tc_gemm_tn(const float* Ahi, const float* Alo, long lda, int pitchA, in
     }
   }
   const int BN = J <= 64 ? 64 : 128;
-  const int flush_ch = (mode == 1) ? 4 : 0;      // fold TMEM into fp32 sums every 128 rows
+  const int kr = 4 * (32 / esz);                 // reduction rows per stage
+  const int flush_ch = split ? (128 / kr > 0 ? 128 / kr : 1) : 0;   // fold every 128 rows
   CUtensorMap ah, al, bh, bl;
-  // A as (32 floats, rows-in-group, column blocks of 32, groups): the block dimension has the
-  // smallest stride after the inner one, so one box brings BM/32 MN-blocks of [32 rows x 128 B]
-  uint64_t adims[4] = {32, (uint64_t)rows_per_group, (uint64_t)((I + 31) / 32), (uint64_t)groups};
-  uint64_t astr[3] = {(uint64_t)lda * 4, 128, (uint64_t)pitchA * lda * 4};
-  uint32_t abox[4] = {32, TN_KR, (uint32_t)(BM / 32), 1};
+  // A as (128 B, rows-in-group, column blocks, groups): the block dimension has the smallest
+  // stride after the inner one, so one box brings BM/eb MN-blocks of [kr rows x 128 B]
+  uint64_t adims[4] = {(uint64_t)eb, (uint64_t)rows_per_group, (uint64_t)((I + eb - 1) / eb),
+                       (uint64_t)groups};
+  uint64_t astr[3] = {(uint64_t)lda * esz, 128, (uint64_t)pitchA * lda * esz};
+  uint32_t abox[4] = {(uint32_t)eb, (uint32_t)kr, (uint32_t)(BM / eb), 1};
   // B group g covers folded rows [g*pitchB, ...): rows beyond the allocation are zero-filled
   long rows_in_group = b_rows_total - (long)(groups - 1) * pitchB;
   if (rows_in_group > pitchB + (J + R - 1) / R + 1) rows_in_group = pitchB + (J + R - 1) / R + 1;
   const int b_blocked = (R % BN) == 0;
-  uint64_t bdims[4] = {32, (uint64_t)rows_in_group, (uint64_t)(R / 32), (uint64_t)groups};
-  uint64_t bstr[3] = {(uint64_t)R * 4, 128, (uint64_t)pitchB * R * 4};
-  uint32_t bbox[4] = {32, TN_KR, (uint32_t)(b_blocked ? BN / 32 : 1), 1};
-  // NOTE: when I % 32 != 0 the last A column block reads up to 31 floats past a row's I
+  uint64_t bdims[4] = {(uint64_t)eb, (uint64_t)rows_in_group, (uint64_t)(R / eb),
+                       (uint64_t)groups};
+  uint64_t bstr[3] = {(uint64_t)R * esz, 128, (uint64_t)pitchB * R * esz};
+  uint32_t bbox[4] = {(uint32_t)eb, (uint32_t)kr, (uint32_t)(b_blocked ? BN / eb : 1), 1};
+  // NOTE: when I % eb != 0 the last A column block reads up to eb-1 elements past a row's I
   // columns (they only feed output rows >= I, which are never stored); the caller must
-  // keep 32 floats of slack after the last row of A.
+  // keep 128 bytes of slack after the last row of A.
   int rc;
-  const CUtensorMapSwizzle sw32 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if ((rc = make_map(&ah, Ahi + (long)offA * lda, 4, adims, astr, abox, "tn A.hi", sw32)) != 0)
-    return rc;
-  if ((rc = make_map(&bh, Bhi, 4, bdims, bstr, bbox, "tn B.hi", sw32)) != 0) return rc;
-  if (mode == 1) {
-    if ((rc = make_map(&al, Alo + (long)offA * lda, 4, adims, astr, abox, "tn A.lo", sw32)) != 0)
-      return rc;
-    if ((rc = make_map(&bl, Blo, 4, bdims, bstr, bbox, "tn B.lo", sw32)) != 0) return rc;
+  const CUtensorMapSwizzle sw = esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                         : CU_TENSOR_MAP_SWIZZLE_128B;
+  const char* Ah_off = reinterpret_cast<const char*>(Ahi) + (long)offA * lda * esz;
+  if ((rc = make_map(&ah, Ah_off, mode, 4, adims, astr, abox, "tn A.hi", sw)) != 0) return rc;
+  if ((rc = make_map(&bh, Bhi, mode, 4, bdims, bstr, bbox, "tn B.hi", sw)) != 0) return rc;
+  if (split) {
+    const char* Al_off = reinterpret_cast<const char*>(Alo) + (long)offA * lda * esz;
+    if ((rc = make_map(&al, Al_off, mode, 4, adims, astr, abox, "tn A.lo", sw)) != 0) return rc;
+    if ((rc = make_map(&bl, Blo, mode, 4, bdims, bstr, bbox, "tn B.lo", sw)) != 0) return rc;
   } else {
     al = ah;
     bl = bh;
   }
-#define PASE_TN(BNV)                                                                            \
-  (mode == 1 ? launch_tn<BNV, true>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,    \
-                                    alpha, flush_ch, b_blocked, st)                             \
-             : launch_tn<BNV, false>(ah, al, bh, bl, R, C, ldc, I, J, groups, rows_per_group,   \
-                                     alpha, flush_ch, b_blocked, st))
-  if (BN == 64) return PASE_TN(64);
-  return PASE_TN(128);
+  TNArgs a;
+  a.R = R; a.C = C; a.ldc = ldc; a.I = I; a.J = J; a.groups = groups;
+  a.rows_per_group = rows_per_group; a.alpha = alpha; a.alpha_dev = alpha_dev;
+  a.chunks_per_split = 0; a.flush_ch = flush_ch; a.stages = 0; a.b_blocked = b_blocked;
+#define PASE_TN(BNV)                                                      \
+  switch (mode) {                                                         \
+    case 0: return launch_tn<BNV, 0>(ah, al, bh, bl, a, st);              \
+    case 1: return launch_tn<BNV, 1>(ah, al, bh, bl, a, st);              \
+    case 2: return launch_tn<BNV, 2>(ah, al, bh, bl, a, st);              \
+    default: return launch_tn<BNV, 3>(ah, al, bh, bl, a, st);             \
+  }
+  if (BN == 64) { PASE_TN(64) }
+  PASE_TN(128)
 #undef PASE_TN
 }
 

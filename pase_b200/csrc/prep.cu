@@ -218,8 +218,27 @@ __device__ __forceinline__ float w_tf32_rn(float v) {
   return __uint_as_float(u & 0xFFFFE000u);
 }
 
+// fmt: operand format of the hi/lo outputs -- 0: 3xTF32 split (fp32 hi/lo), 1: bf16 into
+// `hi`, 2: fp16 pair (hi, lo' = (v-hi)*2^11).  dst (fp32, may be NULL) gets the plain value.
+__device__ __forceinline__ void w_store(float* dst, void* hi, void* lo, long e, float v, int fmt) {
+  if (dst != nullptr) dst[e] = v;
+  if (hi == nullptr) return;
+  if (fmt == 0) {
+    const float h = w_tf32_rn(v);
+    reinterpret_cast<float*>(hi)[e] = h;
+    reinterpret_cast<float*>(lo)[e] = w_tf32_rn(v - h);
+  } else if (fmt == 1) {
+    reinterpret_cast<__nv_bfloat16*>(hi)[e] = __float2bfloat16_rn(v);
+  } else {
+    __half h, l;
+    f16_split(v, h, l);
+    reinterpret_cast<__half*>(hi)[e] = h;
+    reinterpret_cast<__half*>(lo)[e] = l;
+  }
+}
+
 __global__ void conv_w_batch_kernel(const long* __restrict__ table, int njobs, long total, int op,
-                                    float* __restrict__ dst_base) {
+                                    float* __restrict__ dst_base, int fmt) {
   __shared__ long jt[WJOB_MAX * WJOB];
   for (int i = threadIdx.x; i < njobs * WJOB; i += blockDim.x) jt[i] = table[i];
   __syncthreads();
@@ -230,8 +249,8 @@ __global__ void conv_w_batch_kernel(const long* __restrict__ table, int njobs, l
     const long* J = jt + j * WJOB;
     const float* src = reinterpret_cast<const float*>(J[0]);
     float* dst = (op == 2) ? dst_base + J[1] : reinterpret_cast<float*>(J[1]);
-    float* hi = reinterpret_cast<float*>(J[2]);
-    float* lo = reinterpret_cast<float*>(J[3]);
+    void* hi = reinterpret_cast<void*>(J[2]);
+    void* lo = reinterpret_cast<void*>(J[3]);
     const int Cout = (int)J[4], Cin = (int)J[5], k = (int)J[6], sd = (int)J[7], taps = (int)J[8];
     const long e = i - J[9];
     float v;
@@ -257,12 +276,7 @@ __global__ void conv_w_batch_kernel(const long* __restrict__ table, int njobs, l
       const int co = (int)(r / Cin);
       v = src[((long)co * k + jj) * Cin + ci];
     }
-    dst[e] = v;
-    if (hi != nullptr) {
-      const float h = w_tf32_rn(v);
-      hi[e] = h;
-      lo[e] = w_tf32_rn(v - h);
-    }
+    w_store(dst, hi, lo, e, v, fmt);
   }
 }
 
@@ -273,17 +287,8 @@ __global__ void conv_w_batch_kernel(const long* __restrict__ table, int njobs, l
 constexpr int WB_CI = 8;
 constexpr int WB_SMEM_FLOATS = 12000;          // 46.9 KB (+ the static job row < 48 KB)
 
-__device__ __forceinline__ void w_store(float* dst, float* hi, float* lo, long e, float v) {
-  dst[e] = v;
-  if (hi != nullptr) {
-    const float h = w_tf32_rn(v);
-    hi[e] = h;
-    lo[e] = w_tf32_rn(v - h);
-  }
-}
-
 __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int njobs, int op,
-                                          float* __restrict__ dst_base) {
+                                          float* __restrict__ dst_base, int fmt) {
   extern __shared__ float tile[];
   __shared__ long J[WJOB];
   if (threadIdx.x == 0) {
@@ -294,8 +299,8 @@ __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int nj
   __syncthreads();
   const float* src = reinterpret_cast<const float*>(J[0]);
   float* dst = (op == 5) ? dst_base + J[1] : reinterpret_cast<float*>(J[1]);
-  float* hi = reinterpret_cast<float*>(J[2]);
-  float* lo = reinterpret_cast<float*>(J[3]);
+  void* hi = reinterpret_cast<void*>(J[2]);
+  void* lo = reinterpret_cast<void*>(J[3]);
   const int Cout = (int)J[4], Cin = (int)J[5], k = (int)J[6], sd = (int)J[7], taps = (int)J[8];
   const int b = (int)((long)blockIdx.x - J[11]);
   if (op == 3) {                       // Wt[co][j][ci] = W[co][ci][j]
@@ -305,7 +310,7 @@ __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int nj
     __syncthreads();
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
       const int ci = e % Cin, jj = e / Cin;
-      w_store(dst, hi, lo, (long)b * n + e, tile[ci * k + jj]);
+      w_store(dst, hi, lo, (long)b * n + e, tile[ci * k + jj], fmt);
     }
   } else if (op == 5) {                // dW[co][ci][j] = dWt[co][j][ci]
     const int n = Cin * k, pitch = Cin + 1;
@@ -334,7 +339,7 @@ __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int nj
       const int jj = sd * (taps - 1 - v) + pp;
       const float val = (jj < k) ? tile[lane * pitch + cl * k + jj] : 0.f;
       const long e = (((long)pp * Cin + ci0 + cl) * taps + v) * Cout + co0 + lane;
-      w_store(dst, hi, lo, e, val);
+      w_store(dst, hi, lo, e, val, fmt);
     }
   }
 }
@@ -359,24 +364,26 @@ int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, 
   return PASE_OK;
 }
 
-int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* dst_base,
+int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* dst_base, int fmt,
                       void* stream) {
   PASE_CHECK_ARG(table && njobs > 0 && njobs <= WJOB_MAX && total > 0,
                  "pase_conv_w_batch: bad args (njobs=%d, at most %d)", njobs, WJOB_MAX);
   PASE_CHECK_ARG(op >= 0 && op <= 5 && ((op % 3) != 2 || dst_base != nullptr),
                  "pase_conv_w_batch: op=%d (0 to_fwd, 1 to_dgrad, 2 from_fwd + dst_base; 3..5 "
                  "tiled)", op);
+  PASE_CHECK_ARG(fmt >= 0 && fmt <= 2, "pase_conv_w_batch: fmt=%d (0 tf32 split, 1 bf16, 2 f16 "
+                 "pair)", fmt);
   if (op >= 3) {
     // tiled: `total` thread blocks, 48 KB of shared memory (the caller guarantees that a
     // slab fits: (Cin+1)*k resp. 32*(8*k+1) floats <= 12000, Cout % 32 == 0, Cin % 8 == 0)
     PASE_CHECK_ARG(total < (1L << 31), "pase_conv_w_batch: too many blocks");
     conv_w_batch_tiled_kernel<<<(unsigned)total, 256, WB_SMEM_FLOATS * sizeof(float),
-                                (cudaStream_t)stream>>>(table, njobs, op, dst_base);
+                                (cudaStream_t)stream>>>(table, njobs, op, dst_base, fmt);
     PASE_LAUNCH_CHECK("pase_conv_w_batch");
     return PASE_OK;
   }
   conv_w_batch_kernel<<<nblk(total), 256, 0, (cudaStream_t)stream>>>(table, njobs, total, op,
-                                                                    dst_base);
+                                                                    dst_base, fmt);
   PASE_LAUNCH_CHECK("pase_conv_w_batch");
   return PASE_OK;
 }

@@ -80,9 +80,9 @@ class _DecoderStackFn(torch.autograd.Function):
                 out = torch.empty(B * g.L, g.Cout, dtype=torch.float32, device=rows.device)
                 dst, d_ss = out.reshape(-1), g.L * g.Cout
             C = g.Cout
-            call("pase_bn_prelu_pad_fwd", plan.yfull[i][g.pad * C:], g.U * g.s * C, B, g.L, C,
-                 plan.ones[:C], plan.zeros[:C], alpha.reshape(-1), dst, d_ss, C, 0, 0,
-                 None, 0, 0, 0, 0, None)
+            call("pase_bn_prelu_pad_fwd", plan.yfull[i][g.pad * C:], 0, g.U * g.s * C, B, g.L, C,
+                 plan.ones[:C], plan.zeros[:C], alpha.reshape(-1), dst, None, 0, d_ss, C, 0, 0,
+                 None, 0, 0, 0, 0)
         ctx.plan, ctx.generation = plan, plan.generation
         ctx.save_for_backward(*params)
         return out
@@ -106,10 +106,10 @@ class _DecoderStackFn(torch.autograd.Function):
             acc = plan.acc
             acc.zero_()
             S1, S2, dal, dbi = acc[:C], acc[C:2 * C], acc[2 * C:3 * C], acc[3 * C:4 * C]
-            call("pase_bn_prelu_bwd_reduce", plan.yfull[i][g.pad * C:], g.U * g.s * C, B, g.L, C,
+            call("pase_bn_prelu_bwd_reduce", plan.yfull[i][g.pad * C:], 0, g.U * g.s * C, B, g.L, C,
                  plan.zeros[:C], plan.ones[:C], plan.ones[:C], plan.zeros[:C], alpha.reshape(-1),
-                 src, g.L * C, C, 0, 0, None, 0, 0, 0, None, 0, 0, 0, 0,
-                 plan.dyfull[i][g.pad * C:], g.U * g.s * C, S1, S2, dal)
+                 src, 0, g.L * C, C, 0, 0, None, 0, 0, 0, None, 0, 0, 0, 0,
+                 plan.dyfull[i][g.pad * C:], g.U * g.s * C, S1, S2, dal, None)
             call("pase_colsum", plan.dyfull[i], C, B * g.U * g.s, C, dbi)
             small = torch.empty(4 * C, dtype=torch.float32, device=dev)
             call("pase_cast_d2f", acc, small, 4 * C, 1.0)

@@ -23,9 +23,17 @@ from . import ops
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 SINC_FOLD = 4            # polyphase fold of the sinc layer on the fp32 FFMA path
-TC_SINC_FOLD = 32        # on the tensor-core path one folded row = one 128-byte TMA row
-# numerics of the GEMMs: None = fp32 FFMA; 1 = 3xTF32 tcgen05 (fp32-equivalent); 0 = TF32
-PRECISIONS = {"fp32": None, "3xtf32": 1, "tf32": 0}
+# on the tensor-core path one folded row = one 128-byte TMA row: 32 fp32 / 64 16-bit elements
+TC_SINC_FOLD = {0: 32, 1: 32, 2: 64, 3: 64}
+# numerics of the GEMMs (pase_tc_gemm_* `mode`): None = fp32 FFMA; 0 = TF32; 1 = 3xTF32
+# (fp32-equivalent); 2 = bf16 operands AND bf16 activation storage; 3 = 3xF16 (fp16 operand
+# pairs, fp32-equivalent products at half the tensor time / operand bytes of 3xTF32)
+PRECISIONS = {"fp32": None, "3xtf32": 1, "tf32": 0, "bf16": 2, "3xf16": 3}
+# storage format codes of the C-ABI (include/pase_b200.h)
+FMT_F32, FMT_BF16, FMT_F16X2 = 0, 1, 2
+OP_FMT = {None: FMT_F32, 0: FMT_F32, 1: FMT_F32, 2: FMT_BF16, 3: FMT_F16X2}
+OP_DTYPE = {None: torch.float32, 0: torch.float32, 1: torch.float32, 2: torch.bfloat16,
+            3: torch.float16}
 
 
 def _cdiv(a, b):
@@ -64,7 +72,7 @@ class ConvGeom(object):
             # polyphase fold: row u of the GEMM produces times fold*u .. fold*u+fold-1
             self.fold = sinc_fold
             self.lda = sinc_fold                       # floats between consecutive rows
-            self.K = _ru(k + sinc_fold - 1, 32 if sinc_fold >= 32 else 4)
+            self.K = _ru(k + sinc_fold - 1, sinc_fold if sinc_fold >= 32 else 4)
             self.Nn = sinc_fold * Cout
             self.P = _cdiv(self.Tpad, sinc_fold)       # rows per sample
             self.rows_out = _cdiv(self.T_out, sinc_fold)
@@ -102,21 +110,51 @@ def frame_counts(cfg, T):
     return [g.T_out for g in build_geometry(cfg, T)]
 
 
+class Operand(object):
+    """One GEMM operand in the format of the plan's GEMM mode.
+    hi / lo: the tensors handed to pase_tc_gemm_* (lo None outside the split modes);
+    alpha: device float[2] = {1/s, s} when the operand is a power-of-two scaled gradient
+    (3xF16), else None;  src: the fp32 tensor it is converted from (None when the producing
+    kernel writes the operand format directly)."""
+    __slots__ = ("hi", "lo", "alpha", "src", "kind", "amax")
+
+    def __init__(self, hi, lo=None, alpha=None, src=None, kind="act", amax=None):
+        self.hi, self.lo, self.alpha, self.src, self.kind, self.amax = hi, lo, alpha, src, kind, amax
+
+
 class EncoderPlan(object):
     """All HBM buffers of one (N, T) problem, allocated once and reused every
     step (180 GB HBM: nothing is recomputed or re-allocated).  Padded operand
     buffers are zero-initialised once; kernels only ever write their valid
-    region, so halos / slack stay finite."""
+    region, so halos / slack stay finite.
+
+    Storage by precision:
+      fp32 / tf32 / 3xtf32: everything fp32 (3xtf32 adds tf32-residual twins of the operands);
+      bf16 : GEMM operands, raw conv outputs y, gradients dxpad / du / dy in bf16; statistics,
+             weights' master copies, weight gradients and the small output-side tensors fp32;
+      3xf16: GEMM operands as fp16 (hi, lo') pairs, everything else fp32."""
 
     def __init__(self, cfg, N, T, device, prec="fp32"):
         self.cfg, self.N, self.T, self.device = cfg, N, T, device
         if prec not in PRECISIONS:
             raise ValueError("precision must be one of %s" % (sorted(PRECISIONS),))
         self.prec, self.mode = prec, PRECISIONS[prec]
-        self._twins = {}
+        mode = self.mode
+        self.fmt = OP_FMT[mode]
+        self.op_dtype = OP_DTYPE[mode]
+        self.split_mode = mode in (1, 3)
+        self.y_bf16 = 1 if mode == 2 else 0
+        self.eb = 64 if mode in (2, 3) else 32          # elements per 128-byte TMA row
+        self._ops = {}
         self._wtables = {}
-        self.geoms = build_geometry(cfg, T, TC_SINC_FOLD if self.mode is not None else SINC_FOLD)
+        self.geoms = build_geometry(cfg, T, TC_SINC_FOLD[mode] if mode is not None else SINC_FOLD)
         G = self.geoms
+        if mode in (2, 3):
+            for g in G:
+                if (g.lda % 64) or (g.Cout % 64 and not g.sinc):
+                    raise NotImplementedError(
+                        "precision %r needs channel counts that are multiples of 64 (block %d: "
+                        "Cin=%d Cout=%d stride=%d)" % (prec, g.idx, g.Cin, g.Cout, g.s))
         self.nblk = len(G)
         self.Tq = G[-1].T_out
         self.emb = cfg["emb_dim"]
@@ -127,8 +165,12 @@ class EncoderPlan(object):
         self.H = (cfg["rnn_dim"] // 2) * 2 if self.rnn else 0
         f32 = dict(dtype=torch.float32, device=device)
         f64 = dict(dtype=torch.float64, device=device)
+        opd = dict(dtype=self.op_dtype, device=device)
+        yd = dict(dtype=torch.bfloat16 if mode == 2 else torch.float32, device=device)
         z = lambda n: torch.zeros(int(n), **f32)
         e = lambda n: torch.empty(int(n), **f32)
+        zo = lambda n: torch.zeros(int(n), **opd)          # operand-format buffers (hi / lo)
+        zlo = lambda n: torch.zeros(int(n), **opd) if self.split_mode else None
 
         # concatenated [rnn-out | pooled skips] operand of the output projection
         self.col_off = []
@@ -140,37 +182,56 @@ class EncoderPlan(object):
         self.Kc = off
         self.pool_d = [max(g.T_out // self.Tq, 1) for g in G[:-1]]
 
-        self.apad, self.y, self.bn = [], [], []
-        self.Wt, self.dWt, self.Wd, self.dyz, self.dxpad = [], [], [], [], []
+        self.apad, self.apad_lo, self.y, self.bn = [], [], [], []
+        self.Wt, self.dWt, self.Wd, self.dyz, self.dyz_lo, self.dxpad = [], [], [], [], [], []
+        self.gscale = []
+        du_max = 0
         for g in G:
-            self.apad.append(z(N * g.apad_floats + g.K + 64))
-            self.y.append(e(N * g.rows_out * g.Nn))
+            n_apad = N * g.apad_floats + g.K + 64
+            self.apad.append(zo(n_apad))
+            self.apad_lo.append(zlo(n_apad))
+            self._ops[("apad", g.idx)] = Operand(self.apad[-1], self.apad_lo[-1])
+            self.y.append(torch.empty(int(N * g.rows_out * g.Nn), **yd))
             self.bn.append(torch.zeros(4, g.Cout, **f32))       # mean, invstd, scale, shift
             self.Wt.append(e(g.Nn * g.K))
             self.dWt.append(e(g.Nn * g.K))
+            gs = torch.ones(2, **f32) if mode == 3 else None
+            self.gscale.append(gs)
             if g.sinc:
+                n_dyz = N * g.rows_out * g.Nn + 128
                 self.Wd.append(None)
-                self.dyz.append(z(N * g.rows_out * g.Nn))
                 self.dxpad.append(None)
             else:
+                n_dyz = N * g.Pd * g.Cout + g.taps * g.Cout + 128
                 self.Wd.append(e(g.s * g.Cin * g.taps * g.Cout))
-                self.dyz.append(z(N * g.Pd * g.Cout + g.taps * g.Cout + 64))
-                self.dxpad.append(e(N * g.apad_floats) if g.idx > 0 else None)
+                self.dxpad.append(torch.empty(int(N * g.apad_floats), **yd) if g.idx > 0 else None)
+            self.dyz.append(zo(n_dyz))
+            self.dyz_lo.append(zlo(n_dyz))
+            self._ops[("dyz", g.idx)] = Operand(self.dyz[-1], self.dyz_lo[-1],
+                                                None if gs is None else gs, kind="grad")
+            du_max = max(du_max, n_dyz)
+        # 3xF16: du lives in an fp32 scratch between the two BatchNorm backward passes (the
+        # fp16 pair is written by pass 2 once the power-of-two scale is known)
+        self.du_scratch = e(du_max) if mode == 3 else None
         rows = N * self.Tq
         self.rows = rows
         if self.rnn:
             Cq, H = self.Clast, self.H
-            self.xq = z(N * (self.Tq + 1) * Cq + 2 * Cq + 64)
-            self.Yg, self.Cst, self.dYg = e(rows * 3 * H), e(rows * H), e(rows * 3 * H)
+            n_xq = N * (self.Tq + 1) * Cq + 2 * Cq + 64
+            self.xq, self.xq_lo = zo(n_xq), zlo(n_xq)
+            self._ops["xq"] = Operand(self.xq, self.xq_lo)
+            self.Yg, self.Cst, self.dYg = e(rows * 3 * H), e(rows * H), z(rows * 3 * H + 64)
             self.dsrc = e(rows * 2 * Cq)
+            self.Wq = e(3 * H * 2 * Cq)
             self.WqT = e(2 * Cq * 3 * H)
             self.dWq = e(3 * H * 2 * Cq)
         self.cat = z(rows * self.Kc)
         self.dcat = e(rows * self.Kc)
+        self.Wcat = e(self.emb * self.Kc)
         self.WcatT = e(self.Kc * self.emb)
         self.dWcat = e(self.emb * self.Kc)
         self.yout = e(rows * self.emb)
-        self.g = torch.zeros(rows * self.emb + 64, **f32)     # +slack: TC wgrad reads 32-col blocks
+        self.g = torch.zeros(rows * self.emb + 64, **f32)     # +slack: TC wgrad reads whole blocks
         self.bn_out = torch.zeros(4, self.emb, **f32)
         self.bn_out[1].fill_(1.0)
         self.bn_out[2].fill_(1.0)
@@ -198,37 +259,71 @@ class EncoderPlan(object):
         self.stats_b = torch.zeros(n, **f64)
         self.grad_vec = torch.zeros(n, **f32)
         self.zeros64 = torch.zeros(max(2 * max(g.Cout for g in G), 2 * self.emb), **f64)
+        # running maxima for the 3xF16 gradient scales: 2 floats per use, zeroed per backward
+        self.amax = torch.zeros(2 * (self.nblk + 4), **f32) if mode == 3 else None
         self.generation = 0
 
-    # -- GEMM dispatch: fp32 FFMA kernels or tcgen05 tensor-core kernels -------------
-    def split(self, name, buf, fresh=True, weights=False):
-        """mode 1 (3xTF32): (hi, lo) parts of an operand.
-        Activations: kind::tf32 reads only the upper 19 bits of an fp32 operand, so the
-        operand itself is "hi" and only lo = rn(x - trunc(x)) needs a twin buffer.
-        Weights (small): explicit hi = rn(x), lo = rn(x - hi), so that the dropped lo*lo and
-        residual terms have random sign (no coherent bias in strongly cancelling sums).
-        `fresh=False` reuses the split computed earlier in the same step."""
-        if self.mode != 1:
-            return buf, None
-        tw = self._twins.get(name)
-        if tw is None or tw[1].numel() != buf.numel():
-            tw = (torch.zeros_like(buf) if weights else None, torch.zeros_like(buf))
-            self._twins[name] = tw
+    # -- GEMM operands -----------------------------------------------------------------
+    def operand(self, name, buf, fresh=True, kind="act"):
+        """Operand `name` in the plan's GEMM format.  Operands whose producer writes the GEMM
+        format directly (apad, xq, dyz) are registered at construction; everything else is an
+        fp32 tensor converted here (`fresh=False` reuses this step's earlier conversion):
+          tf32   : the tensor itself;
+          3xtf32 : activations: the tensor is "hi" (kind::tf32 truncates), lo = rn(x-trunc(x));
+                   weights: explicit hi = rn(x), lo = rn(x - hi) (no coherent bias);
+          bf16   : bf16 copy;    3xf16 : fp16 (hi, lo') pair, gradients pre-scaled by a power
+                   of two (alpha = {1/s, s} on the device)."""
+        op = self._ops.get(name)
+        if op is not None and op.src is None:
+            return op
+        mode = self.mode
+        if mode == 0:
+            return Operand(buf)
+        if op is None or op.src.numel() != buf.numel() or op.src.data_ptr() != buf.data_ptr():
+            f32 = dict(dtype=torch.float32, device=self.device)
+            if mode == 1:
+                hi = torch.zeros_like(buf) if kind == "weight" else buf
+                op = Operand(hi, torch.zeros_like(buf), src=buf, kind=kind)
+            elif mode == 2:
+                op = Operand(torch.zeros(buf.numel(), dtype=torch.bfloat16, device=self.device),
+                             src=buf, kind=kind)
+            else:
+                h = torch.zeros(buf.numel(), dtype=torch.float16, device=self.device)
+                grad = kind == "grad"
+                op = Operand(h, torch.zeros_like(h),
+                             torch.ones(2, **f32) if grad else None, src=buf, kind=kind,
+                             amax=torch.zeros(2, **f32) if grad else None)
+            self._ops[name] = op
             fresh = True
         if fresh:
-            ops.call("pase_split_tf32", buf, tw[0], tw[1], buf.numel())
-        return (tw[0] if weights else buf), tw[1]
+            n = buf.numel()
+            if mode == 1:
+                ops.call("pase_split_tf32", buf, op.hi if kind == "weight" else None, op.lo, n)
+            elif mode == 2:
+                ops.call("pase_cast_bf16", buf, op.hi, n)
+            else:
+                if op.amax is not None:
+                    op.amax.zero_()
+                    ops.call("pase_absmax", buf, n, op.amax)
+                ops.call("pase_split_f16", buf, op.hi, op.lo, n, op.amax, op.alpha)
+        return op
 
-    def twins_w(self, name, buf):
-        """(hi, lo) twin buffers of a weight operand for producers that write the split
-        themselves (pase_conv_w_batch); (None, None) outside 3xTF32 mode."""
-        if self.mode != 1:
+    def w_operand(self, name, buf):
+        """(hi, lo) buffers of a weight operand written by pase_conv_w_batch itself."""
+        mode = self.mode
+        if mode is None or mode == 0:
             return None, None
-        tw = self._twins.get(name)
-        if tw is None or tw[0] is None or tw[1].numel() != buf.numel():
-            tw = (torch.zeros_like(buf), torch.zeros_like(buf))
-            self._twins[name] = tw
-        return tw
+        op = self._ops.get(name)
+        if op is None:
+            if mode == 1:
+                op = Operand(torch.zeros_like(buf), torch.zeros_like(buf))
+            elif mode == 2:
+                op = Operand(torch.zeros(buf.numel(), dtype=torch.bfloat16, device=self.device))
+            else:
+                h = torch.zeros(buf.numel(), dtype=torch.float16, device=self.device)
+                op = Operand(h, torch.zeros_like(h))
+            self._ops[name] = op
+        return op.hi, op.lo
 
     def w_batch(self, op, jobs, dst_base=None):
         """One launch for the weight re-layouts of every conv block (pase_conv_w_batch).
@@ -250,50 +345,68 @@ class EncoderPlan(object):
             table = torch.tensor(rows, dtype=torch.int64).reshape(-1).to(self.device)
             ent = (rows, table)
             self._wtables[op] = ent
+        fmt = {1: 0, 2: 1, 3: 2}.get(self.mode, 0)
         if tiled:
-            ops.call("pase_conv_w_batch", ent[1], len(rows), blocks, op + 3, dst_base)
+            ops.call("pase_conv_w_batch", ent[1], len(rows), blocks, op + 3, dst_base, fmt)
         else:
-            ops.call("pase_conv_w_batch", ent[1], len(rows), start, op, dst_base)
+            ops.call("pase_conv_w_batch", ent[1], len(rows), start, op, dst_base, fmt)
 
-    def lo_of(self, name, buf):
-        """Residual twin of an activation operand, for producers that write it themselves
-        (mode 1 only; zero-initialised so halos / slack stay valid)."""
-        if self.mode != 1:
-            return None
-        tw = self._twins.get(name)
-        if tw is None or tw[1].numel() != buf.numel():
-            tw = (None, torch.zeros_like(buf))
-            self._twins[name] = tw
-        return tw[1]
+    def _tc_ok(self, *elem_strides):
+        """Tensor-core path: every operand row stride must be a multiple of 16 bytes (and the
+        A operand's folded row a multiple of 128 bytes -- checked by the caller)."""
+        q = 8 if self.mode in (2, 3) else 4
+        return all(s % q == 0 for s in elem_strides)
 
     def nt(self, an, A, lda, afresh, bn, B, ldb, bfresh, C, ldc, M, N, K, alpha, bias,
-           rows_in, t_valid, rows_out, fold, cs, cq, acc):
-        if self.mode is None or lda % 32 != 0 or K % 4 != 0 or ldb % 4 != 0:
+           rows_in, t_valid, rows_out, fold, cs, cq, acc, akind="act"):
+        """C = alpha * A B^T (+ bias): tensor-core kernel in the plan's GEMM mode, or the fp32
+        FFMA kernel (precision fp32, or shapes the TMA path cannot address)."""
+        direct = an in self._ops and self._ops[an].src is None      # no fp32 copy exists
+        if self.mode is None or lda % self.eb != 0 or not self._tc_ok(K, ldb):
+            if direct and self.mode in (2, 3):
+                raise NotImplementedError("precision %r: GEMM shape (lda=%d K=%d) outside the "
+                                          "tensor-core path" % (self.prec, lda, K))
             return ops.call("pase_gemm_nt", A, lda, B, ldb, C, ldc, M, N, K, alpha, bias,
                             rows_in, t_valid, rows_out, fold, cs, cq, acc)
-        Ah, Al = self.split(an, A, afresh)
-        Bh, Bl = self.split(bn, B, bfresh, weights=True)
-        return ops.call("pase_tc_gemm_nt", Ah, Al, A.numel() // lda, lda, Bh, Bl, ldb, C, ldc,
-                        M, N, K, alpha, bias, rows_in, t_valid, rows_out, fold, cs, cq, acc,
-                        self.mode)
+        a = self.operand(an, A, afresh, akind)
+        b = self.operand(bn, B, bfresh, "weight")
+        c16 = 1 if C.dtype == torch.bfloat16 else 0
+        return ops.call("pase_tc_gemm_nt", a.hi, a.lo, a.hi.numel() // lda, lda, b.hi, b.lo, ldb,
+                        C, ldc, M, N, K, alpha, None if a.alpha is None else a.alpha, bias,
+                        rows_in, t_valid, rows_out, fold, cs, cq, acc, self.mode, c16)
 
     def tn(self, an, A, lda, pitchA, offA, afresh, bn, B, ldb, pitchB, bfresh, C, ldc, I, J,
-           groups, rpg, alpha, acc):
-        if self.mode is None or ldb % 32 != 0 or lda % 4 != 0 or I % 4 != 0 or J % 32 != 0:
+           groups, rpg, alpha, acc, akind="grad"):
+        direct = (an in self._ops and self._ops[an].src is None) or \
+            (bn in self._ops and self._ops[bn].src is None)
+        if self.mode is None or ldb % self.eb != 0 or not self._tc_ok(lda) or I % 4 != 0 or \
+                J % self.eb != 0:
+            if direct and self.mode in (2, 3):
+                raise NotImplementedError("precision %r: weight-gradient GEMM shape (lda=%d "
+                                          "ldb=%d I=%d J=%d) outside the tensor-core path"
+                                          % (self.prec, lda, ldb, I, J))
             return ops.call("pase_gemm_tn", A, lda, pitchA, offA, B, ldb, pitchB, 0, C, ldc, I, J,
                             groups, rpg, alpha, acc)
-        Ah, Al = self.split(an, A, afresh)
-        Bh, Bl = self.split(bn, B, bfresh)
-        return ops.call("pase_tc_gemm_tn", Ah, Al, lda, pitchA, offA, Bh, Bl, ldb, pitchB,
-                        B.numel() // ldb, C, ldc, I, J, groups, rpg, alpha, acc, self.mode)
+        a = self.operand(an, A, afresh, akind)
+        b = self.operand(bn, B, bfresh, "act")
+        return ops.call("pase_tc_gemm_tn", a.hi, a.lo, lda, pitchA, offA, b.hi, b.lo, ldb, pitchB,
+                        b.hi.numel() // ldb, C, ldc, I, J, groups, rpg, alpha,
+                        None if a.alpha is None else a.alpha, acc, self.mode)
 
     def nbytes(self):
-        tot = 0
+        tot, seen = 0, set()
+
+        def add(t):
+            nonlocal tot
+            if isinstance(t, torch.Tensor) and t.data_ptr() not in seen:
+                seen.add(t.data_ptr())
+                tot += t.numel() * t.element_size()
         for v in self.__dict__.values():
-            vs = v if isinstance(v, list) else [v]
-            for t in vs:
-                if isinstance(t, torch.Tensor):
-                    tot += t.numel() * t.element_size()
+            for t in (v if isinstance(v, list) else [v]):
+                add(t)
+        for op in self._ops.values():
+            add(op.hi)
+            add(op.lo)
         return tot
 
 
@@ -331,21 +444,23 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
     plan.generation += 1
     P = lambda name: _flat(params[name])
     buf = lambda name: _flat(mod.get_buffer(name))
+    fmt, ybf = plan.fmt, plan.y_bf16
 
     g0 = G[0]
-    call("pase_reflect_pad_wave", x.reshape(-1), plan.apad[0], N, plan.T, g0.padL, g0.padR,
-         g0.apad_floats)
+    call("pase_reflect_pad_wave", x.reshape(-1), plan.apad[0], plan.apad_lo[0], fmt, N, plan.T,
+         g0.padL, g0.padR, g0.apad_floats)
     if training:
         plan.stats_f.zero_()
     if plan.skips:
         plan.cat.zero_()
 
-    # GEMM operands (+ 3xTF32 split) of every conv block's weight: one launch
+    # GEMM operands (in the plan's operand format) of every conv block's weight: one launch
     jobs = []
     for l, g in enumerate(G):
         if not g.sinc:
-            hi, lo = plan.twins_w(("Wt", l), plan.Wt[l])
-            jobs.append((P("blocks.%d.conv.weight" % l), plan.Wt[l], hi, lo, g.Cout, g.Cin, g.k,
+            hi, lo = plan.w_operand(("Wt", l), plan.Wt[l])
+            dst = plan.Wt[l] if plan.mode in (None, 0, 1) else None
+            jobs.append((P("blocks.%d.conv.weight" % l), dst, hi, lo, g.Cout, g.Cin, g.k,
                          1, 1, g.Cout * g.Cin * g.k))
     if jobs:
         plan.w_batch(0, jobs)
@@ -365,7 +480,9 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
             cs, cq = plan.stats_f[o:o + g.Nn], plan.stats_f[o + g.Nn:o + 2 * g.Nn]
         else:
             cs = cq = None
-        plan.nt(("apad", l), plan.apad[l], g.lda, l == 0, ("Wt", l), plan.Wt[l], g.K, g.sinc,
+        # sinc: the band-pass operand is regenerated (and converted) every step; conv blocks:
+        # pase_conv_w_batch already wrote the operand format
+        plan.nt(("apad", l), plan.apad[l], g.lda, False, ("Wt", l), plan.Wt[l], g.K, g.sinc,
                 plan.y[l], g.Nn, N * g.P, g.Nn, g.K, 1.0, bias, g.P, g.T_out, g.rows_out,
                 g.fold, cs, cq, 0)
         mean, invstd, scale, shift = plan.bn[l][0], plan.bn[l][1], plan.bn[l][2], plan.bn[l][3]
@@ -380,30 +497,32 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
                  buf(pre + "norm.running_var"), P(pre + "norm.weight"), P(pre + "norm.bias"),
                  g.Cout, BN_EPS, mean, invstd, scale, shift)
         C = g.Cout
-        dst_lo = None            # 3xTF32: the producer also writes the operand's tf32 residual
+        # the producer writes the next GEMM's operand in its own format (3xTF32: + the tf32
+        # residual twin; 3xF16: the fp16 pair)
         if l + 1 < plan.nblk:
             nx = G[l + 1]
-            dst, d_ss, d_rs, pl, pr = plan.apad[l + 1], nx.apad_floats, C, nx.padL, nx.padR
-            dst_lo = plan.lo_of(("apad", l + 1), plan.apad[l + 1])
+            dst, dst_lo, dfmt = plan.apad[l + 1], plan.apad_lo[l + 1], fmt
+            d_ss, d_rs, pl, pr = nx.apad_floats, C, nx.padL, nx.padR
         elif plan.rnn:
-            dst, d_ss, d_rs, pl, pr = plan.xq[C:], (Tq + 1) * C, C, 0, 0
-            lo = plan.lo_of("xq", plan.xq)
-            dst_lo = None if lo is None else lo[C:]
+            dst, dfmt = plan.xq[C:], fmt
+            dst_lo = None if plan.xq_lo is None else plan.xq_lo[C:]
+            d_ss, d_rs, pl, pr = (Tq + 1) * C, C, 0, 0
         else:
-            dst, d_ss, d_rs, pl, pr = plan.cat, Tq * Kc, Kc, 0, 0
+            dst, dst_lo, dfmt, d_ss, d_rs, pl, pr = plan.cat, None, FMT_F32, Tq * Kc, Kc, 0, 0
         if plan.skips and l + 1 < plan.nblk:
             pool, pd = plan.cat[plan.col_off[l]:], plan.pool_d[l]
         else:
             pool, pd = None, 0
-        call("pase_bn_prelu_pad_fwd", plan.y[l], g.Ty * C, N, g.T_out, C, scale, shift,
-             P(pre + "act.weight"), dst, d_ss, d_rs, pl, pr, pool, Tq * Kc, Kc, pd, Tq, dst_lo)
+        call("pase_bn_prelu_pad_fwd", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, scale, shift,
+             P(pre + "act.weight"), dst, dst_lo, dfmt, d_ss, d_rs, pl, pr, pool, Tq * Kc, Kc, pd,
+             Tq)
 
     if plan.rnn:
         Cq, H = plan.Clast, plan.H
         Wl = params["rnn.layers.0.linear.weight"].detach()
-        Wq = torch.cat([Wl[:, Cq:], Wl[:, :Cq]], 1).contiguous()      # [x_{t-1} | x_t] order
-        plan.Wq = Wq
-        plan.nt("xq", plan.xq, Cq, False, "Wq", Wq.reshape(-1), 2 * Cq, True, plan.Yg, 3 * H,
+        Wq = plan.Wq.view(3 * H, 2 * Cq)
+        torch.cat([Wl[:, Cq:], Wl[:, :Cq]], 1, out=Wq)               # [x_{t-1} | x_t] order
+        plan.nt("xq", plan.xq, Cq, False, "Wq", plan.Wq, 2 * Cq, True, plan.Yg, 3 * H,
                 N * (Tq + 1), 3 * H, 2 * Cq, 1.0, P("rnn.layers.0.linear.bias"),
                 Tq + 1, Tq, Tq, 1, None, None, 0)
         call("pase_qrnn_scan_fwd", plan.Yg, plan.cat, Kc, plan.Cst, N, Tq, H)
@@ -412,15 +531,14 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
     if plan.skips:
         parts += [params["denseskips.%d.weight" % i].detach().reshape(emb, -1)
                   for i in range(plan.nblk - 1)]
-    Wcat = torch.cat(parts, 1).contiguous() if len(parts) > 1 else parts[0].contiguous()
-    plan.Wcat = Wcat
+    torch.cat(parts, 1, out=plan.Wcat.view(emb, Kc))
     use_stats = plan.norm_out and training
     if use_stats:
         o = plan.fs_out
         cs, cq = plan.stats_f[o:o + emb], plan.stats_f[o + emb:o + 2 * emb]
     else:
         cs = cq = None
-    plan.nt("cat", plan.cat, Kc, True, "Wcat", Wcat.reshape(-1), Kc, True, plan.yout, emb,
+    plan.nt("cat", plan.cat, Kc, True, "Wcat", plan.Wcat, Kc, True, plan.yout, emb,
             rows, emb, Kc, 1.0, P("W.bias"), rows, rows, rows, 1, cs, cq, 0)
     bo = plan.bn_out
     if plan.norm_out:
@@ -452,12 +570,16 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
     grads = {}
     sb = plan.stats_b
     sb.zero_()
-    # dgrad operands (+ split) of every conv block with an input gradient: one launch
+    if plan.amax is not None:
+        plan.amax.zero_()
+    fmt, ybf = plan.fmt, plan.y_bf16
+    # dgrad operands (operand format) of every conv block with an input gradient: one launch
     jobs = []
     for l, g in enumerate(G):
         if not g.sinc and l > 0:
-            hi, lo = plan.twins_w(("Wd", l), plan.Wd[l])
-            jobs.append((P("blocks.%d.conv.weight" % l), plan.Wd[l], hi, lo, g.Cout, g.Cin, g.k,
+            hi, lo = plan.w_operand(("Wd", l), plan.Wd[l])
+            dst = plan.Wd[l] if plan.mode in (None, 0, 1) else None
+            jobs.append((P("blocks.%d.conv.weight" % l), dst, hi, lo, g.Cout, g.Cin, g.k,
                          g.s, g.taps, g.s * g.Cin * g.taps * g.Cout))
     if jobs:
         plan.w_batch(1, jobs)
@@ -474,9 +596,9 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
     call("pase_colsum", plan.g, emb, rows, emb, sb[plan.bs_bw:plan.bs_bw + emb])
     plan.tn("g", plan.g, emb, rows, 0, True, "cat", plan.cat, Kc, rows, False, plan.dWcat, Kc,
             emb, Kc, 1, rows, 1.0, 0)
-    call("pase_transpose_pad", plan.Wcat.reshape(-1), Kc, plan.WcatT, emb, emb, Kc)
+    call("pase_transpose_pad", plan.Wcat, Kc, plan.WcatT, emb, emb, Kc)
     plan.nt("g", plan.g, emb, False, "WcatT", plan.WcatT, emb, True, plan.dcat, Kc, rows, Kc,
-            emb, 1.0, None, rows, rows, rows, 1, None, None, 0)
+            emb, 1.0, None, rows, rows, rows, 1, None, None, 0, akind="grad")
     dWcat = plan.dWcat.view(emb, Kc)
     first = plan.H if plan.rnn else plan.Clast
     # gradients handed to autograd must not alias plan-owned buffers (the next backward
@@ -498,9 +620,9 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
                 plan.dWq, 2 * Cq, 3 * H, 2 * Cq, N, Tq, 1.0, 0)
         dWq = plan.dWq.view(3 * H, 2 * Cq)
         grads["rnn.layers.0.linear.weight"] = torch.cat([dWq[:, Cq:], dWq[:, :Cq]], 1)
-        call("pase_transpose_pad", plan.Wq.reshape(-1), 2 * Cq, plan.WqT, 3 * H, 3 * H, 2 * Cq)
+        call("pase_transpose_pad", plan.Wq, 2 * Cq, plan.WqT, 3 * H, 3 * H, 2 * Cq)
         plan.nt("dYg", plan.dYg, 3 * H, False, "WqT", plan.WqT, 3 * H, True, plan.dsrc, 2 * Cq,
-                rows, 2 * Cq, 3 * H, 1.0, None, rows, rows, rows, 1, None, None, 0)
+                rows, 2 * Cq, 3 * H, 1.0, None, rows, rows, rows, 1, None, None, 0, akind="grad")
         last_src = dict(A=plan.dsrc[Cq:], a_ss=Tq * 2 * Cq, a_rs=2 * Cq,
                         B=plan.dsrc, b_ss=Tq * 2 * Cq, b_rs=2 * Cq, b_shift=1)
     else:
@@ -513,36 +635,37 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
         mean, invstd, scale, shift = plan.bn[l][0], plan.bn[l][1], plan.bn[l][2], plan.bn[l][3]
         if l == plan.nblk - 1:
             s = dict(last_src)
-            s.update(padL=0, padR=0)
+            s.update(padL=0, padR=0, a_bf16=0)          # dsrc / dcat are fp32 in every mode
         else:
             nx = G[l + 1]
             s = dict(A=plan.dxpad[l + 1], a_ss=nx.apad_floats, a_rs=C, padL=nx.padL,
-                     padR=nx.padR, B=None, b_ss=0, b_rs=0, b_shift=0)
+                     padR=nx.padR, B=None, b_ss=0, b_rs=0, b_shift=0, a_bf16=ybf)
         if plan.skips and l + 1 < plan.nblk:
             pool, pd = plan.dcat[plan.col_off[l]:], plan.pool_d[l]
         else:
             pool, pd = None, 0
-        if g.sinc:
-            dst, d_ss = plan.dyz[l], g.Ty * C
-        else:
-            dst, d_ss = plan.dyz[l][(g.taps - 1) * C:], g.Pd * C
+        doff = 0 if g.sinc else (g.taps - 1) * C
+        d_ss = g.Ty * C if g.sinc else g.Pd * C
+        dst = plan.dyz[l][doff:]
+        dst_lo = None if plan.dyz_lo[l] is None else plan.dyz_lo[l][doff:]
+        # du: in place in the dy buffer (same type as y), except 3xF16 (fp32 scratch)
+        du = plan.du_scratch[doff:] if plan.mode == 3 else dst
+        amax = None if plan.amax is None else plan.amax[2 * l:2 * l + 2]
         o = plan.bs_off[l]
         S1, S2, dal, dbi = sb[o:o + C], sb[o + C:o + 2 * C], sb[o + 2 * C:o + 3 * C], \
             sb[o + 3 * C:o + 4 * C]
-        call("pase_bn_prelu_bwd_reduce", plan.y[l], g.Ty * C, N, g.T_out, C, mean, invstd,
+        call("pase_bn_prelu_bwd_reduce", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
              scale, shift, P(pre + "act.weight"),
-             s["A"], s["a_ss"], s["a_rs"], s["padL"], s["padR"],
+             s["A"], s["a_bf16"], s["a_ss"], s["a_rs"], s["padL"], s["padR"],
              s["B"], s["b_ss"], s["b_rs"], s["b_shift"],
-             pool, Tq * Kc, Kc, pd, Tq, dst, d_ss, S1, S2, dal)
+             pool, Tq * Kc, Kc, pd, Tq, du, d_ss, S1, S2, dal, amax)
         if training:
             a1, a2 = S1, S2
         else:
             a1, a2 = zeros[:C], zeros[C:2 * C]
-        lo = plan.lo_of(("dyz", l), plan.dyz[l])
-        dst_lo = None if lo is None else (lo if g.sinc else lo[(g.taps - 1) * C:])
-        call("pase_bn_prelu_bwd_apply", plan.y[l], g.Ty * C, N, g.T_out, C, mean, invstd,
-             P(pre + "norm.weight"), a1, a2, float(N * g.T_out), dst, d_ss,
-             None if g.sinc else dbi, dst_lo)
+        call("pase_bn_prelu_bwd_apply", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
+             P(pre + "norm.weight"), a1, a2, float(N * g.T_out), du, dst, dst_lo, fmt, d_ss,
+             None if g.sinc else dbi, amax, plan.gscale[l])
         if g.sinc:
             plan.tn(("dyz", l), plan.dyz[l], g.Nn, g.rows_out, 0, False, ("apad", l), plan.apad[l],
                     g.lda, g.P, False, plan.dWt[l], g.K, g.Nn, g.K, N, g.rows_out, 1.0, 0)
@@ -559,7 +682,7 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
             if l > 0:
                 plan.nt(("dyz", l), plan.dyz[l], C, False, ("Wd", l), plan.Wd[l], g.taps * C, False,
                         plan.dxpad[l], g.s * g.Cin, N * g.Pd, g.s * g.Cin, g.taps * C, 1.0, None,
-                        g.Pd, g.P, g.P, 1, None, None, 0)
+                        g.Pd, g.P, g.P, 1, None, None, 0, akind="grad")
 
     # conv weight gradients: GEMM layout -> parameter layout for every block in one launch,
     # into one per-call buffer (the gradients handed to autograd are views of it)

@@ -140,7 +140,8 @@ class WaveFe(Model):
         if cfg["norm_out"]:
             self.norm_out = nn.BatchNorm1d(emb, affine=False)
         self._plans = OrderedDict()
-        # GEMM numerics: "fp32" (FFMA), "3xtf32" (tcgen05, fp32-equivalent), "tf32" (tcgen05)
+        # GEMM numerics (encoder.PRECISIONS): "fp32" (FFMA), "3xtf32" / "3xf16" (tcgen05,
+        # fp32-equivalent), "tf32" (tcgen05), "bf16" (tcgen05, bf16 operands and activations)
         self.precision = os.environ.get("PASE_B200_PRECISION", DEFAULT_PRECISION)
         self._sinc_n = self._sinc_win = None
         self.last_output_ntc = None
@@ -212,7 +213,9 @@ class WaveFe(Model):
 
     def forward(self, batch, device=None, mode=None):
         if device is None:
-            device = next(super().parameters()).device
+            # Model.parameters() only yields trainable parameters: a frozen encoder (a fixed
+            # feature extractor downstream) must still resolve its device
+            device = self.W.weight.device
         x, data_fmt = format_frontend_chunk(batch, device)
         if not x.is_cuda:
             x = x.to(device)

@@ -68,7 +68,7 @@ def gemm_nt(A, lda, a_used, B, ldb, b_used, C, ldc, M, N, K, bias, rows_in=None,
     Ah, Al = _split_act(A, a_used, mode)
     Bh, Bl = _split_w(B, b_used, mode)
     return ops.call("pase_tc_gemm_nt", Ah, Al, a_used // lda, lda, Bh, Bl, ldb, C, ldc, M, N, K,
-                    1.0, bias, rows_in, t_valid, rows_out, 1, None, None, 0, mode)
+                    1.0, None, bias, rows_in, t_valid, rows_out, 1, None, None, 0, mode, 0)
 
 
 def gemm_tn(A, lda, a_used, B, ldb, b_used, C, ldc, I, J, rows, groups=1, pitchA=None, offA=0,
@@ -83,7 +83,7 @@ def gemm_tn(A, lda, a_used, B, ldb, b_used, C, ldc, I, J, rows, groups=1, pitchA
     Ah, Al = _split_act(A, a_used, mode)
     Bh, Bl = _split_act(B, b_used, mode)
     return ops.call("pase_tc_gemm_tn", Ah, Al, lda, pitchA, offA, Bh, Bl, ldb, pitchB,
-                    b_used // ldb, C, ldc, I, J, groups, rows, 1.0, 0, mode)
+                    b_used // ldb, C, ldc, I, J, groups, rows, 1.0, None, 0, mode)
 
 
 def _rows_ld(x):

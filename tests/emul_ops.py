@@ -139,11 +139,61 @@ def pase_sinc_grad(dWp, low_hz, band_hz, n_, win, dlow, dband, C, k, fold, Kv, m
     dband[:C] = gb
 
 
-def pase_reflect_pad_wave(x, dst, N, T, padL, padR, pitch):
+F16_LO_MUL = 2048.0        # lo' = rn_f16((x - hi) * 2^11)
+
+
+def _store_fmt(val, dst, dst_lo, fmt, size, stride):
+    """Write fp32 `val` (shape `size`) into the strided view of dst in storage format `fmt`
+    (0 fp32 [+ tf32 residual], 1 bf16, 2 fp16 pair); returns the value a reader sees."""
+    if fmt == 0:
+        _as(dst, size, stride).copy_(val)
+        if dst_lo is not None:
+            _as(dst_lo, size, stride).copy_(_residual(val.contiguous()))
+        return val
+    if fmt == 1:
+        assert dst.dtype == torch.bfloat16
+        _as(dst, size, stride).copy_(val.to(torch.bfloat16))
+        return val.to(torch.bfloat16).float()
+    assert dst.dtype == torch.float16 and dst_lo.dtype == torch.float16
+    hi = val.to(torch.float16)
+    _as(dst, size, stride).copy_(hi)
+    _as(dst_lo, size, stride).copy_(((val - hi.float()) * F16_LO_MUL).to(torch.float16))
+    return val
+
+
+def f16_grad_scale(bound):
+    """power of two s with bound * s <= 2^14 (common.cuh::f16_grad_scale)."""
+    bound = float(bound)
+    if not (bound > 0.0) or not (bound < 3.0e38):
+        return 1.0
+    _, e = math.frexp(bound)
+    k = max(-100, min(100, 14 - e))
+    return math.ldexp(1.0, k)
+
+
+def pase_reflect_pad_wave(x, dst, dst_lo, dst_fmt, N, T, padL, padR, pitch):
     Tp = T + padL + padR
     src = x[:N * T].view(N, T)
     idx = _reflect(torch.arange(Tp) - padL, T)
-    _as(dst, (N, Tp), (pitch, 1)).copy_(src[:, idx])
+    _store_fmt(src[:, idx], dst, dst_lo, dst_fmt, (N, Tp), (pitch, 1))
+
+
+def pase_cast_bf16(x, dst, n):
+    dst[:n] = x[:n].to(torch.bfloat16)
+
+
+def pase_absmax(x, n, amax):
+    amax[0] = max(float(amax[0]), float(x[:n].abs().max()))
+
+
+def pase_split_f16(x, hi, lo, n, amax, scale_out):
+    s = f16_grad_scale(float(amax[0]) * 1.0001) if amax is not None else 1.0
+    if scale_out is not None:
+        scale_out[0], scale_out[1] = 1.0 / s, s
+    v = x[:n] * s
+    h = v.to(torch.float16)
+    hi[:n] = h
+    lo[:n] = ((v - h.float()) * F16_LO_MUL).to(torch.float16)
 
 
 def pase_bn_finalize(colsum, colsumsq, C, fold, count, gamma, beta, rm, rv, momentum, eps,
@@ -183,29 +233,30 @@ def _residual(a):
     return _tf32_rn(a - _tf32_trunc(a))
 
 
-def pase_bn_prelu_pad_fwd(y, y_ss, N, T, C, scale, shift, alpha, dst, d_ss, d_rs, padL, padR,
-                          pool, p_ss, p_rs, pool_d, pool_T, dst_lo=None):
-    yv = _as(y, (N, T, C), (y_ss, C, 1))
+def pase_bn_prelu_pad_fwd(y, y_bf16, y_ss, N, T, C, scale, shift, alpha, dst, dst_lo, dst_fmt,
+                          d_ss, d_rs, padL, padR, pool, p_ss, p_rs, pool_d, pool_T):
+    assert (y.dtype == torch.bfloat16) == bool(y_bf16)
+    yv = _as(y, (N, T, C), (y_ss, C, 1)).float()
     a = _prelu(yv * scale[:C] + shift[:C], alpha[:C])
     Tp = T + padL + padR
     idx = _reflect(torch.arange(Tp) - padL, T)
-    _as(dst, (N, Tp, C), (d_ss, d_rs, 1)).copy_(a[:, idx])
-    if dst_lo is not None:
-        _as(dst_lo, (N, Tp, C), (d_ss, d_rs, 1)).copy_(_residual(a[:, idx].contiguous()))
+    seen = _store_fmt(a[:, idx], dst, dst_lo, dst_fmt, (N, Tp, C), (d_ss, d_rs, 1))
     if pool is not None and pool_d > 0:
         L = pool_T * pool_d
         pv = _as(pool, (N, pool_T, C), (p_ss, p_rs, 1))
-        pv += a[:, :L].reshape(N, pool_T, pool_d, C).mean(2)
+        pv += seen[:, padL:padL + L].reshape(N, pool_T, pool_d, C).mean(2)
 
 
-def pase_bn_prelu_bwd_reduce(y, y_ss, N, T, C, mean, invstd, scale, shift, alpha,
-                             srcA, a_ss, a_rs, padL, padR, srcB, b_ss, b_rs, b_shift,
-                             pool, p_ss, p_rs, pool_d, pool_T, dst, d_ss, S1, S2, dalpha):
-    yv = _as(y, (N, T, C), (y_ss, C, 1))
+def pase_bn_prelu_bwd_reduce(y, y_bf16, y_ss, N, T, C, mean, invstd, scale, shift, alpha,
+                             srcA, a_bf16, a_ss, a_rs, padL, padR, srcB, b_ss, b_rs, b_shift,
+                             pool, p_ss, p_rs, pool_d, pool_T, dst, d_ss, S1, S2, dalpha, amax):
+    assert (y.dtype == torch.bfloat16) == bool(y_bf16) and dst.dtype == y.dtype
+    yv = _as(y, (N, T, C), (y_ss, C, 1)).float()
     g = torch.zeros(N, T, C)
     if srcA is not None:
+        assert (srcA.dtype == torch.bfloat16) == bool(a_bf16)
         Tp = T + padL + padR
-        av = _as(srcA, (N, Tp, C), (a_ss, a_rs, 1))
+        av = _as(srcA, (N, Tp, C), (a_ss, a_rs, 1)).float()
         idx = _reflect(torch.arange(Tp) - padL, T)
         g.index_add_(1, idx, av.contiguous())
     if srcB is not None:
@@ -225,20 +276,28 @@ def pase_bn_prelu_bwd_reduce(y, y_ss, N, T, C, mean, invstd, scale, shift, alpha
     S1[:C] += du.double().sum((0, 1))
     S2[:C] += (du * xh).double().sum((0, 1))
     dalpha[:C] += torch.where(pos, torch.zeros_like(g), u * g).double().sum((0, 1))
-    _as(dst, (N, T, C), (d_ss, C, 1)).copy_(du)
+    if amax is not None:
+        amax[0] = max(float(amax[0]), float(du.abs().max()))
+        amax[1] = max(float(amax[1]), float(xh.abs().max()))
+    _as(dst, (N, T, C), (d_ss, C, 1)).copy_(du.to(dst.dtype))
 
 
-def pase_bn_prelu_bwd_apply(y, y_ss, N, T, C, mean, invstd, gamma, S1, S2, count, dst, d_ss,
-                            dbias, dst_lo=None):
-    yv = _as(y, (N, T, C), (y_ss, C, 1))
-    dv = _as(dst, (N, T, C), (d_ss, C, 1))
+def pase_bn_prelu_bwd_apply(y, y_bf16, y_ss, N, T, C, mean, invstd, gamma, S1, S2, count, du,
+                            dst, dst_lo, dst_fmt, d_ss, dbias, amax, scale_out):
+    assert (y.dtype == torch.bfloat16) == bool(y_bf16) and du.dtype == y.dtype
+    yv = _as(y, (N, T, C), (y_ss, C, 1)).float()
+    dv = _as(du, (N, T, C), (d_ss, C, 1)).float()
     xh = (yv - mean[:C]) * invstd[:C]
     gi = (gamma[:C] if gamma is not None else 1.0) * invstd[:C]
     m1, m2 = (S1[:C] / count).float(), (S2[:C] / count).float()
     out = gi * (dv - m1 - xh * m2)
-    dv.copy_(out)
-    if dst_lo is not None:
-        _as(dst_lo, (N, T, C), (d_ss, C, 1)).copy_(_residual(out.contiguous()))
+    s = 1.0
+    if dst_fmt == 2:
+        gia = gi.abs() if isinstance(gi, torch.Tensor) else torch.full((C,), abs(gi))
+        bound = float((gia * (float(amax[0]) + m1.abs() + float(amax[1]) * m2.abs())).max())
+        s = f16_grad_scale(bound * 1.0001)
+        scale_out[0], scale_out[1] = 1.0 / s, s
+    _store_fmt(out * s, dst, dst_lo, dst_fmt, (N, T, C), (d_ss, C, 1))
     if dbias is not None:
         dbias[:C] += out.double().sum((0, 1))
 
@@ -391,17 +450,21 @@ def pase_scale_dev(x, n, dev_scalar, host_coef):
     x[:n] *= (float(dev_scalar[0]) if dev_scalar is not None else 1.0) * host_coef
 
 
-def _host_view(ptr, n):
-    """Float32 view of n elements at a HOST address (the emulation's stand-in for a device
-    pointer stored in a job table); shares memory with the tensor that owns the address."""
+def _host_view(ptr, n, dtype=torch.float32):
+    """View of n elements at a HOST address (the emulation's stand-in for a device pointer
+    stored in a job table); shares memory with the tensor that owns the address."""
     import ctypes
     import numpy as np
-    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr)))
+    if dtype == torch.float32:
+        return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr)))
+    raw = torch.from_numpy(np.ctypeslib.as_array((ctypes.c_int16 * n).from_address(ptr)))
+    return raw.view(dtype)
 
 
-def pase_conv_w_batch(table, njobs, total, op, dst_base):
+def pase_conv_w_batch(table, njobs, total, op, dst_base, fmt=0):
     """ops 3..5: same results as 0..2 (shared-memory tiled kernels; `total` = thread blocks,
-    table[.., 11] = first block of the job)."""
+    table[.., 11] = first block of the job).  fmt: what hi/lo receive (0 tf32 split, 1 bf16,
+    2 fp16 pair); dst may be 0."""
     t = table.reshape(njobs, 12).tolist()
     tiled, op = op >= 3, op % 3
     done = blocks = 0
@@ -415,13 +478,19 @@ def pase_conv_w_batch(table, njobs, total, op, dst_base):
             out = dst_base[dst:dst + count]
             pase_conv_w_from_fwd(_host_view(src, n_w), out, Cout, Cin, k)
         else:
-            out = _host_view(dst, count)
+            out = _host_view(dst, count) if dst else torch.zeros(count)
             if op == 0:
                 pase_conv_w_to_fwd(_host_view(src, n_w), out, Cout, Cin, k)
             else:
                 pase_conv_w_to_dgrad(_host_view(src, n_w), out, Cout, Cin, k, sd, taps)
         if hi:
-            pase_split_tf32(out, _host_view(hi, count), _host_view(lo, count), count)
+            if fmt == 0:
+                pase_split_tf32(out, _host_view(hi, count), _host_view(lo, count), count)
+            elif fmt == 1:
+                _host_view(hi, count, torch.bfloat16).copy_(out.to(torch.bfloat16))
+            else:
+                pase_split_f16(out, _host_view(hi, count, torch.float16),
+                               _host_view(lo, count, torch.float16), count, None, None)
         done += count
     assert (blocks if tiled else done) == total
 
@@ -471,34 +540,51 @@ def _like(lo, hi):
     return out
 
 
-def pase_tc_gemm_nt(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, C, ldc, M, N, K, alpha, bias, rows_in,
-                    t_valid, rows_out, fold, colsum, colsumsq, accumulate, mode):
+def _operand(hi, lo, mode, n=None):
+    """fp32 value of a GEMM operand as the tensor core sees it in `mode`."""
+    hi = hi if n is None else hi[:n]
+    if mode <= 1:
+        v = _tf32_trunc(hi)
+        if mode == 1:
+            v = v + _tf32_trunc(lo if n is None else lo[:n])
+        return v
+    if mode == 2:
+        assert hi.dtype == torch.bfloat16
+        return hi.float()
+    assert hi.dtype == torch.float16 and lo.dtype == torch.float16
+    return hi.float() + (lo if n is None else lo[:n]).float() / F16_LO_MUL
+
+
+def pase_tc_gemm_nt(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, C, ldc, M, N, K, alpha, alpha_dev, bias,
+                    rows_in, t_valid, rows_out, fold, colsum, colsumsq, accumulate, mode, c_bf16):
     Alo, Blo = _like(Alo, Ahi), _like(Blo, Bhi)
     need = M * R + K
     A = torch.zeros(need)
     lim = min(a_rows * R, Ahi.numel(), need)         # TMA zero-fills rows >= a_rows
-    # the tensor core reads only the upper 19 bits of each fp32 operand (truncation)
-    A[:lim] = _tf32_trunc(Ahi[:lim])
-    if mode == 1:
-        A[:lim] += _tf32_trunc(Alo[:lim])
-    B = _tf32_trunc(Bhi[:N * ldb])
-    if mode == 1:
-        B += _tf32_trunc(Blo[:N * ldb])
+    A[:lim] = _operand(Ahi, Alo, mode, lim)
+    B = _operand(Bhi, Blo, mode, N * ldb)
+    if alpha_dev is not None:
+        alpha = alpha * float(alpha_dev[0])
+    if c_bf16:
+        assert C.dtype == torch.bfloat16 and not accumulate
+        Cf = C.float()
+        pase_gemm_nt(A, R, B, ldb, Cf, ldc, M, N, K, alpha, bias, rows_in, t_valid, rows_out,
+                     fold, colsum, colsumsq, 0)
+        C.copy_(Cf.to(torch.bfloat16))
+        return
     pase_gemm_nt(A, R, B, ldb, C, ldc, M, N, K, alpha, bias, rows_in, t_valid, rows_out, fold,
                  colsum, colsumsq, accumulate)
 
 
 def pase_tc_gemm_tn(Ahi, Alo, lda, pitchA, offA, Bhi, Blo, R, pitchB, b_rows_total, C, ldc, I, J,
-                    groups, rows_per_group, alpha, accumulate, mode):
+                    groups, rows_per_group, alpha, alpha_dev, accumulate, mode):
     Alo, Blo = _like(Alo, Ahi), _like(Blo, Bhi)
-    A = _tf32_trunc(Ahi)
-    if mode == 1:
-        A = A + _tf32_trunc(Alo)
+    A = _operand(Ahi, Alo, mode)
     needB = ((groups - 1) * pitchB + rows_per_group) * R + J
     B = torch.zeros(max(needB, Bhi.numel()))
     lim = min(b_rows_total * R, Bhi.numel())
-    B[:lim] = _tf32_trunc(Bhi[:lim])
-    if mode == 1:
-        B[:lim] += _tf32_trunc(Blo[:lim])
+    B[:lim] = _operand(Bhi, Blo, mode, lim)
+    if alpha_dev is not None:
+        alpha = alpha * float(alpha_dev[0])
     pase_gemm_tn(A, lda, pitchA, offA, B, R, pitchB, 0, C, ldc, I, J, groups, rows_per_group,
                  alpha, accumulate)

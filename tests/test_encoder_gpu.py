@@ -31,11 +31,16 @@ def _native(cfg, seed, training, precision="fp32"):
     return m.cuda().train(training)
 
 
-# "fp32": FFMA kernels; "3xtf32": tcgen05 tensor cores with error-compensated TF32
-# (fp32-equivalent) -- both must meet the fp32 parity bar.
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+WIDE = [c for c in CASES if "mini" not in c]       # channel counts multiples of 64
+
+
+# "fp32": FFMA kernels; "3xtf32" / "3xf16": tcgen05 tensor cores with error-compensated
+# TF32 / fp16 products (fp32-equivalent) -- all three must meet the fp32 parity bar.
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16"])
 @pytest.mark.parametrize("name", CASES)
 def test_encoder_matches_reference_golden(name, precision):
+    if precision == "3xf16" and name not in WIDE:
+        pytest.skip("16-bit operand modes need channel counts that are multiples of 64")
     gold, meta = load_golden(name)
     cfg = resolve_cfg(meta["cfg"])
     model = _native(cfg, meta["seed"], meta["training"], precision)
@@ -106,7 +111,65 @@ def test_dict_batch_and_modes():
             assert_close(m(x, mode=mode), O.select_output(base.cpu(), mode), 1e-5, 1e-6, mode)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+def _oracle_fwd_bwd(cfg, seed, x, cot_seed):
+    """CPU oracle forward + backward of sum(y * cot): (y, {name: grad})."""
+    sd = fill_state_dict(WaveFe(**cfg).state_dict(), seed)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(leaves)
+    y_ref = O.encoder_forward(x, full, cfg, training=True)
+    cot = seeded_randn(tuple(y_ref.shape), cot_seed)
+    (y_ref * cot).sum().backward()
+    return y_ref.detach(), {k: v.grad for k, v in leaves.items()}, cot
+
+
+_ORACLE_CACHE = {}
+
+
+def _oracle_cached(cfg, seed, N, T):
+    key = (seed, N, T)
+    if key not in _ORACLE_CACHE:
+        x = seeded_randn((N, 1, T), seed + 1, 0.5)
+        _ORACLE_CACHE[key] = (x,) + _oracle_fwd_bwd(cfg, seed, x, seed + 2)
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("precision,N,T", [("3xtf32", 32, 32000), ("3xf16", 32, 32000),
+                                           ("3xf16", 8, 48000), ("3xtf32", 4, 48000)])
+def test_benchmark_shape_against_oracle(precision, N, T):
+    """The benchmark shapes themselves against the CPU oracle: BASELINE.json configs[1]
+    (B=32, T=32000) and the config[4] chunk length (T=48000), forward + backward.
+    Forward: the fp32 bar elementwise (rtol 1e-3 / atol 1e-5).  Gradients: relative L2 per
+    parameter < 2e-3 AND, elementwise, at most a PReLU-kink-sized fraction out of tolerance
+    (see DESIGN.md section 5 for the kink argument)."""
+    cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
+    seed = 31
+    x, y_ref, gref, cot = _oracle_cached(cfg, seed, N, T)
+    model = _native(cfg, seed, True, precision)
+    y = model(x.cuda())
+    assert tuple(y.shape) == (N, 256, T // 160)
+    assert_close(y, y_ref, RTOL, ATOL, "%s N=%d T=%d fwd" % (precision, N, T))
+    assert rel_l2(y.cpu(), y_ref) < 1e-4
+    (y * cot.cuda()).sum().backward()
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if k.endswith("conv.bias") or k == "W.bias":      # analytically zero under train BN
+            assert float(p.grad.abs().max()) <= 1e-3 * max(float(gref[k].abs().max()), 1.0) + 2e-3
+            continue
+        ref, got = gref[k], p.grad.cpu()
+        r = rel_l2(got, ref)
+        worst = max(worst, r)
+        assert r < 2e-3, "grad %s rel-L2 %.3e" % (k, r)
+        # elementwise: the entries outside (rtol 2e-3, atol 2e-4 max|g|) must be rare
+        tol = 2e-4 * float(ref.abs().max()) + 2e-3 * ref.abs()
+        frac = float(((got - ref).abs() > tol).float().mean())
+        assert frac < 0.02, "grad %s: %.2f%% of entries out of elementwise tolerance" % (
+            k, 100 * frac)
+    print("worst grad rel-L2 %s N=%d T=%d: %.3e" % (precision, N, T, worst))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16"])
 def test_full_length_against_oracle(precision):
     """T=32000 (the BASELINE.json chunk length), N=3 chunks, fwd + bwd vs the CPU oracle."""
     cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
@@ -156,6 +219,9 @@ def test_tf32_mode_is_l2_equivalent():
     model = _native(cfg, meta["seed"], True, "tf32")
     x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5).cuda()
     y = model(x)
+    # single-pass TF32 truncates both operands to 10 mantissa bits: through 10 GEMM layers
+    # the measured relative L2 is 1.1e-3..1.6e-3 on the goldens, i.e. at the north_star's
+    # "1e-3" clause but not reliably under it -- which is why 3xtf32 / 3xf16 are the default
     assert rel_l2(y.detach().cpu(), gold["y"]) < 2e-3
     cot = seeded_randn(tuple(y.shape), meta["seed"] + 2).cuda()
     (y * cot).sum().backward()
@@ -164,7 +230,89 @@ def test_tf32_mode_is_l2_equivalent():
     assert rel_l2(sample_view(g), gold["gsample/blocks.4.conv.weight"]) < 1e-1
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+def _emulated_bf16_reference(cfg, seed, training, x, cot):
+    """The SAME host orchestration with every kernel replaced by its torch spec
+    (tests/emul_ops.py) on CPU: a bf16-exact restatement (same rounding points, products of
+    the rounded operands accumulated in fp64)."""
+    import emul_ops
+    import pase_b200.ops as ops
+    from pase_b200 import encoder as enc
+    m = WaveFe(**cfg)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    m.precision = "bf16"
+    m.train(training)
+    real = ops.call
+    ops.call = emul_ops.call
+    try:
+        m._sinc_consts(x.device)
+        plan = m._plan(x.shape[0], x.shape[2], x.device)
+        named = list(m.named_parameters())
+        y, _ = enc._EncoderFn.apply(x, m, plan, training, tuple(n for n, _ in named),
+                                    *[p for _, p in named])
+        (y * cot).sum().backward()
+    finally:
+        ops.call = real
+    return y.detach(), {k: p.grad for k, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("name", ["enc_pasep_train_3200", "enc_pasep_train_4001",
+                                  "enc_pase_train_2400"])
+def test_bf16_mode(name):
+    """precision='bf16' (BASELINE.json configs[2]/[4]): bf16 operands, bf16 storage of y and
+    of the activation-sized gradients, fp32 accumulation / statistics / parameters.
+      (a) against the bf16-exact restatement of the same arithmetic (emulated kernels on
+          CPU): forward relative L2 <= 1e-3; the only differences are fp32
+          accumulation order and the rare bf16 roundings it flips;
+      (b) against the fp32 reference golden: forward relative L2 < 2e-2 -- the intrinsic
+          error of 8-bit mantissas through 10 layers (measured 1.2e-2..1.6e-2);
+      gradients: ReLU-type gates flip for ~1 % of the units at this perturbation level, so
+      gradients agree in relative L2 to ~1e-1 with fp32 (any bf16 implementation) and to a
+      few 1e-2 with the bf16 restatement."""
+    gold, meta = load_golden(name)
+    cfg = resolve_cfg(meta["cfg"])
+    x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5)
+    cot = seeded_randn(tuple(gold["y"].shape), meta["seed"] + 2)
+    y_em, g_em = _emulated_bf16_reference(cfg, meta["seed"], True, x, cot)
+    model = _native(cfg, meta["seed"], True, "bf16")
+    y = model(x.cuda())
+    assert rel_l2(y.detach().cpu(), y_em) < 1e-3, rel_l2(y.detach().cpu(), y_em)
+    assert rel_l2(y.detach().cpu(), gold["y"]) < 2e-2
+    (y * cot.cuda()).sum().backward()
+    for k, p in model.named_parameters():
+        if k.endswith("conv.bias") or k == "W.bias":
+            continue
+        r = rel_l2(p.grad.cpu(), g_em[k])
+        assert r < 5e-2, "grad %s vs bf16 restatement: rel-L2 %.3e" % (k, r)
+    sd = model.state_dict()
+    for key, val in gold.items():
+        if key.startswith("stat/") and "num_batches" not in key:
+            assert rel_l2(sd[key[5:]].float().cpu(), val.float()) < 3e-2, key
+
+
+@pytest.mark.parametrize("T", [32000, 48000])
+def test_bf16_benchmark_lengths(T):
+    """bf16 at the BASELINE chunk lengths (T=32000 config[2], T=48000 config[4]) against the
+    fp32 CPU oracle: forward relative L2 < 2e-2; gradient direction preserved
+    (cosine > 0.98 for every weight tensor)."""
+    cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
+    seed, N = 31, (32 if T == 32000 else 8)
+    if (seed, N, T) not in _ORACLE_CACHE and T == 48000:
+        N = 8
+    x, y_ref, gref, cot = _oracle_cached(cfg, seed, N, T)
+    model = _native(cfg, seed, True, "bf16")
+    y = model(x.cuda())
+    assert tuple(y.shape) == (N, 256, T // 160) and bool(torch.isfinite(y).all())
+    assert rel_l2(y.detach().cpu(), y_ref) < 2e-2
+    (y * cot.cuda()).sum().backward()
+    for k, p in model.named_parameters():
+        if k.endswith("conv.bias") or k == "W.bias":
+            continue
+        a, b = p.grad.cpu().double().reshape(-1), gref[k].double().reshape(-1)
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+        assert cos > 0.98, "grad %s cosine %.4f" % (k, cos)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xf16", "bf16"])
 def test_benchmark_shape_properties(precision):
     """B=32, T=32000 (BASELINE.json configs[1]): properties that do not need the oracle."""
     cfg = resolve_cfg("cfg/frontend/PASE+.cfg")
@@ -188,7 +336,9 @@ def test_benchmark_shape_properties(precision):
     g1 = torch.autograd.grad((y2 * c).sum(), model.W.weight, retain_graph=False)[0]
     y3 = model(x)
     g2 = torch.autograd.grad((y3 * (2 * c)).sum(), model.W.weight)[0]
-    assert rel_l2(g2, 2 * g1) < 1e-4
+    # exact up to atomics ordering; bf16 / fp16-pair storage rounds 2c's products at the same
+    # relative positions (powers of two commute with rounding), bf16 gets a wider margin
+    assert rel_l2(g2, 2 * g1) < (1e-4 if precision != "bf16" else 2e-3)
 
 
 def test_stale_plan_is_detected():

@@ -21,7 +21,7 @@ def run_both(name, args, rtol=1e-4, atol=1e-5, cmp_scale=None, skip=()):
         if not isinstance(c, torch.Tensor) or i in skip:
             continue
         d = d.cpu()
-        if c.dtype == torch.float64:
+        if c.dtype in (torch.float64, torch.bfloat16, torch.float16):
             c, d = c.float(), d.float()
         scale = max(float(c.abs().max()), 1.0) if cmp_scale is None else cmp_scale
         err = (c - d).abs()
@@ -107,7 +107,18 @@ def test_sinc_make_and_grad():
 
 def test_reflect_pad_and_bn_finalize():
     N, T = 3, 700
-    run_both("pase_reflect_pad_wave", [R(N * T, seed=13), torch.zeros(N * 960), N, T, 125, 125, 960])
+    run_both("pase_reflect_pad_wave", [R(N * T, seed=13), torch.zeros(N * 960), None, 0, N, T, 125,
+                                       125, 960])
+    # operand formats: tf32 residual twin, bf16, fp16 pair (bit-exact element-wise maps)
+    x = R(N * T, seed=13) * 3.0
+    for fmt, dt in ((0, torch.float32), (1, torch.bfloat16), (2, torch.float16)):
+        dst = torch.zeros(N * 960, dtype=dt)
+        lo = torch.zeros(N * 960, dtype=dt) if fmt != 1 else None
+        cpu, dev = run_both("pase_reflect_pad_wave", [x, dst, lo, fmt, N, T, 125, 125, 960],
+                            rtol=0, atol=0)
+        assert torch.equal(cpu[1], dev[1].cpu())
+        if lo is not None:
+            assert torch.equal(cpu[2], dev[2].cpu())
     C, fold = 48, 4
     cs = R(C * fold, seed=14).double() * 100
     cq = (R(C * fold, seed=15).double().abs() + 1.0) * 5000
@@ -130,16 +141,55 @@ def test_bn_prelu_pad_fwd(N, T, C, padL, padR, pool_d, with_lo):
     pool_T = T // pool_d if pool_d else 0
     pool = torch.zeros(N * max(pool_T, 1) * 200 + C) if pool_d else None
     cpu, dev = run_both("pase_bn_prelu_pad_fwd", [
-        y, (T + 3) * C, N, T, C, R(C, seed=21), R(C, seed=22), R(C, seed=23, scale=0.3), dst,
-        (Tp + 2) * d_rs, d_rs, padL, padR, pool, max(pool_T, 1) * 200, 200, pool_d, pool_T,
-        torch.zeros_like(dst) if with_lo else None], skip=(18,))
+        y, 0, (T + 3) * C, N, T, C, R(C, seed=21), R(C, seed=22), R(C, seed=23, scale=0.3), dst,
+        torch.zeros_like(dst) if with_lo else None, 0,
+        (Tp + 2) * d_rs, d_rs, padL, padR, pool, max(pool_T, 1) * 200, 200, pool_d, pool_T],
+        skip=(10,))
     if with_lo:
         # the residual is a discontinuous function of the last bits of dst, so it is checked
         # against the GPU's own dst: trunc_tf32(dst) + lo == dst to 2^-21
-        d, lo = dev[8].cpu(), dev[18].cpu()
+        d, lo = dev[9].cpu(), dev[10].cpu()
         rec = emul_ops._tf32_trunc(d) + lo
         assert float((rec - d).abs().max()) <= float(d.abs().max()) * 2.0 ** -21
         assert torch.equal(lo, emul_ops._residual(d))
+
+
+@pytest.mark.parametrize("y_bf16,fmt", [(1, 1), (0, 2), (1, 0), (0, 1)])
+@pytest.mark.parametrize("N,T,C,padL,padR,pool_d", [(2, 203, 64, 4, 5, 16), (2, 1001, 128, 5, 5, 8),
+                                                    (2, 50, 512, 9, 10, 2)])
+def test_bn_prelu_pad_fwd_16bit(N, T, C, padL, padR, pool_d, y_bf16, fmt):
+    """bf16 y and/or bf16 / fp16-pair operand output.  The stored value is a discontinuous
+    function of the fp32 result near rounding boundaries: the bf16 output is compared at one
+    bf16 ulp, the fp16 pair through the value it encodes (hi + lo/2^11) at fp32 accuracy."""
+    Tp = T + padL + padR
+    y = R(N * (T + 3) * C, seed=20)
+    if y_bf16:
+        y = y.to(torch.bfloat16)
+    d_rs = C + 8
+    dt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[fmt]
+    dst = torch.zeros(N * (Tp + 2) * d_rs, dtype=dt)
+    lo = torch.zeros_like(dst) if fmt == 2 else None
+    pool_T = T // pool_d
+    pool = torch.zeros(N * pool_T * 200 + C)
+    args = [y, y_bf16, (T + 3) * C, N, T, C, R(C, seed=21), R(C, seed=22),
+            R(C, seed=23, scale=0.3), dst, lo, fmt, (Tp + 2) * d_rs, d_rs, padL, padR, pool,
+            pool_T * 200, 200, pool_d, pool_T]
+    cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    emul_ops.call("pase_bn_prelu_pad_fwd", *cpu)
+    _lib.call("pase_bn_prelu_pad_fwd", *dev)
+    torch.cuda.synchronize()
+    if fmt == 2:
+        vc = cpu[9].float() + cpu[10].float() / 2048.0
+        vd = dev[9].cpu().float() + dev[10].cpu().float() / 2048.0
+        tol = 2e-6
+    else:
+        vc, vd = cpu[9].float(), dev[9].cpu().float()
+        tol = 2.0 ** -7 if fmt == 1 else 2e-6
+    err = (vc - vd).abs()
+    assert bool((err <= tol * vc.abs() + 1e-6).all()), float(err.max())
+    # pooled values: one differently-rounded bf16 element moves a window mean by ulp/pool_d
+    assert float((cpu[16] - dev[16].cpu()).abs().max()) <= (2e-2 if fmt == 1 else 2e-5)
 
 
 @pytest.mark.parametrize("N,T,C,padL,padR,pool_d,useB", [(2, 203, 64, 4, 5, 16, False),
@@ -156,14 +206,88 @@ def test_bn_prelu_bwd(N, T, C, padL, padR, pool_d, useB):
     pool = R(N * max(pool_T, 1) * C, seed=32) if pool_d else None
     dst = torch.zeros(N * T * C)
     S1, S2, dal = (torch.zeros(C, dtype=torch.float64) for _ in range(3))
+    amax = torch.zeros(2)
     cpu, dev = run_both("pase_bn_prelu_bwd_reduce", [
-        y, T * C, N, T, C, mean, invstd, scale, shift, alpha, srcA, Tp * C, C, padL, padR,
+        y, 0, T * C, N, T, C, mean, invstd, scale, shift, alpha, srcA, 0, Tp * C, C, padL, padR,
         srcB, T * 2 * C, 2 * C, 1, pool, max(pool_T, 1) * C, C, pool_d, pool_T, dst, T * C,
-        S1, S2, dal], rtol=2e-4, atol=2e-5)
-    du, s1, s2 = cpu[24], cpu[26], cpu[27]
-    run_both("pase_bn_prelu_bwd_apply", [y, T * C, N, T, C, mean, invstd, R(C, seed=33), s1, s2,
-                                         float(N * T), du, T * C, torch.zeros(C, dtype=torch.float64),
-                                         None], rtol=2e-4, atol=2e-5)
+        S1, S2, dal, amax], rtol=2e-4, atol=2e-5)
+    du, s1, s2, am = cpu[26], cpu[28], cpu[29], cpu[31]
+    assert float(am[0]) > 0 and float(am[1]) > 0
+    gamma = R(C, seed=33)
+    run_both("pase_bn_prelu_bwd_apply", [y, 0, T * C, N, T, C, mean, invstd, gamma, s1, s2,
+                                         float(N * T), du, du.clone(), None, 0, T * C,
+                                         torch.zeros(C, dtype=torch.float64), None, None],
+             rtol=2e-4, atol=2e-5)
+    # fp16-pair output: dy scaled by the power of two derived from the bound; the pair must
+    # encode s*dy at fp32 accuracy and stay far inside fp16's range
+    hi, lo = torch.zeros(N * T * C, dtype=torch.float16), torch.zeros(N * T * C, dtype=torch.float16)
+    sc = torch.zeros(2)
+    args = [y, 0, T * C, N, T, C, mean, invstd, gamma, s1, s2, float(N * T), du, hi, lo, 2, T * C,
+            torch.zeros(C, dtype=torch.float64), am, sc]
+    cpu2 = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    dev2 = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    emul_ops.call("pase_bn_prelu_bwd_apply", *cpu2)
+    _lib.call("pase_bn_prelu_bwd_apply", *dev2)
+    torch.cuda.synchronize()
+    assert torch.equal(cpu2[19], dev2[19].cpu()), (cpu2[19], dev2[19])
+    s = float(cpu2[19][1])
+    vc = cpu2[13].float() + cpu2[14].float() / 2048.0
+    vd = dev2[13].cpu().float() + dev2[14].cpu().float() / 2048.0
+    assert float(vd.abs().max()) <= 16384.0 and float(vd.abs().max()) >= 16384.0 / 64
+    assert float((vc - vd).abs().max()) <= 2e-5 * float(vc.abs().max())
+    ref = torch.zeros(N * T * C)
+    emul_ops.call("pase_bn_prelu_bwd_apply", y, 0, T * C, N, T, C, mean, invstd, gamma, s1, s2,
+                  float(N * T), du, ref, None, 0, T * C, None, None, None)
+    assert float((vd / s - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_bn_prelu_bwd_bf16():
+    """bf16 storage of y, the gradient source, du and dy (in place)."""
+    N, T, C, padL, padR, pool_d = 2, 203, 64, 4, 5, 16
+    Tp = T + padL + padR
+    y = R(N * T * C, seed=24).to(torch.bfloat16)
+    mean, invstd = R(C, seed=25, scale=0.1), R(C, seed=26).abs() + 0.5
+    scale, shift, alpha = R(C, seed=27), R(C, seed=28), R(C, seed=29, scale=0.3)
+    srcA = R(N * Tp * C, seed=30).to(torch.bfloat16)
+    pool_T = T // pool_d
+    pool = R(N * pool_T * C, seed=32)
+    dst = torch.zeros(N * T * C, dtype=torch.bfloat16)
+    S1, S2, dal = (torch.zeros(C, dtype=torch.float64) for _ in range(3))
+    cpu, dev = run_both("pase_bn_prelu_bwd_reduce", [
+        y, 1, T * C, N, T, C, mean, invstd, scale, shift, alpha, srcA, 1, Tp * C, C, padL, padR,
+        None, 0, 0, 0, pool, pool_T * C, C, pool_d, pool_T, dst, T * C, S1, S2, dal, None],
+        rtol=2.0 ** -7, atol=2e-5)
+    du, s1, s2 = cpu[26], cpu[28], cpu[29]
+    run_both("pase_bn_prelu_bwd_apply", [y, 1, T * C, N, T, C, mean, invstd, R(C, seed=33), s1, s2,
+                                         float(N * T), du, du.clone(), None, 1, T * C,
+                                         torch.zeros(C, dtype=torch.float64), None, None],
+             rtol=2.0 ** -7, atol=2e-5, skip=(12,))
+
+
+def test_cast_and_split_f16():
+    x = R(100003, seed=41) * 5.0
+    cpu, dev = run_both("pase_cast_bf16", [x, torch.zeros(100003, dtype=torch.bfloat16), 100003],
+                        rtol=0, atol=0)
+    assert torch.equal(cpu[1], dev[1].cpu())
+    hi, lo = torch.zeros(100003, dtype=torch.float16), torch.zeros(100003, dtype=torch.float16)
+    cpu, dev = run_both("pase_split_f16", [x, hi, lo, 100003, None, None], rtol=0, atol=0)
+    assert torch.equal(cpu[1], dev[1].cpu()) and torch.equal(cpu[2], dev[2].cpu())
+    v = cpu[1].float() + cpu[2].float() / 2048.0
+    assert float((v - x).abs().max()) <= float(x.abs().max()) * 2.0 ** -21
+    # scaled (gradient) form: tiny values are lifted into fp16's range by a power of two
+    g = R(50000, seed=42) * 3e-7
+    am = torch.zeros(2)
+    cpu, dev = run_both("pase_absmax", [g, 50000, am], rtol=0, atol=0)
+    assert float(cpu[2][0]) == float(g.abs().max())
+    sc = torch.zeros(2)
+    cpu, dev = run_both("pase_split_f16", [g, torch.zeros(50000, dtype=torch.float16),
+                                           torch.zeros(50000, dtype=torch.float16), 50000,
+                                           cpu[2], sc], rtol=0, atol=0)
+    assert torch.equal(cpu[1], dev[1].cpu()) and torch.equal(cpu[2], dev[2].cpu())
+    s = float(cpu[5][1])
+    v = (cpu[1].float() + cpu[2].float() / 2048.0) / s
+    assert 8192.0 <= float(g.abs().max()) * s <= 16384.0
+    assert float((v - g).abs().max()) <= float(g.abs().max()) * 2.0 ** -21
 
 
 def test_prelu_colsum_cast():
@@ -274,7 +398,7 @@ def test_conv_w_batch_matches_per_layer_ops(tiled):
             los.append(l if split else None)
             refs.append((ref, rh, rl))
         t, total, opc = table(rows, op)
-        _lib.call("pase_conv_w_batch", t, len(rows), total, opc, None)
+        _lib.call("pase_conv_w_batch", t, len(rows), total, opc, None, 0)
         torch.cuda.synchronize()
         for o, h, l, (ref, rh, rl) in zip(outs, his, los, refs):
             assert torch.equal(o, ref)
@@ -293,7 +417,7 @@ def test_conv_w_batch_matches_per_layer_ops(tiled):
         off += cnt
     t, total, opc = table(rows, 2)
     flat = torch.zeros(off, device=dev)
-    _lib.call("pase_conv_w_batch", t, len(rows), total, opc, flat)
+    _lib.call("pase_conv_w_batch", t, len(rows), total, opc, flat, 0)
     torch.cuda.synchronize()
     for o, cnt, ref in refs:
         assert torch.equal(flat[o:o + cnt], ref)

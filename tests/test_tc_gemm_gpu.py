@@ -1,5 +1,7 @@
-"""tcgen05 / TMA GEMM kernels against the exact fp32 spec.  mode 1 (3xTF32) must be
-fp32-equivalent; mode 0 (single TF32) is checked at TF32 tolerance."""
+"""tcgen05 / TMA GEMM kernels against the exact spec (the product of the operands as the
+tensor core reads them, accumulated in fp64).  Modes 1 (3xTF32) and 3 (3xF16) must be
+fp32-equivalent; mode 0 (TF32) and mode 2 (bf16) are exact products of rounded operands, so
+they too are checked tightly against the spec evaluated on the SAME rounded operands."""
 import pytest
 import torch
 
@@ -8,6 +10,19 @@ from pase_b200 import _lib
 from test_kernels_gpu import R
 
 pytestmark = pytest.mark.gpu
+
+
+def _operands(x, mode, weights=False, scale=None):
+    """(hi, lo) tensors of operand x in GEMM mode `mode` (CPU)."""
+    if mode == 0:
+        return x, None
+    if mode == 1:
+        return _split(x, weights)
+    if mode == 2:
+        return x.to(torch.bfloat16), None
+    v = x if scale is None else x * scale
+    hi = v.to(torch.float16)
+    return hi, ((v - hi.float()) * 2048.0).to(torch.float16)
 
 
 def _split(x, weights=False):
@@ -51,9 +66,12 @@ NT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 0, 3, 2])
 @pytest.mark.parametrize("M,N,K,Rr,rows_in,t_valid,rows_out,fold,bias,stats,acc", NT_CASES)
 def test_tc_gemm_nt(M, N, K, Rr, rows_in, t_valid, rows_out, fold, bias, stats, acc, mode):
+    if mode >= 2:
+        if Rr % 64 or (K * 2) % 16:
+            pytest.skip("16-bit modes need folded rows of 64 elements")
     a_rows = M + (K + Rr - 1) // Rr + 2
     A = R(a_rows * Rr, seed=11)
     B = R(N * K, seed=12, scale=0.1)
@@ -62,28 +80,68 @@ def test_tc_gemm_nt(M, N, K, Rr, rows_in, t_valid, rows_out, fold, bias, stats, 
     bs = R(N, seed=14) if bias else None
     cs = torch.zeros(N, dtype=torch.float64) if stats else None
     cq = torch.zeros(N, dtype=torch.float64) if stats else None
-    if mode == 1:
-        (Ah, Al), (Bh, Bl) = _split(A), _split(B, weights=True)
-    else:
-        Ah, Al, Bh, Bl = A, None, B, None
-    args = [Ah, Al, a_rows, Rr, Bh, Bl, K, C, N, M, N, K, 0.5, bs, rows_in, t_valid, rows_out,
-            fold, cs, cq, acc, mode]
+    (Ah, Al), (Bh, Bl) = _operands(A, mode), _operands(B, mode, weights=True)
+    args = [Ah, Al, a_rows, Rr, Bh, Bl, K, C, N, M, N, K, 0.5, None, bs, rows_in, t_valid,
+            rows_out, fold, cs, cq, acc, mode, 0]
     cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
     dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
     emul_ops.call("pase_tc_gemm_nt", *cpu)
     _lib.call("pase_tc_gemm_nt", *dev)
     torch.cuda.synchronize()
     scale = float((A.abs().mean() * B.abs().mean() * K ** 0.5))
-    tol = (2e-6 if mode == 1 else 2e-5) * max(scale, 1e-3) * 8
+    # split modes: fp32-equivalent; single-pass modes: exact products, fp32 accumulation in
+    # TMEM (round-toward-zero drift over K)
+    tol = (2e-6 if mode in (1, 3) else 2e-5) * max(scale, 1e-3) * 8
     out_c, out_d = cpu[7], dev[7].cpu()
     err = float((out_c - out_d).abs().max())
     assert err <= tol, "C max err %.3e > %.3e (mode %d)" % (err, tol, mode)
     if stats:
-        for i in (18, 19):
+        for i in (19, 20):
             c, d = cpu[i].float(), dev[i].cpu().float()
             e = float((c - d).abs().max())
-            lim = (2e-5 if mode == 1 else 2e-4) * max(float(c.abs().max()), 1.0)
+            lim = (2e-5 if mode in (1, 3) else 2e-4) * max(float(c.abs().max()), 1.0)
             assert e <= lim, "stats arg %d err %.3e > %.3e" % (i, e, lim)
+
+
+@pytest.mark.parametrize("mode", [2, 3, 1])
+@pytest.mark.parametrize("M,N,K,Rr,rows_in,t_valid,rows_out,fold", [
+    (1000, 64, 1280, 640, 103, 100, 100, 1),        # BN=64, 1-CTA
+    (700, 128, 704, 128, 70, 64, 64, 1),            # CTA pair
+    (520, 4096, 320, 64, 130, 8200, 129, 64),       # folded sinc (fold 64), wide N, stats
+    (300, 256, 5632, 1024, 300, 300, 300, 1),       # 256-wide tiles (mode 2) / pair (mode 3)
+])
+def test_tc_gemm_nt_bf16_out_and_alpha_dev(M, N, K, Rr, rows_in, t_valid, rows_out, fold, mode):
+    """bf16 output (C rounded once from the fp32 result) and the device-side alpha that
+    undoes a power-of-two operand scale (3xF16 gradients)."""
+    a_rows = M + (K + Rr - 1) // Rr + 2
+    A = R(a_rows * Rr, seed=31) * (1e-6 if mode == 3 else 1.0)     # tiny gradients
+    B = R(N * K, seed=32, scale=0.1)
+    groups = (M + rows_in - 1) // rows_in
+    s = 2.0 ** 32 if mode == 3 else 1.0
+    alpha_dev = torch.tensor([1.0 / s, s]) if mode == 3 else None
+    (Ah, Al), (Bh, Bl) = _operands(A, mode, scale=s), _operands(B, mode, weights=True)
+    cs, cq = torch.zeros(N, dtype=torch.float64), torch.zeros(N, dtype=torch.float64)
+    for c16 in ((1, 0) if mode != 1 else (1,)):
+        C = torch.zeros(groups * rows_out * N + 8, dtype=torch.bfloat16 if c16 else torch.float32)
+        args = [Ah, Al, a_rows, Rr, Bh, Bl, K, C, N, M, N, K, 1.0, alpha_dev, None, rows_in,
+                t_valid, rows_out, fold, cs.clone(), cq.clone(), 0, mode, c16]
+        cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+        dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+        emul_ops.call("pase_tc_gemm_nt", *cpu)
+        _lib.call("pase_tc_gemm_nt", *dev)
+        torch.cuda.synchronize()
+        out_c, out_d = cpu[7].float(), dev[7].cpu().float()
+        ref_scale = float(out_c.abs().max())
+        assert ref_scale > 0
+        err = (out_c - out_d).abs()
+        if c16:     # one bf16 ulp where the fp32 results straddle a rounding boundary
+            assert bool((err <= 2.0 ** -7 * out_c.abs() + 1e-5 * ref_scale).all()), float(err.max())
+            assert float((err > 1e-5 * ref_scale).float().mean()) < 0.02
+        else:
+            assert float(err.max()) <= (2e-5 if mode == 2 else 4e-6) * ref_scale
+        for i in (19, 20):      # statistics come from the fp32 values before rounding
+            c, d = cpu[i].float(), dev[i].cpu().float()
+            assert float((c - d).abs().max()) <= 2e-4 * max(float(c.abs().max()), 1e-30)
 
 
 TN_CASES = [
@@ -97,19 +155,18 @@ TN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 0, 3, 2])
 @pytest.mark.parametrize("I,J,groups,rpg,lda,pitchA,offA,Rr,pitchB,acc", TN_CASES)
 def test_tc_gemm_tn(I, J, groups, rpg, lda, pitchA, offA, Rr, pitchB, acc, mode):
-    A = R(groups * pitchA * lda + I + 64, seed=21)
+    if mode >= 2 and (Rr % 64 or J % 64 or lda % 8):
+        pytest.skip("16-bit modes need 128-byte rows (64 elements)")
+    A = R(groups * pitchA * lda + I + 128, seed=21)
     b_rows = groups * pitchB + (J + Rr - 1) // Rr + 2
     B = R(b_rows * Rr, seed=22)
     C = R(I * J, seed=23)
-    if mode == 1:
-        (Ah, Al), (Bh, Bl) = _split(A), _split(B)
-    else:
-        Ah, Al, Bh, Bl = A, None, B, None
+    (Ah, Al), (Bh, Bl) = _operands(A, mode), _operands(B, mode)
     args = [Ah, Al, lda, pitchA, offA, Bh, Bl, Rr, pitchB, b_rows, C, J, I, J, groups, rpg, 0.25,
-            acc, mode]
+            None, acc, mode]
     cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
     dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
     emul_ops.call("pase_tc_gemm_tn", *cpu)
@@ -117,6 +174,37 @@ def test_tc_gemm_tn(I, J, groups, rpg, lda, pitchA, offA, Rr, pitchB, acc, mode)
     torch.cuda.synchronize()
     out_c, out_d = cpu[10], dev[10].cpu()
     scale = float(out_c.abs().max())
-    tol = (4e-6 if mode == 1 else 4e-5) * max(scale, 1.0)
+    tol = (4e-6 if mode in (1, 3) else 4e-5) * max(scale, 1.0)
+    err = float((out_c - out_d).abs().max())
+    assert err <= tol, "C max err %.3e > %.3e (mode %d)" % (err, tol, mode)
+
+
+@pytest.mark.parametrize("I,J,groups,rpg,lda,pitchA,offA,Rr,pitchB", [
+    (4096, 320, 2, 131, 4096, 131, 0, 64, 140),      # folded sinc wgrad (fold 64)
+    (1536, 1024, 3, 40, 1536, 40, 0, 512, 41),       # QRNN gate weight gradient
+    (64, 128, 2, 300, 64, 302, 1, 64, 301),          # block-1 dgrad-side shape, J = BN
+])
+@pytest.mark.parametrize("mode", [2, 3])
+def test_tc_gemm_tn_16bit_shapes(I, J, groups, rpg, lda, pitchA, offA, Rr, pitchB, mode):
+    """16-bit-only shapes (64-element folded rows) + the device-side alpha of a scaled
+    gradient operand."""
+    A = R(groups * pitchA * lda + I + 128, seed=41) * (1e-7 if mode == 3 else 1.0)
+    b_rows = groups * pitchB + (J + Rr - 1) // Rr + 2
+    B = R(b_rows * Rr, seed=42)
+    C = torch.zeros(I * J)
+    s = 2.0 ** 36 if mode == 3 else 1.0
+    alpha_dev = torch.tensor([1.0 / s, s]) if mode == 3 else None
+    (Ah, Al), (Bh, Bl) = _operands(A, mode, scale=s), _operands(B, mode)
+    args = [Ah, Al, lda, pitchA, offA, Bh, Bl, Rr, pitchB, b_rows, C, J, I, J, groups, rpg, 1.0,
+            alpha_dev, 0, mode]
+    cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    emul_ops.call("pase_tc_gemm_tn", *cpu)
+    _lib.call("pase_tc_gemm_tn", *dev)
+    torch.cuda.synchronize()
+    out_c, out_d = cpu[10], dev[10].cpu()
+    scale = float(out_c.abs().max())
+    assert scale > 0
+    tol = (4e-6 if mode == 3 else 4e-5) * scale
     err = float((out_c - out_d).abs().max())
     assert err <= tol, "C max err %.3e > %.3e (mode %d)" % (err, tol, mode)
