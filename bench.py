@@ -39,13 +39,15 @@ FP32_FFMA_PEAK_TF = 74.4         # 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
 def gemm_traffic(precision):
-    """DRAM bytes per GEMM launch (dram__bytes_read+write) from the committed ncu --set full
-    capture of this kernel family (profiles/r01_gemm_traffic.json); None if not captured for
-    this precision."""
-    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if precision != "3xtf32" or not os.path.exists(path):
+    """Mean DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum over the
+    GEMM launches of one step) from the committed `ncu --set full` capture of the CURRENT
+    kernels in this precision (profiles/r02_gemm_traffic.json, written by
+    profiles/summarize.py traffic); None when this precision was not captured."""
+    path = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if not os.path.exists(path):
         return None
-    return json.load(open(path))["dram_bytes_per_launch"]
+    ent = json.load(open(path)).get(precision)
+    return None if ent is None else ent["dram_bytes_per_launch"]
 
 
 def load_peaks():
@@ -181,12 +183,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 4            # bounded sample of the B=32 workload: ~1 s of CPU work per step
-    r = time_cpu(batch, args.steps, min(args.warmup, 2), budget_s=150.0)
-    args.steps = r["steps"]          # fewer than asked only if the 150 s budget ran out
+    # the SAME configuration as the native arm: one step = the full B=32 batch (a few seconds
+    # of CPU work); the 200 s budget only cuts the number of timed steps on a slow host
+    batch = B_PER_GPU
+    r = time_cpu(batch, args.steps, min(args.warmup, 3), budget_s=200.0)
+    args.steps = r["steps"]          # fewer than asked only if the budget ran out
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 3),
         "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "PASE+.cfg encoder fwd+bwd+adam, T=32000, fp32, train-mode BN, "
@@ -194,9 +198,10 @@ def run_reference(args):
                    "global_batch": batch, "seq_len": T_CHUNK, "parallelism": "cpu-threads"},
         "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"],
                          "kind": "port",
-                         "sample": "%d chunks of 32000 samples per step (of the B=32 batch); "
+                         "sample": "the full B=%d batch of 32000-sample chunks per step; "
                                    "reference algorithm via oracle/pase_oracle.py (torch CPU "
-                                   "ops, QRNN as python scan: torchqrnn is un-vendored)" % batch},
+                                   "ops, QRNN as python scan: torchqrnn is un-vendored, parity "
+                                   "for that layer unpinned)" % batch},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -269,6 +274,109 @@ def run_workers(args):
                                              "triplets, T=32000" % B,
                                  "gemm_precision": args.precision, "params": nparam},
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
+
+# ------------------------------------------------------------------ extra legs ---
+def _event_time(fn, steps):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def measure_matmul_peaks(dev):
+    """Dense tensor-core peaks of THIS GPU as cuBLAS reaches them (torch.matmul, 8192^3, best
+    of 5 bursts of 10 back-to-back GEMMs): TF32 and fp16, next to the driver-measured bf16
+    figure of MEASURED_PEAKS.json.  Denominators for the issued-MMA fractions."""
+    out = {}
+    n = 8192
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, dt, tf32 in (("tf32", torch.float32, True), ("fp16", torch.float16, False),
+                               ("bf16", torch.bfloat16, False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn(n, n, device=dev, dtype=dt)
+            b = torch.randn(n, n, device=dev, dtype=dt)
+            for _ in range(3):
+                a @ b
+            best = min(_event_time(lambda: a @ b, 10) for _ in range(5))
+            out[name + "_tflops"] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+            del a, b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
+def library_baseline(dev, steps=5):
+    """SURVEY 8(d) / BASELINE.md 4.4: the reference's own module graph on this B200 through
+    the vendor libraries (cuDNN conv / batch-norm, cuBLAS), `cudnn.benchmark=True` as
+    train.py:26 sets it: the oracle restatement with lib_ops on CUDA tensors, fwd + bwd +
+    fused Adam on the same synthetic (32,1,32000) batch, once with TF32 allowed (PyTorch's
+    cuDNN default) and once strict fp32.  QRNN: python scan over 200 frames (torchqrnn's
+    runtime-compiled kernel is un-vendored)."""
+    import pase_oracle as O
+    from pase_b200.frontend import WaveFe
+    torch.manual_seed(0)
+    sd = {k: v.to(dev) for k, v in WaveFe(**PASE_PLUS).state_dict().items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(leaves)
+    opt = torch.optim.Adam(list(leaves.values()), lr=1e-4, fused=True)
+    x = torch.randn(B_PER_GPU, 1, T_CHUNK, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        y = O.encoder_forward(x, full, PASE_PLUS, training=True, new_stats={}, lib_ops=True)
+        y.square().mean().backward()
+        opt.step()
+    res = {}
+    prev = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
+            torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, allow in (("tf32_allowed", True), ("fp32_strict", False)):
+            torch.backends.cudnn.allow_tf32 = allow
+            torch.backends.cuda.matmul.allow_tf32 = allow
+            for _ in range(3):
+                step()
+            ms = _event_time(step, steps)
+            res[name] = {"ms_per_step": ms, "value": B_PER_GPU * T_CHUNK / (ms * 1e-3)}
+    finally:
+        (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
+         torch.backends.cuda.matmul.allow_tf32) = prev
+    res["what"] = ("oracle/pase_oracle.py encoder_forward(lib_ops=True) on CUDA: F.conv1d / "
+                   "F.batch_norm / F.prelu (cuDNN, cuBLAS), cudnn.benchmark=True, eager, fused "
+                   "Adam; B=32, T=32000")
+    res["peak_mem_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
+    return res
+
+
+def time_encoder_config(dev, stream, precision, B, T, steps=10):
+    """ms/step of the native encoder fwd+bwd+Adam at another (precision, B, T) operating
+    point, whole step replayed as one CUDA graph (inputs resident)."""
+    from pase_b200 import wf_builder
+    from pase_b200.graph import GraphedEncoderStep
+    torch.manual_seed(0)
+    model = wf_builder(dict(PASE_PLUS)).to(dev).train()
+    model.precision = precision
+    opt = torch.optim.Adam(list(model.parameters()), lr=1e-4, fused=True, capturable=True)
+    gs = GraphedEncoderStep(model, opt, lambda y: y.square().mean(), (B, 1, T), dev,
+                            stream=stream, resident=True,
+                            x_init=torch.randn(B, 1, T))
+    for _ in range(3):
+        gs.step()
+    ms = _event_time(gs.step, steps)
+    mem = sum(p.nbytes() for p in model._plans.values()) / 2 ** 30
+    del gs, opt, model
+    torch.cuda.empty_cache()
+    return {"precision": precision, "batch": B, "seq_len": T, "ms_per_step": ms,
+            "value": B * T / (ms * 1e-3), "unit": "samples/s", "plan_gb": mem}
 
 
 # ------------------------------------------------------------------ GPU arm ---
@@ -356,7 +464,7 @@ def run_native(args):
     step_resident()
     launches_per_step = ops.launch_count - n0
     value_fn, value_graphed = step_resident, False
-    gopt = None
+    gopt = gres = gs = None
     # N>1: two captured halves ([fwd, bwd, pack gradients] and [Adam]) with the NCCL
     # all-reduce of the flat gradient buffer issued eagerly between the two replays
     gkw = dict(post_backward=red.pack, between=red.all_reduce) if world > 1 else {}
@@ -503,6 +611,37 @@ def run_native(args):
                                "achieved_tflops": FLOP_PER_CHUNK * chunks / (step_ms * 1e-3) / 1e12},
             },
         }
+        if world == 1 and not args.no_extras:
+            # everything below is measured AFTER the timed regions of the headline numbers
+            gres = gs = None                # release the captured graphs' memory pools
+            torch.cuda.empty_cache()
+            pk = measure_matmul_peaks(dev)
+            line["peaks_measured_here"] = pk
+            issued = {"3xtf32": (3.0, "tf32_tflops"), "tf32": (1.0, "tf32_tflops"),
+                      "3xf16": (3.0, "fp16_tflops"), "bf16": (1.0, "bf16_tflops")}.get(args.precision)
+            if issued:
+                line["roofline"]["issued_mma_tflops"] = issued[0] * ach_tf
+                line["roofline"]["issued_mma_frac_of_pipe_peak"] = issued[0] * ach_tf / pk[issued[1]]
+                line["roofline"]["pipe_peak"] = "%s dense, torch.matmul 8192^3 on this GPU: %.0f " \
+                    "TFLOP/s" % (issued[1].split("_")[0], pk[issued[1]])
+            try:
+                line["library_baseline"] = library_baseline(dev)
+            except Exception as exc:                      # never lose the headline line
+                line["library_baseline"] = {"error": repr(exc)[:300]}
+            others = []
+            for (prec, B, T, tag) in (
+                    ("bf16", B_PER_GPU, T_CHUNK, "BASELINE configs[2] encoder part: bf16, B=32, T=32000"),
+                    ("bf16", 64, 48000, "BASELINE configs[4] shape: bf16, B=64/GPU, T=48000"),
+                    ("3xtf32", B_PER_GPU, T_CHUNK, "previous default numerics (round 1)")):
+                if prec == args.precision and B == B_PER_GPU and T == T_CHUNK:
+                    continue
+                try:
+                    r = time_encoder_config(dev, side, prec, B, T)
+                    r["config"] = tag
+                    others.append(r)
+                except Exception as exc:
+                    others.append({"config": tag, "error": repr(exc)[:300]})
+            line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu(4, 3, 1, budget_s=30.0)
             line["cpu_baseline"] = {
@@ -524,6 +663,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the legs measured after the headline: cuBLAS pipe peaks, the "
+                         "cuDNN library baseline, the other operating points")
     ap.add_argument("--no-graph", action="store_true", help="eager end-to-end step (no CUDA graph)")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "workers"],
                     help="encoder = the contract line (BASELINE configs[1]); workers = encoder + "

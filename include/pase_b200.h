@@ -269,6 +269,18 @@ int pase_time_mean_bwd(const float* dout, long ldo, float* dx, long ldx, int B, 
 int pase_axpy(const float* x, float* y, long n, float a, void* stream);
 int pase_scale_dev(float* x, long n, const float* dev_scalar, float host_coef, void* stream);
 
+/* ---- optimizer: the reference steps 13 torch.optim.Adam instances
+ * (trainer.py:86-143, worker_scheduler.py:66-73); here ONE launch updates every
+ * parameter of the flat fp32 buffers.  seg_table: device array of nseg rows of 6 x 8
+ * bytes {long start, long end, float lr, float beta1, float beta2, float eps,
+ * float weight_decay, float pad, long step_index}; segments are sorted, disjoint and
+ * start at multiples of 4 elements; steps: device float vector of step counts (already
+ * incremented for this update).  grad_scale multiplies the gradient (1/world of a
+ * summed all-reduce, or 1).  Semantics = torch.optim.Adam (amsgrad / maximize off). */
+int pase_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n,
+                   const long* seg_table, int nseg, const float* steps, float grad_scale,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

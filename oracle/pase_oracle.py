@@ -81,9 +81,10 @@ def frame_counts(cfg, T):
 def sinc_filters(low_hz_, band_hz_, k=251, sr=16000, min_low=50., min_band=50.):
     """(C,1),(C,1) -> (C,1,k) band-pass bank.  modules.py:868-918."""
     half = k // 2
-    n_lin = torch.linspace(0, (k / 2) - 1, steps=half)
+    dev = low_hz_.device
+    n_lin = torch.linspace(0, (k / 2) - 1, steps=half, device=dev)
     window = 0.54 - 0.46 * torch.cos(2 * math.pi * n_lin / k)
-    n_ = 2 * math.pi * torch.arange(-(k - 1) / 2.0, 0).view(1, -1) / sr
+    n_ = 2 * math.pi * torch.arange(-(k - 1) / 2.0, 0, device=dev).view(1, -1) / sr
     low = min_low + low_hz_.abs()
     high = torch.clamp(low + min_band + band_hz_.abs(), min_low, sr / 2)
     band = (high - low)[:, 0]
@@ -94,10 +95,20 @@ def sinc_filters(low_hz_, band_hz_, k=251, sr=16000, min_low=50., min_band=50.):
 
 
 def _bn(h, sd, prefix, training, affine=True, eps=1e-5, momentum=0.1,
-        new_stats=None):
-    """nn.BatchNorm1d over (N,C,T).  modules.py:79 / frontend.py:206-208."""
+        new_stats=None, lib_ops=False):
+    """nn.BatchNorm1d over (N,C,T).  modules.py:79 / frontend.py:206-208.
+    lib_ops: dispatch to F.batch_norm exactly as nn.BatchNorm1d does (the library call the
+    reference issues; used by bench.py's library-baseline leg on CUDA -> cuDNN)."""
     w = sd[prefix + "weight"] if affine else None
     b = sd[prefix + "bias"] if affine else None
+    if lib_ops:
+        rm = sd[prefix + "running_mean"].clone()
+        rv = sd[prefix + "running_var"].clone()
+        y = F.batch_norm(h, rm, rv, w, b, training, momentum, eps)
+        if training and new_stats is not None:
+            new_stats[prefix + "running_mean"], new_stats[prefix + "running_var"] = rm, rv
+            new_stats[prefix + "num_batches_tracked"] = sd[prefix + "num_batches_tracked"] + 1
+        return y
     if training:
         mean = h.mean(dim=(0, 2))
         var = h.var(dim=(0, 2), unbiased=False)
@@ -161,7 +172,7 @@ def select_output(h, mode=None):
 
 
 def encoder_forward(x, sd, cfg, training=True, new_stats=None,
-                    return_blocks=False):
+                    return_blocks=False, lib_ops=False):
     """WaveFe.forward on a (N,1,T) tensor -> (N,emb,T').  frontend.py:234-279;
     FeBlock modules.py:1058-1077.  ``sd`` uses the reference's state_dict keys;
     ``new_stats`` (dict) receives updated BN running buffers in training."""
@@ -188,8 +199,8 @@ def encoder_forward(x, sd, cfg, training=True, new_stats=None,
         if pl + pr > 0:
             h = F.pad(h, (pl, pr), mode="reflect")
         h = F.conv1d(h, w, b, stride=s)
-        h = _bn(h, sd, p + "norm.", training, new_stats=new_stats)
-        h = _prelu(h, sd[p + "act.weight"])
+        h = _bn(h, sd, p + "norm.", training, new_stats=new_stats, lib_ops=lib_ops)
+        h = F.prelu(h, sd[p + "act.weight"]) if lib_ops else _prelu(h, sd[p + "act.weight"])
         blocks.append(h)
         if cfg["denseskips"] and i + 1 < nblk:
             skips.append(F.conv1d(h, sd["denseskips.%d.weight" % i]))
@@ -200,7 +211,8 @@ def encoder_forward(x, sd, cfg, training=True, new_stats=None,
     for sk in skips:
         y = y + _pool_skip(sk, y.shape[2])
     if cfg["norm_out"]:
-        y = _bn(y, sd, "norm_out.", training, affine=False, new_stats=new_stats)
+        y = _bn(y, sd, "norm_out.", training, affine=False, new_stats=new_stats,
+                lib_ops=lib_ops)
     if return_blocks:
         return y, blocks
     return y
@@ -273,8 +285,8 @@ def gim_inputs(h, augment=False):
 def _pair_labels(y):
     """make_labels, cls_minions.py:47-51."""
     half = y.shape[0] // 2
-    return torch.cat([torch.ones(half, 1, y.shape[2]),
-                      torch.zeros(half, 1, y.shape[2])], 0)
+    return torch.cat([torch.ones(half, 1, y.shape[2], device=y.device),
+                      torch.zeros(half, 1, y.shape[2], device=y.device)], 0)
 
 
 _CRIT = {

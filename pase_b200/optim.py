@@ -1,0 +1,202 @@
+"""Flat-buffer Adam.
+
+The reference trains with one ``torch.optim.Adam`` per worker plus one for the frontend
+(pase/models/WorkerScheduler/trainer.py:86-143) and steps them one after the other
+(worker_scheduler.py:66-73): 13 x (zero_grad + multi-tensor step).  ``FlatAdam`` keeps every
+parameter, gradient and moment of ALL those groups in four flat fp32 buffers and updates them
+with ONE kernel launch (``pase_adam_flat``), with per-group learning rates / betas / eps /
+weight decay.  The gradient buffer is the same flat buffer the data-parallel all-reduce
+works on (``pase_b200.dp.FlatGradAllReducer``), so a step is: backward -> one NCCL
+all-reduce -> one Adam launch.
+
+Drop-in surface: ``param_groups`` (LR schedulers mutate ``group['lr']``), ``step()``,
+``zero_grad()``, ``state_dict()`` / ``load_state_dict()`` in torch.optim.Adam's own format
+(so ``Saver`` checkpoints interchange with the reference's), and ``views()``: one
+per-group facade with ``step()`` / ``zero_grad()`` / ``state_dict()`` for callers that hold a
+dict of optimizers like the reference's ``backprop_scheduler`` -- the facades' steps are
+deferred and the single launch happens when the last group has stepped.
+"""
+import torch
+
+from . import ops
+
+
+def _ru4(n):
+    return (n + 3) // 4 * 4
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 grad_buffer=None, grad_scale=1.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        plist = [p for g in self.param_groups for p in g["params"]]
+        if not plist:
+            raise ValueError("FlatAdam: no parameters")
+        dev = plist[0].device
+        if any(p.dtype != torch.float32 or p.device != dev for p in plist):
+            raise ValueError("FlatAdam: parameters must be fp32 on one device")
+        # segment = one param group; every parameter starts at a multiple of 4 elements
+        self._offsets, self._ranges, off = [], [], 0
+        for g in self.param_groups:
+            start = off
+            for p in g["params"]:
+                self._offsets.append(off)
+                off = _ru4(off + p.numel())
+            self._ranges.append((start, off))
+        self.n = off
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.flat_param = torch.zeros(self.n, **f32)
+        self.exp_avg = torch.zeros(self.n, **f32)
+        self.exp_avg_sq = torch.zeros(self.n, **f32)
+        if grad_buffer is not None and grad_buffer.numel() != self.n:
+            raise ValueError("FlatAdam: grad_buffer has %d elements, layout needs %d"
+                             % (grad_buffer.numel(), self.n))
+        self.flat_grad = grad_buffer if grad_buffer is not None else torch.zeros(self.n, **f32)
+        self.grad_scale = float(grad_scale)
+        self._plist = plist
+        self._pviews, self._gviews = [], []
+        for p, o in zip(plist, self._offsets):
+            pv = self.flat_param[o:o + p.numel()].view_as(p)
+            pv.copy_(p.data)
+            p.data = pv                                   # parameters become views
+            self._pviews.append(pv)
+            self._gviews.append(self.flat_grad[o:o + p.numel()].view_as(p))
+        self.steps = torch.zeros(len(self.param_groups), **f32)       # device step counts
+        self._table = None
+        self._table_key = None
+        self._pending = set()
+
+    # ---- gradient buffer protocol (shared with dp.FlatGradAllReducer) -----------------
+    def attach_grads(self):
+        for p, v in zip(self._plist, self._gviews):
+            p.grad = v
+
+    def pack_grads(self):
+        """Gradients autograd allocated outside the flat buffer are copied in (one
+        multi-tensor copy); parameters without a gradient contribute zeros."""
+        srcs, dsts = [], []
+        for p, v in zip(self._plist, self._gviews):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                srcs.append(p.grad)
+                dsts.append(v)
+        if srcs:
+            torch._foreach_copy_(dsts, srcs)
+        self.attach_grads()
+
+    def zero_grad(self, set_to_none=False):
+        """One memset of the flat gradient buffer; ``.grad`` stays a view of it."""
+        if set_to_none:
+            for p in self._plist:
+                p.grad = None
+        else:
+            self.flat_grad.zero_()
+            self.attach_grads()
+
+    # ---- the update ------------------------------------------------------------------
+    def _segments(self):
+        key = tuple((g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"])
+                    for g in self.param_groups)
+        if key != self._table_key:
+            import struct
+            raw = b"".join(
+                struct.pack("<qqffffffq", a, b, float(k[0]), float(k[1]), float(k[2]), float(k[3]),
+                            float(k[4]), 0.0, i)
+                for i, ((a, b), k) in enumerate(zip(self._ranges, key)))
+            t = torch.frombuffer(bytearray(raw), dtype=torch.int64).clone()
+            self._table = t.to(self.flat_param.device)
+            self._table_key = key
+        return self._table
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.pack_grads()
+        self.steps += 1.0
+        ops.call("pase_adam_flat", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
+                 self.n, self._segments(), len(self.param_groups), self.steps, self.grad_scale)
+        return loss
+
+    # ---- torch.optim.Adam-compatible persistence ----------------------------------------
+    def state_dict(self):
+        state, groups, idx = {}, [], 0
+        steps = self.steps.detach().cpu()
+        for gi, g in enumerate(self.param_groups):
+            ids = []
+            for p in g["params"]:
+                o = self._offsets[idx]
+                state[idx] = {"step": steps[gi].clone(),
+                              "exp_avg": self.exp_avg[o:o + p.numel()].view_as(p).clone(),
+                              "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view_as(p).clone()}
+                ids.append(idx)
+                idx += 1
+            gd = {k: v for k, v in g.items() if k != "params"}
+            gd.update(params=ids, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                      differentiable=False, fused=None)
+            groups.append(gd)
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        idx = 0
+        for gi, (g, sg) in enumerate(zip(self.param_groups, sd["param_groups"])):
+            for k in ("lr", "betas", "eps", "weight_decay"):
+                if k in sg:
+                    g[k] = tuple(sg[k]) if k == "betas" else sg[k]
+            step = None
+            for p in g["params"]:
+                st = sd["state"].get(idx, sd["state"].get(str(idx)))
+                if st is not None:
+                    o = self._offsets[idx]
+                    self.exp_avg[o:o + p.numel()].view_as(p).copy_(st["exp_avg"])
+                    self.exp_avg_sq[o:o + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+                    step = float(st["step"])
+                idx += 1
+            if step is not None:
+                self.steps[gi] = step
+        self._table_key = None
+
+    # ---- per-group facades for callers that hold a dict of optimizers -------------------
+    def views(self):
+        """One facade per param group, in order (e.g. frontend, then each worker)."""
+        return [_GroupView(self, i) for i in range(len(self.param_groups))]
+
+    def _view_step(self, gi):
+        self._pending.add(gi)
+        if len(self._pending) == len(self.param_groups):
+            self._pending.clear()
+            self.step()
+
+
+class _GroupView(object):
+    """What ``backprop_scheduler`` needs from an optimizer (worker_scheduler.py:43-75):
+    ``zero_grad()`` and ``step()``; plus ``param_groups`` for the LR schedulers and
+    ``state_dict`` for the per-worker ``Saver``.  ``step()`` is deferred: the one kernel launch
+    happens when the last group of the engine has stepped."""
+
+    def __init__(self, engine, gi):
+        self.engine, self.gi = engine, gi
+
+    @property
+    def param_groups(self):
+        return [self.engine.param_groups[self.gi]]
+
+    def zero_grad(self, set_to_none=False):
+        a, b = self.engine._ranges[self.gi]
+        self.engine.flat_grad[a:b].zero_()
+        self.engine.attach_grads()
+
+    def step(self, closure=None):
+        self.engine._view_step(self.gi)
+
+    def state_dict(self):
+        full = self.engine.state_dict()
+        ids = full["param_groups"][self.gi]["params"]
+        remap = {old: new for new, old in enumerate(ids)}
+        g = dict(full["param_groups"][self.gi])
+        g["params"] = list(range(len(ids)))
+        return {"state": {remap[i]: full["state"][i] for i in ids}, "param_groups": [g]}

@@ -588,3 +588,18 @@ def pase_tc_gemm_tn(Ahi, Alo, lda, pitchA, offA, Bhi, Blo, R, pitchB, b_rows_tot
         alpha = alpha * float(alpha_dev[0])
     pase_gemm_tn(A, lda, pitchA, offA, B, R, pitchB, 0, C, ldc, I, J, groups, rows_per_group,
                  alpha, accumulate)
+
+
+def pase_adam_flat(param, grad, exp_avg, exp_avg_sq, n, seg_table, nseg, steps, grad_scale):
+    """torch.optim.Adam (amsgrad / maximize off, L2 weight decay) per segment."""
+    import struct
+    raw = seg_table[:nseg * 6].numpy().tobytes()
+    for i in range(nseg):
+        a, b, lr, b1, b2, eps, wd, _, si = struct.unpack_from("<qqffffffq", raw, i * 48)
+        t = float(steps[si])
+        g = grad[a:b] * grad_scale + wd * param[a:b]
+        exp_avg[a:b] = b1 * exp_avg[a:b] + (1 - b1) * g
+        exp_avg_sq[a:b] = b2 * exp_avg_sq[a:b] + (1 - b2) * g * g
+        bias1, bias2 = 1 - b1 ** t, 1 - b2 ** t
+        denom = exp_avg_sq[a:b].sqrt() / math.sqrt(bias2) + eps
+        param[a:b] -= (lr / bias1) * exp_avg[a:b] / denom
