@@ -365,7 +365,8 @@ def time_encoder_config(dev, stream, precision, B, T, steps=10):
     torch.manual_seed(0)
     model = wf_builder(dict(PASE_PLUS)).to(dev).train()
     model.precision = precision
-    opt = torch.optim.Adam(list(model.parameters()), lr=1e-4, fused=True, capturable=True)
+    from pase_b200.optim import FlatAdam
+    opt = FlatAdam(list(model.parameters()), lr=1e-4).bind_encoder(model)
     gs = GraphedEncoderStep(model, opt, lambda y: y.square().mean(), (B, 1, T), dev,
                             stream=stream, resident=True,
                             x_init=torch.randn(B, 1, T))
@@ -405,10 +406,20 @@ def run_native(args):
     model = wf_builder(dict(PASE_PLUS)).to(dev).train()
     model.precision = args.precision
     params = list(model.parameters())
-    # N>1: every .grad is a view of one flat buffer -> a single NCCL all-reduce per step.
-    # N=1: no collective, gradients are handed to Adam as produced (no accumulation adds).
-    red = FlatGradAllReducer(params, attach=False) if world > 1 else None
-    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    # ONE flat fp32 gradient buffer: the encoder's backward kernels write their gradients
+    # straight into it (WaveFe.grad_sink), N>1 all-reduces it with one NCCL call, and one
+    # pase_adam_flat launch updates every parameter (pase_b200/optim.py).
+    # --torch-adam: the round-1 path (autograd-accumulated gradients packed into a flat
+    # buffer, ATen fused Adam) for A/B comparison.
+    from pase_b200.optim import FlatAdam
+    red = None
+    if args.torch_adam:
+        red = FlatGradAllReducer(params, attach=False) if world > 1 else None
+        opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+        grad_bytes = red.nbytes if red is not None else 0
+    else:
+        opt = FlatAdam(params, lr=1e-4).bind_encoder(model)
+        grad_bytes = opt.n * 4 if world > 1 else 0
 
     def zero_grads():
         opt.zero_grad(set_to_none=True)
@@ -416,6 +427,8 @@ def run_native(args):
     def reduce_grads():
         if red is not None:
             red.pack_and_reduce()
+        elif world > 1:
+            opt.reduce_grads()
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)   # distinct data per rank
     x_host = torch.randn(B_PER_GPU, 1, T_CHUNK, generator=g).pin_memory()
     x_dev = x_host.to(dev)
@@ -467,11 +480,16 @@ def run_native(args):
     gopt = gres = gs = None
     # N>1: two captured halves ([fwd, bwd, pack gradients] and [Adam]) with the NCCL
     # all-reduce of the flat gradient buffer issued eagerly between the two replays
-    gkw = dict(post_backward=red.pack, between=red.all_reduce) if world > 1 else {}
+    if world > 1:
+        gkw = dict(post_backward=red.pack, between=red.reduce) if red is not None else \
+            dict(between=opt.reduce_grads)
+    else:
+        gkw = {}
     if not args.no_graph:
         try:
             from pase_b200.graph import GraphedEncoderStep
-            gopt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
+            gopt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True) \
+                if args.torch_adam else opt
             gres = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
                                       (B_PER_GPU, 1, T_CHUNK), dev, stream=side, resident=True,
                                       **gkw)
@@ -497,7 +515,8 @@ def run_native(args):
     if not args.no_graph:
         try:
             from pase_b200.graph import GraphedEncoderStep
-            gopt = gopt or torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
+            gopt = gopt or (torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
+                            if args.torch_adam else opt)
             gs = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
                                     (B_PER_GPU, 1, T_CHUNK), dev, stream=side, **gkw)
             gs.x_host.copy_(x_host)                   # the loader's pinned staging buffer
@@ -579,7 +598,9 @@ def run_native(args):
                        "parallelism": "dp%d" % world, "gemm_precision": args.precision,
                        "cuda_graph": value_graphed,
                        "l2": "no flush: per-step working set (~1.7 GB activations) >> 126 MB L2",
-                       "grad_allreduce_bytes": red.nbytes if red is not None else 0},
+                       "optimizer": "torch fused Adam" if args.torch_adam else
+                       "pase_adam_flat (one launch, gradients written in place)",
+                       "grad_allreduce_bytes": grad_bytes},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "cuda_graph": graphed,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
@@ -663,6 +684,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true",
+                    help="round-1 optimizer path (ATen fused Adam on autograd-accumulated grads)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the legs measured after the headline: cuBLAS pipe peaks, the "
                          "cuDNN library baseline, the other operating points")

@@ -129,6 +129,10 @@ int pase_conv_w_from_fwd(const float* dWt, float* dW, int Cout, int Cin, int k, 
  * 2 = fp16 pair (hi, lo' = (v-hi)*2^11); dst (fp32) may be 0 when only hi/lo are wanted. */
 int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* dst_base,
                       int fmt, void* stream);
+/* njobs strided 2-D copies in one launch: table rows of 6 int64 {src, dst, rows, cols,
+ * src_ld, dst_ld} (device pointers, fp32 elements); total = sum rows*cols.  Used to place
+ * every small gradient of a step into the flat gradient buffer (pase_b200/optim.py). */
+int pase_scatter_copy(const long* table, int njobs, long total, void* stream);
 /* ConvTranspose1d weight (Cin,Cout,k) -> Wu[p*Cout+co, v*Cin+ci] =
  * W[ci,co,s*(taps-1-v)+p] or 0 (forward operand of the transposed conv)     */
 int pase_deconv_w_to_fwd(const float* W, float* Wu, int Cin, int Cout, int k,

@@ -1445,13 +1445,22 @@ int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const 
   // the PASE+ shapes they only pay off for long reductions (profiles/r01_history.md);
   // not available with the two-accumulator 3xF16 mode (TMEM budget)
   const bool wide = N >= 256 && (N % 256) == 0 && K >= 4096 && mode != 3;
-  const int BN = N <= 64 ? 64 : (wide ? 256 : 128);
-  const int rowb = BN == 256 ? 64 : 128;
+  // bf16 (one pass at the full f16 rate) is bound by operand bytes per flop, not by the tensor
+  // pipe: a CTA pair on a 256 x 256 tile loads 32 KB per k-block for twice the flops of the
+  // 24 KB a 256 x 128 pair tile needs (PASE_B200_BF16_WIDE=0 disables)
+  static int bf16_wide = -1;
+  if (bf16_wide < 0) {
+    const char* e = getenv("PASE_B200_BF16_WIDE");
+    bf16_wide = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool pair256 = mode == 2 && bf16_wide && N >= 256 && (N % 256) == 0 && pase_tc_use_2cta();
+  const int BN = N <= 64 ? 64 : ((wide || pair256) ? 256 : 128);
+  const int rowb = (BN == 256 && !pair256) ? 64 : 128;
   const int bk = rowb / esz;
   // split modes: fold the TMEM accumulator into fp32 register sums every K = 128
   const int flush_kb = split ? (128 / bk > 0 ? 128 / bk : 1) : 0;
   CUtensorMap ah, al, bh, bl;
-  const bool pair2 = BN == 128 && (N % 128) == 0 && pase_tc_use_2cta();
+  const bool pair2 = pair256 || (BN == 128 && (N % 128) == 0 && pase_tc_use_2cta());
   uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
   uint64_t astr[1] = {(uint64_t)R * esz};
   uint32_t abox[2] = {(uint32_t)bk, (uint32_t)BM};
@@ -1489,6 +1498,8 @@ int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const 
   }
 #define PASE_NT2(MODEV, O16, BNV) launch_nt2<BNV, MODEV, O16>(ah, al, bh, bl, a, st)
 #define PASE_NT1(MODEV, O16, BNV, RB) launch_nt<BNV, MODEV, RB, O16>(ah, al, bh, bl, a, st)
+  if (pair256) return c_bf16 ? launch_nt2<256, 2, true>(ah, al, bh, bl, a, st)
+                             : launch_nt2<256, 2, false>(ah, al, bh, bl, a, st);
   if (pair2) { PASE_NT_MODES(PASE_NT2, 128) }
   if (BN == 64) { PASE_NT_MODES(PASE_NT1, 64, 128) }
   if (BN == 128) { PASE_NT_MODES(PASE_NT1, 128, 128) }

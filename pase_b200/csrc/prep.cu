@@ -344,9 +344,49 @@ __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int nj
   }
 }
 
+// ---- batched strided copy: every small gradient of a step -> its place in the flat buffer ----
+// table: njobs rows of 6 longs {src, dst, rows, cols, src_ld, dst_ld}; blocks stride over the
+// jobs' elements (job boundaries from an exclusive prefix sum held in shared memory).
+constexpr int SC_MAX = 128;
+
+__global__ void scatter_copy_kernel(const long* __restrict__ table, int njobs) {
+  __shared__ long jt[SC_MAX * 6];
+  __shared__ long pre[SC_MAX + 1];
+  for (int i = threadIdx.x; i < njobs * 6; i += blockDim.x) jt[i] = table[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long acc = 0;
+    for (int j = 0; j < njobs; ++j) {
+      pre[j] = acc;
+      acc += jt[j * 6 + 2] * jt[j * 6 + 3];
+    }
+    pre[njobs] = acc;
+  }
+  __syncthreads();
+  const long total = pre[njobs];
+  int j = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    while (i >= pre[j + 1]) ++j;
+    const long* J = jt + j * 6;
+    const long e = i - pre[j];
+    const long cols = J[3];
+    const long r = e / cols, c = e - r * cols;
+    reinterpret_cast<float*>(J[1])[r * J[5] + c] = reinterpret_cast<const float*>(J[0])[r * J[4] + c];
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int pase_scatter_copy(const long* table, int njobs, long total, void* stream) {
+  PASE_CHECK_ARG(table && njobs > 0 && njobs <= SC_MAX && total > 0,
+                 "pase_scatter_copy: bad args (njobs=%d, at most %d)", njobs, SC_MAX);
+  scatter_copy_kernel<<<nblk(total), 256, 0, (cudaStream_t)stream>>>(table, njobs);
+  PASE_LAUNCH_CHECK("pase_scatter_copy");
+  return PASE_OK;
+}
 
 int pase_conv_w_to_fwd(const float* W, float* Wt, int Cout, int Cin, int k, void* stream) {
   PASE_CHECK_ARG(W && Wt && Cout > 0 && Cin > 0 && k > 0, "pase_conv_w_to_fwd: bad args");

@@ -561,8 +561,15 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
     return out, out_ntc
 
 
-def encoder_backward(plan, mod, params, gout, gntc, training):
-    """Returns dict name -> gradient tensor (fp32, parameter shape)."""
+def encoder_backward(plan, mod, params, gout, gntc, training, sink=None):
+    """Returns dict name -> gradient tensor (fp32, parameter shape).
+
+    sink (optional): dict name -> destination tensor (fp32, parameter shape, contiguous, e.g.
+    views of the flat gradient buffer of pase_b200.optim.FlatAdam).  When given for every
+    parameter, the gradients are WRITTEN (not accumulated) there by the kernels themselves --
+    conv weight gradients by the batched re-layout, the sinc cut-offs by pase_sinc_grad,
+    everything else by one batched strided copy -- and {} is returned: no per-parameter
+    clones, no autograd accumulation kernels, no packing before the all-reduce."""
     call = ops.call
     cfg, G, N = plan.cfg, plan.geoms, plan.N
     Tq, Kc, rows, emb = plan.Tq, plan.Kc, plan.rows, plan.emb
@@ -601,15 +608,23 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
             emb, 1.0, None, rows, rows, rows, 1, None, None, 0, akind="grad")
     dWcat = plan.dWcat.view(emb, Kc)
     first = plan.H if plan.rnn else plan.Clast
-    # gradients handed to autograd must not alias plan-owned buffers (the next backward
-    # would overwrite them): copy the slices out
-    grads["W.weight"] = dWcat[:, :first].clone().reshape(params["W.weight"].shape)
-    if plan.skips:
-        for i in range(plan.nblk - 1):
-            c0 = plan.col_off[i]
-            grads["denseskips.%d.weight" % i] = \
-                dWcat[:, c0:c0 + G[i].Cout].clone().reshape(
-                    params["denseskips.%d.weight" % i].shape)
+    copies = []          # sink mode: (src tensor view, rows, cols, src_ld, destination name)
+    if sink is not None:
+        copies.append((dWcat, emb, first, Kc, "W.weight"))
+        if plan.skips:
+            for i in range(plan.nblk - 1):
+                copies.append((dWcat[:, plan.col_off[i]:], emb, G[i].Cout, Kc,
+                               "denseskips.%d.weight" % i))
+    else:
+        # gradients handed to autograd must not alias plan-owned buffers (the next backward
+        # would overwrite them): copy the slices out
+        grads["W.weight"] = dWcat[:, :first].clone().reshape(params["W.weight"].shape)
+        if plan.skips:
+            for i in range(plan.nblk - 1):
+                c0 = plan.col_off[i]
+                grads["denseskips.%d.weight" % i] = \
+                    dWcat[:, c0:c0 + G[i].Cout].clone().reshape(
+                        params["denseskips.%d.weight" % i].shape)
 
     Cl = plan.Clast
     if plan.rnn:
@@ -619,7 +634,12 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
         plan.tn("dYg", plan.dYg, 3 * H, Tq, 0, True, "xq", plan.xq, Cq, Tq + 1, False,
                 plan.dWq, 2 * Cq, 3 * H, 2 * Cq, N, Tq, 1.0, 0)
         dWq = plan.dWq.view(3 * H, 2 * Cq)
-        grads["rnn.layers.0.linear.weight"] = torch.cat([dWq[:, Cq:], dWq[:, :Cq]], 1)
+        if sink is not None:        # [x_{t-1} | x_t] GEMM order -> the parameter's [x_t | x_{t-1}]
+            dst = sink["rnn.layers.0.linear.weight"].view(3 * H, 2 * Cq)
+            copies.append((dWq[:, Cq:], 3 * H, Cq, 2 * Cq, dst))
+            copies.append((dWq, 3 * H, Cq, 2 * Cq, dst[:, Cq:]))
+        else:
+            grads["rnn.layers.0.linear.weight"] = torch.cat([dWq[:, Cq:], dWq[:, :Cq]], 1)
         call("pase_transpose_pad", plan.Wq, 2 * Cq, plan.WqT, 3 * H, 3 * H, 2 * Cq)
         plan.nt("dYg", plan.dYg, 3 * H, False, "WqT", plan.WqT, 3 * H, True, plan.dsrc, 2 * Cq,
                 rows, 2 * Cq, 3 * H, 1.0, None, rows, rows, rows, 1, None, None, 0, akind="grad")
@@ -669,13 +689,17 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
         if g.sinc:
             plan.tn(("dyz", l), plan.dyz[l], g.Nn, g.rows_out, 0, False, ("apad", l), plan.apad[l],
                     g.lda, g.P, False, plan.dWt[l], g.K, g.Nn, g.K, N, g.rows_out, 1.0, 0)
-            dlow = torch.empty_like(params[pre + "conv.low_hz_"])
-            dband = torch.empty_like(params[pre + "conv.band_hz_"])
+            if sink is not None:
+                dlow, dband = sink[pre + "conv.low_hz_"], sink[pre + "conv.band_hz_"]
+            else:
+                dlow = torch.empty_like(params[pre + "conv.low_hz_"])
+                dband = torch.empty_like(params[pre + "conv.band_hz_"])
             call("pase_sinc_grad", plan.dWt[l], P(pre + "conv.low_hz_"),
                  P(pre + "conv.band_hz_"), mod._sinc_n, mod._sinc_win, dlow.reshape(-1),
                  dband.reshape(-1), g.Cout, g.k, g.fold, g.K, 50.0, 50.0, float(cfg["sr"]))
-            grads[pre + "conv.low_hz_"] = dlow
-            grads[pre + "conv.band_hz_"] = dband
+            if sink is None:
+                grads[pre + "conv.low_hz_"] = dlow
+                grads[pre + "conv.band_hz_"] = dband
         else:
             plan.tn(("dyz", l), plan.dyz[l], C, g.Pd, g.taps - 1, False, ("apad", l), plan.apad[l],
                     g.lda, g.P, False, plan.dWt[l], g.K, C, g.K, N, g.T_out, 1.0, 0)
@@ -685,36 +709,65 @@ def encoder_backward(plan, mod, params, gout, gntc, training):
                         g.Pd, g.P, g.P, 1, None, None, 0, akind="grad")
 
     # conv weight gradients: GEMM layout -> parameter layout for every block in one launch,
-    # into one per-call buffer (the gradients handed to autograd are views of it)
+    # into one per-call buffer (the gradients handed to autograd are views of it) or, in sink
+    # mode, straight into the flat gradient buffer (offsets relative to its lowest address)
+    conv_blocks = [l for l, g in enumerate(G) if not g.sinc]
+    if sink is not None:
+        base = min(sink.values(), key=lambda t: t.data_ptr())
+        base_ptr = base.data_ptr()
     jobs, off = [], 0
-    for l, g in enumerate(G):
-        if not g.sinc:
-            cnt = g.Cout * g.Cin * g.k
-            jobs.append((plan.dWt[l], off, None, None, g.Cout, g.Cin, g.k, 1, 1, cnt))
-            off += cnt
+    for l in conv_blocks:
+        g = G[l]
+        cnt = g.Cout * g.Cin * g.k
+        if sink is not None:
+            d = sink["blocks.%d.conv.weight" % l]
+            o = (d.data_ptr() - base_ptr) // 4
+        else:
+            o = off
+        jobs.append((plan.dWt[l], o, None, None, g.Cout, g.Cin, g.k, 1, 1, cnt))
+        off += cnt
     if jobs:
-        dWflat = torch.empty(off, dtype=torch.float32, device=plan.device)
-        plan.w_batch(2, jobs, dWflat)
-        for (_, o, _, _, Cout, Cin, k, _, _, cnt), l in zip(jobs, [l for l, g in enumerate(G)
-                                                                  if not g.sinc]):
-            grads["blocks.%d.conv.weight" % l] = dWflat[o:o + cnt].view(Cout, Cin, k)
+        if sink is not None:
+            plan.w_batch(2, jobs, base)
+        else:
+            dWflat = torch.empty(off, dtype=torch.float32, device=plan.device)
+            plan.w_batch(2, jobs, dWflat)
+            for (_, o, _, _, Cout, Cin, k, _, _, cnt), l in zip(jobs, conv_blocks):
+                grads["blocks.%d.conv.weight" % l] = dWflat[o:o + cnt].view(Cout, Cin, k)
 
     # one cast for every small reduction (double accumulators -> fp32 gradients) into a
     # per-call vector; the per-parameter gradients are views of it (no copies)
-    gv = torch.empty_like(plan.grad_vec)
+    gv = plan.grad_vec if sink is not None else torch.empty_like(plan.grad_vec)
     call("pase_cast_d2f", sb, gv, sb.numel(), 1.0)
+    small = {}
     for l, g in enumerate(G):
         C, o = g.Cout, plan.bs_off[l]
         pre = "blocks.%d." % l
-        grads[pre + "norm.bias"] = gv[o:o + C]
-        grads[pre + "norm.weight"] = gv[o + C:o + 2 * C]
-        grads[pre + "act.weight"] = gv[o + 2 * C:o + 3 * C]
+        small[pre + "norm.bias"] = gv[o:o + C]
+        small[pre + "norm.weight"] = gv[o + C:o + 2 * C]
+        small[pre + "act.weight"] = gv[o + 2 * C:o + 3 * C]
         if not g.sinc:
-            grads[pre + "conv.bias"] = gv[o + 3 * C:o + 4 * C]
-    grads["W.bias"] = gv[plan.bs_bw:plan.bs_bw + emb]
+            small[pre + "conv.bias"] = gv[o + 3 * C:o + 4 * C]
+    small["W.bias"] = gv[plan.bs_bw:plan.bs_bw + emb]
     if plan.rnn:
-        grads["rnn.layers.0.linear.bias"] = gv[plan.bs_bq:plan.bs_bq + 3 * plan.H]
-    return grads
+        small["rnn.layers.0.linear.bias"] = gv[plan.bs_bq:plan.bs_bq + 3 * plan.H]
+    if sink is None:
+        grads.update(small)
+        return grads
+    # sink mode: every remaining gradient -> its place in the flat buffer, one launch
+    for name, t in small.items():
+        copies.append((t, 1, t.numel(), t.numel(), name))
+    rows = []
+    for (src, r, c, sld, dst) in copies:
+        d = sink[dst] if isinstance(dst, str) else dst
+        dld = c if isinstance(dst, str) else d.stride(0)
+        rows.append([src.data_ptr(), d.data_ptr(), r, c, sld, dld])
+    ent = plan._wtables.get("scatter")
+    if ent is None or ent[0] != rows:
+        ent = (rows, torch.tensor(rows, dtype=torch.int64).reshape(-1).to(plan.device))
+        plan._wtables["scatter"] = ent
+    call("pase_scatter_copy", ent[1], len(rows), sum(r[2] * r[3] for r in rows))
+    return {}
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -743,5 +796,9 @@ class _EncoderFn(torch.autograd.Function):
             gout = gout.contiguous()
         if gntc is not None:
             gntc = gntc.contiguous()
-        grads = encoder_backward(plan, ctx.mod, params, gout, gntc, ctx.training)
+        sink = getattr(ctx.mod, "grad_sink", None)
+        if sink is not None and any(n not in sink for n in ctx.names):
+            raise RuntimeError("pase_b200: WaveFe.grad_sink must name every parameter "
+                               "(missing %s)" % [n for n in ctx.names if n not in sink][:3])
+        grads = encoder_backward(plan, ctx.mod, params, gout, gntc, ctx.training, sink)
         return (None, None, None, None, None) + tuple(grads.get(n) for n in ctx.names)

@@ -66,6 +66,7 @@ class FlatAdam(torch.optim.Optimizer):
         self._table = None
         self._table_key = None
         self._pending = set()
+        self._sunk = set()
 
     # ---- gradient buffer protocol (shared with dp.FlatGradAllReducer) -----------------
     def attach_grads(self):
@@ -76,7 +77,10 @@ class FlatAdam(torch.optim.Optimizer):
         """Gradients autograd allocated outside the flat buffer are copied in (one
         multi-tensor copy); parameters without a gradient contribute zeros."""
         srcs, dsts = [], []
+        sunk = self._sunk
         for p, v in zip(self._plist, self._gviews):
+            if id(p) in sunk:                 # written in place by the encoder's kernels
+                continue
             if p.grad is None:
                 v.zero_()
             elif p.grad.data_ptr() != v.data_ptr():
@@ -87,13 +91,45 @@ class FlatAdam(torch.optim.Optimizer):
         self.attach_grads()
 
     def zero_grad(self, set_to_none=False):
-        """One memset of the flat gradient buffer; ``.grad`` stays a view of it."""
+        """One memset of the flat gradient buffer; ``.grad`` stays a view of it.  Parameters
+        bound through ``bind_encoder`` keep their views even with set_to_none (their
+        gradients are overwritten, not accumulated)."""
         if set_to_none:
             for p in self._plist:
-                p.grad = None
+                if id(p) not in self._sunk:
+                    p.grad = None
         else:
             self.flat_grad.zero_()
             self.attach_grads()
+
+    def bind_encoder(self, encoder):
+        """Make the encoder's backward kernels write their gradients straight into this
+        optimizer's flat gradient buffer (``WaveFe.grad_sink``): no autograd accumulation, no
+        per-parameter copies.  The encoder's gradients are then OVERWRITTEN by each backward
+        (one encoder call per step); other modules' gradients keep autograd's semantics."""
+        byid = {id(p): v for p, v in zip(self._plist, self._gviews)}
+        sink = {}
+        for name, p in encoder.named_parameters():
+            if p.requires_grad:
+                if id(p) not in byid:
+                    raise ValueError("FlatAdam.bind_encoder: %s is not optimised here" % name)
+                sink[name] = byid[id(p)]
+        encoder.grad_sink = sink
+        self._sunk = {id(p) for _, p in encoder.named_parameters() if p.requires_grad}
+        self.attach_grads()
+        return self
+
+    def reduce_grads(self, group=None):
+        """Data parallelism: ONE all-reduce (average) of the flat gradient buffer."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self.pack_grads()
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
+                self.flat_grad.mul_(1.0 / dist.get_world_size(group))
+        return self.flat_grad
 
     # ---- the update ------------------------------------------------------------------
     def _segments(self):

@@ -475,7 +475,7 @@ def pase_conv_w_batch(table, njobs, total, op, dst_base, fmt=0):
             blocks += (Cout // 32) * (Cin // 8) if op == 1 else Cout
         n_w = Cout * Cin * k
         if op == 2:
-            out = dst_base[dst:dst + count]
+            out = _host_view(dst_base.data_ptr() + 4 * dst, count)     # pointer arithmetic
             pase_conv_w_from_fwd(_host_view(src, n_w), out, Cout, Cin, k)
         else:
             out = _host_view(dst, count) if dst else torch.zeros(count)
@@ -603,3 +603,14 @@ def pase_adam_flat(param, grad, exp_avg, exp_avg_sq, n, seg_table, nseg, steps, 
         bias1, bias2 = 1 - b1 ** t, 1 - b2 ** t
         denom = exp_avg_sq[a:b].sqrt() / math.sqrt(bias2) + eps
         param[a:b] -= (lr / bias1) * exp_avg[a:b] / denom
+
+
+def pase_scatter_copy(table, njobs, total, stream=None):
+    t = table.reshape(njobs, 6).tolist()
+    done = 0
+    for (src, dst, rows, cols, sld, dld) in t:
+        s = _host_view(src, (rows - 1) * sld + cols)
+        d = _host_view(dst, (rows - 1) * dld + cols)
+        _as(d, (rows, cols), (dld, 1)).copy_(_as(s, (rows, cols), (sld, 1)))
+        done += rows * cols
+    assert done == total

@@ -183,3 +183,42 @@ def test_weight_batch_table_is_cached_and_rebuilt(emulated, monkeypatch):
     # train-mode outputs of the three steps agree
     assert_close(y2, y1, 1e-6, 1e-7, "step 2")
     assert_close(y3, y1, 1e-6, 1e-7, "step 3")
+
+
+def test_gradient_sink_equals_autograd_path(emulated):
+    """WaveFe.grad_sink (FlatAdam.bind_encoder): gradients written by the kernels straight into
+    the flat buffer == the gradients autograd would have accumulated, and one FlatAdam step ==
+    torch.optim.Adam on the autograd gradients."""
+    from pase_b200.optim import FlatAdam
+    gold, meta = load_golden("enc_pasep_train_3200")
+    cfg = resolve_cfg(meta["cfg"])
+    x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5)
+    cot = seeded_randn(tuple(gold["y"].shape), meta["seed"] + 2)
+    models = []
+    for _ in range(2):
+        m = WaveFe(**cfg)
+        m.precision = "3xf16"
+        m.load_state_dict(fill_state_dict(m.state_dict(), meta["seed"]))
+        models.append(m.train(True))
+    ref, nat = models
+    o_ref = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    o_nat = FlatAdam(list(nat.parameters()), lr=1e-3).bind_encoder(nat)
+    for it in range(2):
+        o_ref.zero_grad(set_to_none=True)
+        o_nat.zero_grad(set_to_none=True)          # must not detach the sunk gradient views
+        for m in (ref, nat):
+            y, _ = run_encoder_cpu(m, x)
+            (y * cot).sum().backward()
+        for (k, a), (_, b) in zip(ref.named_parameters(), nat.named_parameters()):
+            assert b.grad.data_ptr() == o_nat._gviews[[id(p) for p in o_nat._plist].index(id(b))].data_ptr()
+            if it == 0:          # same weights: bit-identical gradients
+                assert torch.equal(a.grad, b.grad), k
+            elif not k.endswith(("conv.bias", "W.bias")):      # (analytically zero: pure noise)
+                # weights differ by the two Adam implementations' round-off
+                assert torch.allclose(a.grad, b.grad, rtol=1e-3,
+                                      atol=1e-4 * float(a.grad.abs().max())), k
+        o_ref.step()
+        o_nat.step()
+        for (k, a), (_, b) in zip(ref.named_parameters(), nat.named_parameters()):
+            if it == 0 or not k.endswith(("conv.bias", "W.bias")):
+                assert torch.allclose(a, b, rtol=1e-5, atol=2e-6), k
