@@ -31,6 +31,7 @@ PASE_PLUS = {"kwidths": [251, 20, 11, 11, 11, 11, 11, 11], "strides": [1, 10, 2,
              "fmaps": [64, 64, 128, 128, 256, 256, 512, 512], "rnn_dim": 512, "denseskips": True,
              "norm_out": True, "rnn_pool": True, "rnn_layers": 1}
 B_PER_GPU, T_CHUNK = 32, 32000
+DP_SPLIT = 3          # blocks below this index form the late (small) all-reduce bucket
 METRIC = "waveform-samples/sec PASE+ encoder fwd+bwd (B=32,T=32000 per GPU)"
 # algorithmic work per 32000-sample chunk
 FLOP_PER_CHUNK = 25.4e9          # fwd+bwd as the reference computes it
@@ -418,6 +419,12 @@ def run_native(args):
         opt = torch.optim.Adam(params, lr=1e-4, fused=True)
         grad_bytes = red.nbytes if red is not None else 0
     else:
+        n_lower = None
+        if world > 1 and not args.no_overlap:
+            # flat buffer ordered [blocks 0..2 | rest]: the all-reduce of the large bucket is
+            # hidden behind the backward of blocks 2..0 (pase_b200/graph.py::PipelinedDPStep)
+            from pase_b200.graph import PipelinedDPStep
+            params, n_lower = PipelinedDPStep.order_params(model, DP_SPLIT)
         opt = FlatAdam(params, lr=1e-4).bind_encoder(model)
         grad_bytes = opt.n * 4 if world > 1 else 0
 
@@ -490,9 +497,14 @@ def run_native(args):
             from pase_b200.graph import GraphedEncoderStep
             gopt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True) \
                 if args.torch_adam else opt
-            gres = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
-                                      (B_PER_GPU, 1, T_CHUNK), dev, stream=side, resident=True,
-                                      **gkw)
+            if world > 1 and not args.torch_adam and not args.no_overlap:
+                gres = PipelinedDPStep(model, opt, lambda y: y.square().mean(),
+                                       (B_PER_GPU, 1, T_CHUNK), dev, split=DP_SPLIT,
+                                       n_lower=n_lower, stream=side, resident=True)
+            else:
+                gres = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
+                                          (B_PER_GPU, 1, T_CHUNK), dev, stream=side,
+                                          resident=True, **gkw)
             gres.x_static.copy_(x_dev)
             value_fn, value_graphed = (lambda: gres.step()), True
             for _ in range(3):
@@ -517,8 +529,13 @@ def run_native(args):
             from pase_b200.graph import GraphedEncoderStep
             gopt = gopt or (torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)
                             if args.torch_adam else opt)
-            gs = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
-                                    (B_PER_GPU, 1, T_CHUNK), dev, stream=side, **gkw)
+            if world > 1 and not args.torch_adam and not args.no_overlap:
+                gs = PipelinedDPStep(model, opt, lambda y: y.square().mean(),
+                                     (B_PER_GPU, 1, T_CHUNK), dev, split=DP_SPLIT,
+                                     n_lower=n_lower, stream=side)
+            else:
+                gs = GraphedEncoderStep(model, gopt, lambda y: y.square().mean(),
+                                        (B_PER_GPU, 1, T_CHUNK), dev, stream=side, **gkw)
             gs.x_host.copy_(x_host)                   # the loader's pinned staging buffer
             e2e_fn = lambda: gs.step()
             graphed = True
@@ -600,6 +617,11 @@ def run_native(args):
                        "l2": "no flush: per-step working set (~1.7 GB activations) >> 126 MB L2",
                        "optimizer": "torch fused Adam" if args.torch_adam else
                        "pase_adam_flat (one launch, gradients written in place)",
+                       "grad_allreduce": None if world == 1 else (
+                           "one flat buffer; upper bucket overlapped with backward of blocks "
+                           "%d..0 (side stream), lower bucket after" % (DP_SPLIT - 1)
+                           if not (args.torch_adam or args.no_overlap) else
+                           "one flat buffer between two graph replays"),
                        "grad_allreduce_bytes": grad_bytes},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "cuda_graph": graphed,
@@ -684,6 +706,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1: all-reduce the whole flat gradient between two graph replays "
+                         "instead of hiding it behind the tail of backward")
     ap.add_argument("--torch-adam", action="store_true",
                     help="round-1 optimizer path (ATen fused Adam on autograd-accumulated grads)")
     ap.add_argument("--no-extras", action="store_true",

@@ -325,7 +325,7 @@ class EncoderPlan(object):
             self._ops[name] = op
         return op.hi, op.lo
 
-    def w_batch(self, op, jobs, dst_base=None):
+    def w_batch(self, op, jobs, dst_base=None, key=None):
         """One launch for the weight re-layouts of every conv block (pase_conv_w_batch).
         jobs: [(src, dst tensor | element offset, hi, lo, Cout, Cin, k, s, taps, count)].
         The device job table is rebuilt only when a pointer changed."""
@@ -340,11 +340,12 @@ class EncoderPlan(object):
                          count, blocks])
             start += count
             blocks += (Cout // 32) * (Cin // 8) if op == 1 else Cout
-        ent = self._wtables.get(op)
+        key = op if key is None else key
+        ent = self._wtables.get(key)
         if ent is None or ent[0] != rows:
             table = torch.tensor(rows, dtype=torch.int64).reshape(-1).to(self.device)
             ent = (rows, table)
-            self._wtables[op] = ent
+            self._wtables[key] = ent
         fmt = {1: 0, 2: 1, 3: 2}.get(self.mode, 0)
         if tiled:
             ops.call("pase_conv_w_batch", ent[1], len(rows), blocks, op + 3, dst_base, fmt)
@@ -562,7 +563,26 @@ def encoder_forward(plan, mod, x, params, training, save_for_backward):
 
 
 def encoder_backward(plan, mod, params, gout, gntc, training, sink=None):
-    """Returns dict name -> gradient tensor (fp32, parameter shape).
+    """Returns dict name -> gradient tensor (fp32, parameter shape); see
+    encoder_backward_steps (this runs it to completion)."""
+    gen = encoder_backward_steps(plan, mod, params, gout, gntc, training, sink)
+    try:
+        while True:
+            next(gen)
+    except StopIteration as done:
+        return done.value
+
+
+def encoder_backward_steps(plan, mod, params, gout, gntc, training, sink=None, split=None):
+    """Generator form of the backward sweep.  Returns (StopIteration.value) dict name ->
+    gradient tensor (fp32, parameter shape).
+
+    split (sink mode only): block index s.  The generator yields ONCE, after every gradient
+    of the output layer, the QRNN and blocks >= s has been written to its sink destination
+    (their re-layout / cast / scatter launches are issued before the yield) and before the
+    backward of blocks s-1 .. 0 is launched.  Data parallelism starts the all-reduce of that
+    (large) part of the flat gradient buffer on a side stream at the yield and hides it behind
+    the remaining backward, which contains the two largest activations (pase_b200/graph.py).
 
     sink (optional): dict name -> destination tensor (fp32, parameter shape, contiguous, e.g.
     views of the flat gradient buffer of pase_b200.optim.FlatAdam).  When given for every
@@ -648,7 +668,15 @@ def encoder_backward(plan, mod, params, gout, gntc, training, sink=None):
     else:
         last_src = dict(A=plan.dcat, a_ss=Tq * Kc, a_rs=Kc, B=None, b_ss=0, b_rs=0, b_shift=0)
 
+    if split is not None and (sink is None or not (0 < split < plan.nblk)):
+        raise ValueError("encoder_backward_steps: split needs sink mode and 0 < split < nblk")
     for l in range(plan.nblk - 1, -1, -1):
+        if split is not None and l == split - 1:
+            # everything above is final: emit the upper part of the gradients, then hand control
+            # back (the caller launches the collective of that bucket)
+            _emit_sunk_grads(plan, G, sink, copies, range(split, plan.nblk), True, "hi")
+            copies = []
+            yield "upper"
         g = G[l]
         C = g.Cout
         pre = "blocks.%d." % l
@@ -708,39 +736,41 @@ def encoder_backward(plan, mod, params, gout, gntc, training, sink=None):
                         plan.dxpad[l], g.s * g.Cin, N * g.Pd, g.s * g.Cin, g.taps * C, 1.0, None,
                         g.Pd, g.P, g.P, 1, None, None, 0, akind="grad")
 
-    # conv weight gradients: GEMM layout -> parameter layout for every block in one launch,
-    # into one per-call buffer (the gradients handed to autograd are views of it) or, in sink
-    # mode, straight into the flat gradient buffer (offsets relative to its lowest address)
-    conv_blocks = [l for l, g in enumerate(G) if not g.sinc]
     if sink is not None:
-        base = min(sink.values(), key=lambda t: t.data_ptr())
-        base_ptr = base.data_ptr()
+        if split is not None:
+            _emit_sunk_grads(plan, G, sink, copies, range(0, split), False, "lo")
+        else:
+            _emit_sunk_grads(plan, G, sink, copies, range(0, plan.nblk), True, "all")
+        return {}
+
+    # conv weight gradients: GEMM layout -> parameter layout for every block in one launch,
+    # into one per-call buffer (the gradients handed to autograd are views of it)
+    conv_blocks = [l for l, g in enumerate(G) if not g.sinc]
     jobs, off = [], 0
     for l in conv_blocks:
         g = G[l]
         cnt = g.Cout * g.Cin * g.k
-        if sink is not None:
-            d = sink["blocks.%d.conv.weight" % l]
-            o = (d.data_ptr() - base_ptr) // 4
-        else:
-            o = off
-        jobs.append((plan.dWt[l], o, None, None, g.Cout, g.Cin, g.k, 1, 1, cnt))
+        jobs.append((plan.dWt[l], off, None, None, g.Cout, g.Cin, g.k, 1, 1, cnt))
         off += cnt
     if jobs:
-        if sink is not None:
-            plan.w_batch(2, jobs, base)
-        else:
-            dWflat = torch.empty(off, dtype=torch.float32, device=plan.device)
-            plan.w_batch(2, jobs, dWflat)
-            for (_, o, _, _, Cout, Cin, k, _, _, cnt), l in zip(jobs, conv_blocks):
-                grads["blocks.%d.conv.weight" % l] = dWflat[o:o + cnt].view(Cout, Cin, k)
-
+        dWflat = torch.empty(off, dtype=torch.float32, device=plan.device)
+        plan.w_batch(2, jobs, dWflat)
+        for (_, o, _, _, Cout, Cin, k, _, _, cnt), l in zip(jobs, conv_blocks):
+            grads["blocks.%d.conv.weight" % l] = dWflat[o:o + cnt].view(Cout, Cin, k)
     # one cast for every small reduction (double accumulators -> fp32 gradients) into a
     # per-call vector; the per-parameter gradients are views of it (no copies)
-    gv = plan.grad_vec if sink is not None else torch.empty_like(plan.grad_vec)
+    gv = torch.empty_like(plan.grad_vec)
     call("pase_cast_d2f", sb, gv, sb.numel(), 1.0)
+    grads.update(_small_grad_views(plan, G, gv, range(plan.nblk), True))
+    return grads
+
+
+def _small_grad_views(plan, G, gv, layers, top):
+    """Views into the cast reduction vector: BatchNorm / PReLU / bias gradients of `layers`
+    (+ the output-side biases when `top`)."""
     small = {}
-    for l, g in enumerate(G):
+    for l in layers:
+        g = G[l]
         C, o = g.Cout, plan.bs_off[l]
         pre = "blocks.%d." % l
         small[pre + "norm.bias"] = gv[o:o + C]
@@ -748,26 +778,46 @@ def encoder_backward(plan, mod, params, gout, gntc, training, sink=None):
         small[pre + "act.weight"] = gv[o + 2 * C:o + 3 * C]
         if not g.sinc:
             small[pre + "conv.bias"] = gv[o + 3 * C:o + 4 * C]
-    small["W.bias"] = gv[plan.bs_bw:plan.bs_bw + emb]
-    if plan.rnn:
-        small["rnn.layers.0.linear.bias"] = gv[plan.bs_bq:plan.bs_bq + 3 * plan.H]
-    if sink is None:
-        grads.update(small)
-        return grads
-    # sink mode: every remaining gradient -> its place in the flat buffer, one launch
-    for name, t in small.items():
+    if top:
+        small["W.bias"] = gv[plan.bs_bw:plan.bs_bw + plan.emb]
+        if plan.rnn:
+            small["rnn.layers.0.linear.bias"] = gv[plan.bs_bq:plan.bs_bq + 3 * plan.H]
+    return small
+
+
+def _emit_sunk_grads(plan, G, sink, copies, layers, top, tag):
+    """Sink mode: write the gradients of `layers` (+ output-side tensors when `top`) into their
+    destinations: conv weights by the batched re-layout (offsets relative to the lowest sink
+    address), everything else by ONE batched strided copy."""
+    call = ops.call
+    base = min(sink.values(), key=lambda t: t.data_ptr())
+    base_ptr = base.data_ptr()
+    jobs = []
+    for l in layers:
+        g = G[l]
+        if g.sinc:
+            continue
+        d = sink["blocks.%d.conv.weight" % l]
+        jobs.append((plan.dWt[l], (d.data_ptr() - base_ptr) // 4, None, None, g.Cout, g.Cin, g.k,
+                     1, 1, g.Cout * g.Cin * g.k))
+    if jobs:
+        plan.w_batch(2, jobs, base, key=("from_fwd", tag))
+    gv = plan.grad_vec
+    sb = plan.stats_b
+    call("pase_cast_d2f", sb, gv, sb.numel(), 1.0)
+    copies = list(copies)
+    for name, t in _small_grad_views(plan, G, gv, layers, top).items():
         copies.append((t, 1, t.numel(), t.numel(), name))
     rows = []
     for (src, r, c, sld, dst) in copies:
         d = sink[dst] if isinstance(dst, str) else dst
         dld = c if isinstance(dst, str) else d.stride(0)
         rows.append([src.data_ptr(), d.data_ptr(), r, c, sld, dld])
-    ent = plan._wtables.get("scatter")
+    ent = plan._wtables.get(("scatter", tag))
     if ent is None or ent[0] != rows:
         ent = (rows, torch.tensor(rows, dtype=torch.int64).reshape(-1).to(plan.device))
-        plan._wtables["scatter"] = ent
+        plan._wtables[("scatter", tag)] = ent
     call("pase_scatter_copy", ent[1], len(rows), sum(r[2] * r[3] for r in rows))
-    return {}
 
 
 class _EncoderFn(torch.autograd.Function):

@@ -100,3 +100,164 @@ class GraphedEncoderStep(object):
             return None
         self.stream.synchronize()
         return float(self.loss_host)
+
+
+class PipelinedDPStep(object):
+    """Data-parallel training step of the encoder with the gradient all-reduce HIDDEN behind
+    the tail of backward (pure DP, one flat gradient buffer).
+
+    The flat gradient buffer of ``FlatAdam`` is ordered [blocks 0..split-1 | everything else].
+    One step =
+        graph A1   H2D, forward, loss, backward of the output layer / QRNN / blocks >= split;
+                   those gradients are final in the flat buffer when A1 ends
+        eager      NCCL all-reduce (average) of the UPPER bucket (~98 % of the bytes) on a
+                   side stream ...
+        graph A2   ... while the backward of blocks split-1 .. 0 -- the two largest
+                   activations, ~40 % of the backward time -- runs on the main stream
+        eager      NCCL all-reduce of the LOWER bucket (blocks 0..split-1: ~1 MB)
+        graph B    one pase_adam_flat launch, D2H of the loss
+    Collectives are never captured (capturing NCCL hung in this image, profiles/r01_history.md);
+    they are ordered against the graph replays with events.  ``optimizer`` must be a FlatAdam
+    whose FIRST parameters are exactly the encoder's blocks < split (see ``order_params``)."""
+
+    @staticmethod
+    def order_params(model, split):
+        """Parameter list for FlatAdam: blocks 0..split-1 first (the lower bucket)."""
+        lower, upper = [], []
+        for name, p in model.named_parameters():
+            if not p.requires_grad:
+                continue
+            head = name.split(".")
+            is_lower = head[0] == "blocks" and int(head[1]) < split
+            (lower if is_lower else upper).append(p)
+        return lower + upper, len(lower)
+
+    def __init__(self, model, optimizer, loss_fn, shape, device, split=3, n_lower=None,
+                 group=None, stream=None, resident=False, warmup=3, x_init=None):
+        import torch.distributed as dist
+        from . import encoder as enc
+        self.dist, self.enc = dist, enc
+        self.model, self.opt, self.loss_fn, self.split, self.group = model, optimizer, loss_fn, \
+            split, group
+        if getattr(model, "grad_sink", None) is None:
+            optimizer.bind_encoder(model)
+        self.sink = model.grad_sink
+        if n_lower is None:
+            n_lower = sum(1 for n, p in model.named_parameters() if p.requires_grad and
+                          n.startswith("blocks.") and int(n.split(".")[1]) < split)
+        first_upper = optimizer._offsets[n_lower] if n_lower < len(optimizer._offsets) else optimizer.n
+        lo_ids = {id(p) for p in optimizer._plist[:n_lower]}
+        want = {id(p) for n, p in model.named_parameters() if p.requires_grad and
+                n.startswith("blocks.") and int(n.split(".")[1]) < split}
+        if lo_ids != want:
+            raise ValueError("PipelinedDPStep: the optimizer's first %d parameters must be the "
+                             "encoder's blocks < %d (use PipelinedDPStep.order_params)"
+                             % (n_lower, split))
+        self.lower = optimizer.flat_grad[:first_upper]
+        self.upper = optimizer.flat_grad[first_upper:]
+        self.x_static = torch.zeros(shape, dtype=torch.float32, device=device)
+        self.x_host = torch.zeros(shape, dtype=torch.float32).pin_memory()
+        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        if x_init is not None:
+            self.x_host.copy_(x_init)
+            self.x_static.copy_(x_init)
+        self.resident = resident
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
+        self.comm = torch.cuda.Stream(device=device)
+        self.ev_upper = torch.cuda.Event()
+        self._loss = self._gen = None
+        self.gA1 = self.gA2 = self.gB = None
+        self._capture(warmup)
+
+    # -- the pieces ----------------------------------------------------------------------
+    def _a1(self):
+        enc = self.enc
+        if not self.resident:
+            self.x_static.copy_(self.x_host, non_blocking=True)
+        m = self.model
+        m._sinc_consts(self.x_static.device)
+        plan = m._plan(self.x_static.shape[0], self.x_static.shape[2], self.x_static.device)
+        params = dict(m.named_parameters())
+        with torch.no_grad():
+            y, _ = enc.encoder_forward(plan, m, self.x_static, params, True, True)
+        yl = y.detach().requires_grad_(True)
+        self._loss = self.loss_fn(yl)
+        self._loss.backward()
+        self._gen = enc.encoder_backward_steps(plan, m, params, yl.grad.contiguous(), None, True,
+                                               self.sink, self.split)
+        next(self._gen)                                  # ... up to the split
+
+    def _a2(self):
+        try:
+            next(self._gen)
+            raise RuntimeError("encoder_backward_steps yielded twice")
+        except StopIteration:
+            pass
+        self._gen = None
+
+    def _b(self):
+        self.opt.step()
+        if not self.resident:
+            self.loss_host.copy_(self._loss.detach(), non_blocking=True)
+
+    def _reduce(self, t):
+        dist = self.dist
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.mul_(1.0 / dist.get_world_size(self.group))
+
+    def _reduce_upper_async(self):
+        """on the side stream, after everything enqueued on the main stream so far"""
+        self.ev_upper.record(self.stream)
+        self.comm.wait_event(self.ev_upper)
+        with torch.cuda.stream(self.comm):
+            self._reduce(self.upper)
+
+    def _reduce_lower_and_join(self):
+        with torch.cuda.stream(self.stream):
+            self._reduce(self.lower)
+            self.stream.wait_stream(self.comm)
+
+    def _eager(self):
+        self._a1()
+        self._reduce_upper_async()
+        self._a2()
+        self._reduce_lower_and_join()
+        self._b()
+
+    def _capture(self, warmup):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                self._eager()
+        self.stream.synchronize()
+        self.comm.synchronize()
+        torch.cuda.current_stream().wait_stream(self.stream)
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, stream=self.stream):
+            self._a1()
+        self._reduce_upper_async()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, stream=self.stream, pool=g1.pool()):
+            self._a2()
+        self._reduce_lower_and_join()
+        g3 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g3, stream=self.stream, pool=g1.pool()):
+            self._b()
+        self.gA1, self.gA2, self.gB = g1, g2, g3
+
+    def step(self, x_host=None):
+        if x_host is not None:
+            self.x_host.copy_(x_host)
+        with torch.cuda.stream(self.stream):
+            self.gA1.replay()
+            self._reduce_upper_async()
+            self.gA2.replay()
+            self._reduce_lower_and_join()
+            self.gB.replay()
+        if self.resident:
+            return None
+        self.stream.synchronize()
+        return float(self.loss_host)
