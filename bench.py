@@ -228,27 +228,28 @@ def workers_plus_cfg():
     return {"regr": regr, "cls": cls}
 
 
-def run_workers(args):
-    """Extra workload (BASELINE configs[2-3] shape): encoder on the 3B concatenated chunks +
-    all workers+ heads + summed loss, fwd+bwd+Adam, 1 GPU, eager.  Not the contract line."""
+def time_workers(dev, precision, B, T=T_CHUNK, steps=5, warmup=3, graph=True, stream=None):
+    """BASELINE configs[2]/[3] shape on one GPU: PASE+ encoder on the 3B concatenated chunks +
+    all 12 workers+ heads + summed loss, fwd + bwd + ONE flat Adam launch; the whole step
+    replayed as one CUDA graph when `graph`.  -> dict (ms/step, chunk-samples/s, ...)."""
     from pase_b200.pase import pase, total_loss
     from pase_b200.utils import parse_workers
     from pase_b200 import functional as Fn
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    Fn.set_precision(args.precision)
+    from pase_b200.optim import FlatAdam
+    Fn.set_precision(precision)
     torch.manual_seed(0)
     wcfg = workers_plus_cfg()
     model = pase(frontend_cfg=dict(PASE_PLUS), minions_cfg=parse_workers(wcfg)).to(dev).train()
-    model.frontend.precision = args.precision
-    B = args.batch
-    Tq = T_CHUNK // 160
-    batch = {k: torch.randn(B, 1, T_CHUNK, device=dev) for k in
+    model.frontend.precision = precision
+    Tq = T // 160
+    batch = {k: torch.randn(B, 1, T, device=dev) for k in
              ("chunk", "chunk_ctxt", "chunk_rand", "cchunk")}
     for w in wcfg["regr"]:
         if w["name"] != "cchunk":
             batch[w["name"]] = torch.randn(B, w["num_outputs"], Tq, device=dev)
-    opt = torch.optim.Adam([p for p in model.parameters()], lr=1e-4, fused=True)
+    # the reference steps 13 Adam instances (trainer.py:86-143); here: one launch
+    opt = FlatAdam([p for p in model.parameters()], lr=1e-4).bind_encoder(model.frontend)
+    loss_dev = torch.zeros((), device=dev)
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -256,26 +257,47 @@ def run_workers(args):
         tot, _ = total_loss(model, preds, labels)
         tot.backward()
         opt.step()
-        return tot
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+        loss_dev.copy_(tot.detach())
+    stream = stream or torch.cuda.current_stream()
+    with torch.cuda.stream(stream):
+        for _ in range(max(warmup, 3)):
+            step()
+    stream.synchronize()
+    fn, graphed, why = step, False, None
+    if graph:
+        try:
+            opt.zero_grad(set_to_none=True)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                step()
+            fn, graphed = g.replay, True
+            for _ in range(2):
+                fn()
+        except Exception as exc:
+            why = repr(exc)[:200]
+            torch.cuda.synchronize()
+    ms = _event_time(fn, steps)
     nparam = sum(p.numel() for p in model.parameters())
-    print(json.dumps({"metric": "waveform-samples/sec PASE+ encoder(3B chunks)+workers+ heads "
-                                "fwd+bwd+adam", "value": B * T_CHUNK / (ms * 1e-3),
-                      "unit": "chunk-samples/s", "ms_per_step": ms, "n_gpus": 1,
-                      "config": {"workload": "PASE+.cfg + workers+.cfg (12 workers), B=%d chunk "
-                                             "triplets, T=32000" % B,
-                                 "gemm_precision": args.precision, "params": nparam},
-                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+    return {"metric": "waveform-samples/sec PASE+ encoder(3B chunks)+workers+ heads fwd+bwd+adam",
+            "value": B * T / (ms * 1e-3), "unit": "chunk-samples/s", "ms_per_step": ms,
+            "n_gpus": 1, "cuda_graph": graphed, "graph_error": why,
+            "loss": float(loss_dev),
+            "config": {"workload": "PASE+.cfg + workers+.cfg (12 workers), B=%d chunk triplets, "
+                                   "T=%d" % (B, T),
+                       "gemm_precision": precision, "params": nparam,
+                       "optimizer": "pase_adam_flat, one launch for all 13 parameter groups"},
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
 
+
+def run_workers(args):
+    """Extra workload (BASELINE configs[2-3] shape).  Not the contract line."""
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    print(json.dumps(time_workers(dev, args.precision, args.batch, steps=args.steps,
+                                  warmup=args.warmup, graph=not args.no_graph, stream=side)),
+          flush=True)
 
 
 # ------------------------------------------------------------------ extra legs ---
@@ -684,6 +706,12 @@ def run_native(args):
                     others.append(r)
                 except Exception as exc:
                     others.append({"config": tag, "error": repr(exc)[:300]})
+            try:
+                w = time_workers(dev, args.precision, B_PER_GPU, stream=side)
+                w["config"]["baseline"] = "BASELINE configs[2]/[3] per-GPU shape"
+                others.append(w)
+            except Exception as exc:
+                others.append({"config": "workers+ full step", "error": repr(exc)[:300]})
             line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu(4, 3, 1, budget_s=30.0)
@@ -719,7 +747,7 @@ def main():
                     help="encoder = the contract line (BASELINE configs[1]); workers = encoder + "
                          "all workers+ heads (informational)")
     ap.add_argument("--batch", type=int, default=32, help="chunk triplets per step (workers workload)")
-    ap.add_argument("--precision", default=os.environ.get("PASE_B200_PRECISION", "3xtf32"),
+    ap.add_argument("--precision", default=os.environ.get("PASE_B200_PRECISION", "3xf16"),
                     choices=["fp32", "3xtf32", "3xf16", "tf32", "bf16"],
                     help="GEMM numerics: fp32 FFMA; 3xTF32 / 3xF16 tcgen05 (fp32-equivalent); TF32 "
                          "tcgen05; bf16 tcgen05 with bf16 activation storage (BASELINE configs[2,4])")

@@ -115,7 +115,13 @@ class _DecoderStackFn(torch.autograd.Function):
             call("pase_cast_d2f", acc, small, 4 * C, 1.0)
             grads[3 * i + 2] = small[2 * C:3 * C].clone().view_as(alpha)
             grads[3 * i + 1] = small[3 * C:4 * C].clone()
-            Fn.gemm_tn(plan.dyfull[i], g.s * C, plan.dyfull[i].numel(), plan.xz[i], g.Cin,
+            # dY feeds the weight-gradient and the input-gradient GEMM: one operand conversion
+            dyop = plan.dyfull[i]
+            mode = Fn._MODES[Fn.PRECISION]
+            if mode not in (None, 0) and (g.s * C) % Fn._eb(mode) == 0 and \
+                    g.Cin % Fn._eb(mode) == 0 and (g.taps * g.Cin) % Fn._eb(mode) == 0:
+                dyop = Fn.to_operand(plan.dyfull[i], plan.dyfull[i].numel(), mode, "grad")
+            Fn.gemm_tn(dyop, g.s * C, plan.dyfull[i].numel(), plan.xz[i], g.Cin,
                        plan.xz[i].numel(), plan.dWu[i], g.taps * g.Cin, g.s * C, g.taps * g.Cin,
                        g.U, groups=B, pitchA=g.U, offA=0, pitchB=g.Pd)
             dW = torch.empty_like(W)
@@ -124,9 +130,9 @@ class _DecoderStackFn(torch.autograd.Function):
             grads[3 * i] = dW
             if i > 0 or ctx.needs_input_grad[0]:
                 call("pase_deconv_w_to_bwd", W.reshape(-1), plan.Wb[i], g.Cin, g.Cout, g.k)
-                Fn.gemm_nt(plan.dyfull[i], g.s * C, plan.dyfull[i].numel(), plan.Wb[i], g.k * C,
+                Fn.gemm_nt(dyop, g.s * C, plan.dyfull[i].numel(), plan.Wb[i], g.k * C,
                            plan.Wb[i].numel(), plan.dx[i], g.Cin, B * g.U, g.Cin, g.k * C, None,
-                           g.U, g.T_in, g.T_in)
+                           g.U, g.T_in, g.T_in, a_kind="grad")
                 src = plan.dx[i]
         dx = None
         if ctx.needs_input_grad[0]:

@@ -23,7 +23,10 @@ from . import encoder as _enc
 # fp32 parity bar); "fp32": FFMA kernels; "tf32": single-pass TF32 (L2-equivalent only).
 # Shapes the tensor-core kernels cannot take (channel counts not multiples of 32) fall back
 # to the FFMA kernels per GEMM -- still on the GPU, never to a CPU path.
-DEFAULT_PRECISION = "3xtf32"
+# "auto": 3xF16 (fp32-equivalent products from fp16 operand pairs: half the tensor time and
+# operand bytes of 3xTF32) when every channel count is a multiple of 64 (PASE.cfg, PASE+.cfg),
+# else 3xTF32.  Both meet the fp32 parity bar (tests/test_encoder_gpu.py).
+DEFAULT_PRECISION = "auto"
 
 _DEFAULTS = dict(
     num_inputs=1, sincnet=True,
@@ -173,11 +176,18 @@ class WaveFe(Model):
              "channel counts that are not multiples of 4")
 
     # -- engine plumbing ---------------------------------------------------
+    def resolved_precision(self):
+        if self.precision != "auto":
+            return self.precision
+        wide = all(f % 64 == 0 for f in self.cfg["fmaps"])
+        return "3xf16" if wide else "3xtf32"
+
     def _plan(self, N, T, device):
-        key = (N, T, str(device), self.precision)
+        prec = self.resolved_precision()
+        key = (N, T, str(device), prec)
         plan = self._plans.get(key)
         if plan is None:
-            plan = _enc.EncoderPlan(self.cfg, N, T, device, self.precision)
+            plan = _enc.EncoderPlan(self.cfg, N, T, device, prec)
             self._plans[key] = plan
             while len(self._plans) > self.MAX_PLANS:
                 self._plans.popitem(last=False)

@@ -11,10 +11,11 @@ import torch
 
 from . import ops
 
-# GEMM numerics of the heads (same meaning as WaveFe.precision): "3xtf32" (tcgen05, fp32-
-# equivalent), "tf32", or "fp32" (FFMA kernels).
-PRECISION = os.environ.get("PASE_B200_PRECISION", "3xtf32")
-_MODES = {"fp32": None, "3xtf32": 1, "tf32": 0}
+# GEMM numerics of the heads (same meaning as WaveFe.precision): "3xf16" / "3xtf32" (tcgen05,
+# fp32-equivalent products), "tf32", "bf16" (bf16 operands, fp32 everything else), or "fp32"
+# (FFMA kernels).
+PRECISION = os.environ.get("PASE_B200_PRECISION", "3xf16")
+_MODES = {"fp32": None, "3xtf32": 1, "tf32": 0, "bf16": 2, "3xf16": 3}
 
 
 def set_precision(p):
@@ -28,62 +29,106 @@ def _ru4(n):
     return (n + 3) // 4 * 4
 
 
-def _ru32(n):
-    return (n + 31) // 32 * 32
+def _ru(n, m):
+    return (n + m - 1) // m * m
+
+
+def _eb(mode):
+    """elements per 128-byte TMA row of the GEMM operands"""
+    return 64 if mode in (2, 3) else 32
 
 
 def _pad_ld(n):
-    """leading dimension of a rows-matrix with n columns: tensor-core modes pad to 32 so the
-    matrix can itself be a TMA operand (one folded row = k 128-byte boxes)."""
-    return _ru4(n) if _MODES[PRECISION] is None else _ru32(n)
+    """leading dimension of a rows-matrix with n columns: tensor-core modes pad to one
+    128-byte row so the matrix can itself be a TMA operand."""
+    mode = _MODES[PRECISION]
+    return _ru4(n) if mode is None else _ru(n, _eb(mode))
 
 
-def _split_act(flat, n, mode):
-    if mode != 1:
-        return flat, None
-    lo = torch.empty(n, dtype=torch.float32, device=flat.device)
-    ops.call("pase_split_tf32", flat, None, lo, n)
-    return flat, lo
+class Operand(object):
+    """A GEMM operand converted to the current mode's format: hi / lo tensors + the device
+    scalar that undoes a gradient's power-of-two scale (3xF16)."""
+    __slots__ = ("hi", "lo", "alpha")
+
+    def __init__(self, hi, lo=None, alpha=None):
+        self.hi, self.lo, self.alpha = hi, lo, alpha
 
 
-def _split_w(flat, n, mode):
-    if mode != 1:
-        return flat, None
-    hi = torch.empty(n, dtype=torch.float32, device=flat.device)
-    lo = torch.empty(n, dtype=torch.float32, device=flat.device)
-    ops.call("pase_split_tf32", flat, hi, lo, n)
-    return hi, lo
+def to_operand(flat, n, mode, kind="act"):
+    """flat: fp32 1-D view (>= n elements).  kind: 'act' | 'weight' | 'grad'."""
+    if isinstance(flat, Operand):
+        return flat
+    dev = flat.device
+    if mode == 0:
+        return Operand(flat)
+    if mode == 1:
+        lo = torch.empty(n, dtype=torch.float32, device=dev)
+        if kind == "weight":
+            hi = torch.empty(n, dtype=torch.float32, device=dev)
+            ops.call("pase_split_tf32", flat, hi, lo, n)
+            return Operand(hi, lo)
+        ops.call("pase_split_tf32", flat, None, lo, n)
+        return Operand(flat, lo)
+    if mode == 2:
+        hi = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        ops.call("pase_cast_bf16", flat, hi, n)
+        return Operand(hi)
+    hi = torch.empty(n, dtype=torch.float16, device=dev)
+    lo = torch.empty(n, dtype=torch.float16, device=dev)
+    if kind == "grad":
+        amax = torch.zeros(2, dtype=torch.float32, device=dev)
+        scale = torch.empty(2, dtype=torch.float32, device=dev)
+        ops.call("pase_absmax", flat, n, amax)
+        ops.call("pase_split_f16", flat, hi, lo, n, amax, scale)
+        return Operand(hi, lo, scale)
+    ops.call("pase_split_f16", flat, hi, lo, n, None, None)
+    return Operand(hi, lo)
 
 
 def gemm_nt(A, lda, a_used, B, ldb, b_used, C, ldc, M, N, K, bias, rows_in=None, t_valid=None,
-            rows_out=None):
+            rows_out=None, a_kind="act"):
     """C[map(m),n] = sum_k A[m*lda+k] B[n*ldb+k] + bias[n]; dispatches tcgen05 / FFMA.
-    Optional row map (rows_in, t_valid, rows_out) as in pase_gemm_nt."""
+    Optional row map (rows_in, t_valid, rows_out) as in pase_gemm_nt.  A / B may be fp32 flat
+    views or already-converted Operands."""
     mode = _MODES[PRECISION]
     if rows_in is None:
         rows_in = t_valid = rows_out = M
-    if mode is None or lda % 32 != 0 or K % 4 != 0 or ldb % 4 != 0:
+    esz = 2 if mode in (2, 3) else 4
+    if mode is None or lda % _eb(mode) != 0 or (K * esz) % 16 != 0 or (ldb * esz) % 16 != 0:
+        assert not isinstance(A, Operand) and not isinstance(B, Operand)
         return ops.call("pase_gemm_nt", A, lda, B, ldb, C, ldc, M, N, K, 1.0, bias,
                         rows_in, t_valid, rows_out, 1, None, None, 0)
-    Ah, Al = _split_act(A, a_used, mode)
-    Bh, Bl = _split_w(B, b_used, mode)
-    return ops.call("pase_tc_gemm_nt", Ah, Al, a_used // lda, lda, Bh, Bl, ldb, C, ldc, M, N, K,
-                    1.0, None, bias, rows_in, t_valid, rows_out, 1, None, None, 0, mode, 0)
+    a = to_operand(A, a_used, mode, a_kind)
+    b = to_operand(B, b_used, mode, "weight")
+    return ops.call("pase_tc_gemm_nt", a.hi, a.lo, a_used // lda, lda, b.hi, b.lo, ldb, C, ldc,
+                    M, N, K, 1.0, a.alpha, bias, rows_in, t_valid, rows_out, 1, None, None, 0,
+                    mode, 0)
 
 
 def gemm_tn(A, lda, a_used, B, ldb, b_used, C, ldc, I, J, rows, groups=1, pitchA=None, offA=0,
-            pitchB=None):
+            pitchB=None, a_kind="grad"):
     """C[i,j] = sum_r A[rowA(r)*lda+i] B[rowB(r)*ldb+j] over `groups` x `rows` rows."""
     mode = _MODES[PRECISION]
     pitchA = rows if pitchA is None else pitchA
     pitchB = rows if pitchB is None else pitchB
-    if mode is None or ldb % 32 != 0 or lda % 4 != 0 or I % 4 != 0 or J % 32 != 0:
+    esz = 2 if mode in (2, 3) else 4
+    if mode is None or ldb % _eb(mode) != 0 or (lda * esz) % 16 != 0 or I % 4 != 0 or \
+            J % _eb(mode) != 0:
+        assert not isinstance(A, Operand) and not isinstance(B, Operand)
         return ops.call("pase_gemm_tn", A, lda, pitchA, offA, B, ldb, pitchB, 0, C, ldc, I, J,
                         groups, rows, 1.0, 0)
-    Ah, Al = _split_act(A, a_used, mode)
-    Bh, Bl = _split_act(B, b_used, mode)
-    return ops.call("pase_tc_gemm_tn", Ah, Al, lda, pitchA, offA, Bh, Bl, ldb, pitchB,
-                    b_used // ldb, C, ldc, I, J, groups, rows, 1.0, None, 0, mode)
+    a = to_operand(A, a_used, mode, a_kind)
+    b = to_operand(B, b_used, mode, "act")
+    return ops.call("pase_tc_gemm_tn", a.hi, a.lo, lda, pitchA, offA, b.hi, b.lo, ldb, pitchB,
+                    b_used // ldb, C, ldc, I, J, groups, rows, 1.0, a.alpha, 0, mode)
+
+
+def tc_shapes_ok(lda, K, ldb):
+    """True when gemm_nt would take the tensor-core path in the current mode."""
+    mode = _MODES[PRECISION]
+    esz = 2 if mode in (2, 3) else 4
+    return mode is not None and lda % _eb(mode) == 0 and (K * esz) % 16 == 0 and \
+        (ldb * esz) % 16 == 0
 
 
 def _rows_ld(x):
@@ -123,9 +168,9 @@ class _LinearRows(torch.autograd.Function):
         assert w2.shape[1] == K and K % 4 == 0, "in-features %d must match and be a multiple of 4" % K
         w2 = w2.contiguous()
         ldo = _pad_ld(N)
-        # +32 floats of slack: the tensor-core weight-gradient kernel reads whole 32-column
-        # blocks of dY
-        buf = torch.empty(rows * ldo + 32, dtype=torch.float32, device=x.device)
+        # +64 floats of slack: the tensor-core weight-gradient kernel reads whole 128-byte
+        # column blocks of dY
+        buf = torch.empty(rows * ldo + 64, dtype=torch.float32, device=x.device)
         out = buf[:rows * ldo].view(rows, ldo)
         buf[rows * ldo:].zero_()
         if ldo != N:
@@ -144,17 +189,22 @@ class _LinearRows(torch.autograd.Function):
         N, ldx, ldo = ctx.N, ctx.ldx, ctx.ldo
         assert dy.shape == (rows, ldo)
         dev = x.device
-        dyb = torch.empty(rows * ldo + 32, dtype=torch.float32, device=dev)
+        dyb = torch.empty(rows * ldo + 64, dtype=torch.float32, device=dev)
         dyb[:rows * ldo].view(rows, ldo).copy_(dy)
         dyb[rows * ldo:].zero_()
         dyf = dyb
+        mode = _MODES[PRECISION]
+        # dY feeds both backward GEMMs: convert it to the operand format once
+        if mode is not None and mode != 0 and tc_shapes_ok(ldo, ldo, ldo) and \
+                ldx % _eb(mode) == 0 and K % _eb(mode) == 0 and ldo % 4 == 0:
+            dyf = to_operand(dyb, rows * ldo + 64, mode, "grad")
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             wT = torch.empty(K, ldo, dtype=torch.float32, device=dev)
             ops.call("pase_transpose_pad", w2.reshape(-1), K, wT.reshape(-1), ldo, N, K)
             dx = torch.empty(rows, K, dtype=torch.float32, device=dev)
             gemm_nt(dyf, ldo, rows * ldo, wT.reshape(-1), ldo, K * ldo, dx.reshape(-1), K,
-                    rows, K, ldo, None)
+                    rows, K, ldo, None, a_kind="grad")
         if ctx.needs_input_grad[1]:
             dWp = torch.empty(ldo, K, dtype=torch.float32, device=dev)
             gemm_tn(dyf, ldo, rows * ldo, _flat_from(x), ldx, rows * ldx, dWp.reshape(-1), K,
