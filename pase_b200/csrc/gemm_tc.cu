@@ -217,6 +217,16 @@ __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map,
       "l"(0x1000000000000000ull)
       : "memory");
 }
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map,
+                                             uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "l"(0x1000000000000000ull)
+      : "memory");
+}
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* slot) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -1141,6 +1151,196 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ TN kernel, CTA pair ----
+// Same contract as tc_gemm_tn_kernel for I >= 256: a cluster of two CTAs computes a 256 (I) x
+// BN (J) tile with tcgen05.mma.cta_group::2.  CTA rank r loads the A columns [i0 + 128 r,
+// +128) (BM/EB MN-blocks) and ONE half of B's BN columns ([j0 + r BN/2, + BN/2)) of every
+// reduction chunk; barriers as in tc_gemm_nt2_kernel (transaction bytes on the leader's
+// `full`, multicast commits, the leader's `acc_empty` counts both CTAs' epilogue warps).
+// Operand bytes read from shared memory per MMA: 6 KB instead of 8 KB per SM, and 25 % fewer
+// bytes through TMA / L2 per flop.
+template <int BN, int MODE>
+struct TN2Cfg {
+  using MT = ModeT<MODE>;
+  static constexpr int EB = MT::EB;
+  static constexpr int KR = 4 * MT::UMMA_K;
+  static constexpr int BH = BN / 2;                        // B columns held by one CTA
+  static constexpr int A_BYTES = KR * BM * MT::ESZ;
+  static constexpr int B_BYTES = KR * BH * MT::ESZ;
+  static constexpr int STAGE_BYTES = (MT::SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);   // per CTA
+  static constexpr int ACC_COLS = MT::NACC * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static constexpr int EPI_ACTIVE = 4 * (BN / 32);
+  static constexpr int LAYOUT = MT::ESZ == 4 ? 1 : 2;
+  static constexpr int SBO = MT::ESZ == 4 ? 512 : 1024;
+  static constexpr int LBO = KR * 128;
+  static constexpr int KSTEP_DESC = (MT::UMMA_K * 128) >> 4;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
+  static_assert(BH % EB == 0, "each CTA's B half must be whole 128-byte MN blocks");
+};
+
+template <int BN, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS_V3, 1)
+tc_gemm_tn2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                   const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
+                   const TNArgs a) {
+  using Cfg = TN2Cfg<BN, MODE>;
+  using MT = ModeT<MODE>;
+  constexpr int KR = Cfg::KR, EB = Cfg::EB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int stages = a.stages;
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_full = empty_bar + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_out = reinterpret_cast<float*>(smem + stages * Cfg::STAGE_BYTES + BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int R = a.R;
+  const int j0 = (blockIdx.x >> 1) * BN, i0 = blockIdx.y * (2 * BM) + (int)rank * BM;
+  const int cpg = (a.rows_per_group + KR - 1) / KR;           // chunks per group
+  const long total_chunks = (long)a.groups * cpg;
+  const long c_begin = (long)blockIdx.z * a.chunks_per_split;
+  long c_end = c_begin + a.chunks_per_split;
+  if (c_end > total_chunks) c_end = total_chunks;
+  const int nch = (int)(c_end - c_begin);                    // identical in both CTAs
+  int flush_ch = a.flush_ch;
+  if (flush_ch <= 0 || flush_ch > nch) flush_ch = nch > 0 ? nch : 1;
+  const int nflush = (nch + flush_ch - 1) / flush_ch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * Cfg::EPI_ACTIVE);
+    }
+    fence_barrier_init();
+    tmap_prefetch(&mAhi);
+    tmap_prefetch(&mBhi);
+  }
+  if (warp == 1) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // this CTA's half of the B tile: columns [j0 + rank*BH, +BH)
+  const int jb = j0 + (int)rank * Cfg::BH;
+  const int jq = jb / R, jc = jb % R;
+
+  if (nch > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int s = -1;
+        uint32_t ph = 1;
+        for (int it = 0; it < nch; ++it) {
+          if (++s == stages || it == 0) {
+            s = 0;
+            ph ^= 1;
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1, 31);
+          const long ch = c_begin + it;
+          const int g = (int)(ch / cpg);
+          const int u0 = (int)(ch - (long)g * cpg) * KR;
+          uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          uint8_t* a_hi = st;
+          uint8_t* b_hi = st + Cfg::A_BYTES;
+          uint8_t* a_lo = b_hi + Cfg::B_BYTES;
+          uint8_t* b_lo = a_lo + Cfg::A_BYTES;
+          tma2_load_4d(a_hi, &mAhi, fb, 0, u0, i0 / EB, g);
+          if (MT::SPLIT) tma2_load_4d(a_lo, &mAlo, fb, 0, u0, i0 / EB, g);
+#pragma unroll
+          for (int nb = 0; nb < Cfg::BH / EB; ++nb) {
+            // EB consecutive columns never straddle a folded row (R % EB == 0)
+            const int col = jc + nb * EB;
+            const int qq = jq + col / R, cc = col % R;
+            tma2_load_4d(b_hi + nb * KR * 128, &mBhi, fb, 0, u0 + qq, cc / EB, g);
+            if (MT::SPLIT) tma2_load_4d(b_lo + nb * KR * 128, &mBlo, fb, 0, u0 + qq, cc / EB, g);
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (leader) {
+        constexpr uint32_t idesc = make_idesc(2 * BM, BN, 1, 1, MT::FMT);
+        const uint64_t dconst = desc_hi_bits<Cfg::LAYOUT>((uint32_t)a.lbo, (uint32_t)a.sbo);
+        const uint32_t tiles_u32 = smem_u32(tiles);
+        const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int f = 0; f < nflush; ++f) {
+          const uint32_t b = f & 1, aph = (f >> 1) & 1;
+          mbar_wait(&acc_empty[b], aph ^ 1, 34);
+          tc_fence_after();
+          const uint32_t d_tmem = tm0 + b * Cfg::ACC_COLS;
+          const int it_lo = f * flush_ch;
+          const int it_hi = (it_lo + flush_ch < nch) ? it_lo + flush_ch : nch;
+          for (int it = it_lo; it < it_hi; ++it) {
+            mbar_wait(&full_bar[s], ph, 32);
+            tc_fence_after();
+            const uint64_t dah = dconst + ((tiles_u32 + s * Cfg::STAGE_BYTES) >> 4);
+            const uint64_t dbh = dah + (Cfg::A_BYTES >> 4);
+            const uint64_t dal = dbh + (Cfg::B_BYTES >> 4);
+            const uint64_t dbl = dal + (Cfg::A_BYTES >> 4);
+            issue_kblock<MODE, 2, 4, Cfg::KSTEP_DESC>(d_tmem, BN, dah, dbh, dal, dbl, idesc,
+                                                      (it == it_lo) ? 0u : 1u);
+            umma2_commit_mc_w(&empty_bar[s]);
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+          umma2_commit_mc_w(&acc_full[b]);
+        }
+      }
+      __syncwarp();
+    } else {
+      const int e = warp - 2;
+      const int q = warp & 3;
+      const int cc = e >> 2;
+      if (cc < BN / 32) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+        const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
+        float sums[32];
+        for (int f = 0; f < nflush; ++f) {
+          const uint32_t b = f & 1, aph = (f >> 1) & 1;
+          mbar_wait(&acc_full[b], aph, 33);
+          tc_fence_after();
+          fold_chunk<MODE>(taddr + b * Cfg::ACC_COLS, BN, sums, f == 0);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(acc_empty0 + b * 8);
+        }
+        const int i = i0 + q * 32 + lane;
+        const bool vec_ok = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0);
+        const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sums[j] *= alpha;
+        store_chunk<true>(s_out + e * OUT_STG_FLOATS, sums, lane, a.C, a.ldc, (long)i,
+                          i < a.I ? a.J : 0, j0 + cc * 32, vec_ok, 0);
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------ host side ----
 static bool pase_tc_use_2cta() {
   static int v = -1;
@@ -1353,6 +1553,51 @@ int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   return PASE_OK;
 }
 
+template <int BN, int MODE>
+int launch_tn2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+               const CUtensorMap& bl, TNArgs a, cudaStream_t st) {
+  using Cfg = TN2Cfg<BN, MODE>;
+  static bool attr = false;
+  a.stages = pick_stages(Cfg::STAGE_BYTES, 0);
+  a.lbo = Cfg::LBO;
+  a.sbo = Cfg::SBO;
+  const int smem = smem_bytes(a.stages, Cfg::STAGE_BYTES, 0);
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn2_kernel<BN, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      pase_set_error("pase_tc_gemm_tn (2-CTA): smem attribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr = true;
+  }
+  const int ti = (a.I + 2 * BM - 1) / (2 * BM), tj = (a.J + BN - 1) / BN;
+  const int cpg = (a.rows_per_group + Cfg::KR - 1) / Cfg::KR;
+  const long total = (long)a.groups * cpg;
+  // one CTA pair per (tile, split): fill whole waves of the SM pairs (see launch_tn)
+  const long tiles = (long)ti * tj;
+  const int pairs = pase_num_sms() / 2;
+  long best = 1;
+  double best_eff = -1.0;
+  for (long sp = 1; sp <= total && sp * tiles <= 4L * pairs; ++sp) {
+    const long cps_try = (total + sp - 1) / sp;
+    if (cps_try < 8 && sp > 1) break;
+    const long ctas = tiles * ((total + cps_try - 1) / cps_try);
+    const long waves = (ctas + pairs - 1) / pairs;
+    const double cost = (double)waves * (double)(cps_try + 6);
+    const double eff = 1.0 / cost;
+    if (eff > best_eff) { best_eff = eff; best = sp; }
+  }
+  long splits = best;
+  long cps = (total + splits - 1) / splits;
+  splits = (total + cps - 1) / cps;
+  a.chunks_per_split = (int)cps;
+  dim3 grid(2 * tj, ti, (unsigned)splits);               // cluster (2,1,1) along x
+  tc_gemm_tn2_kernel<BN, MODE><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_TC_LAUNCH_CHECK("pase_tc_gemm_tn(2cta)");
+  return PASE_OK;
+}
+
 // tf32 helpers: the tensor core reads the upper 19 bits of an fp32 operand (truncation).
 __device__ __forceinline__ float tf32_trunc(float v) {
   return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -1556,7 +1801,15 @@ int pase_tc_gemm_tn(const void* Ahi, const void* Alo, long lda, int pitchA, int 
   // B group g covers folded rows [g*pitchB, ...): rows beyond the allocation are zero-filled
   long rows_in_group = b_rows_total - (long)(groups - 1) * pitchB;
   if (rows_in_group > pitchB + (J + R - 1) / R + 1) rows_in_group = pitchB + (J + R - 1) / R + 1;
-  const int b_blocked = (R % BN) == 0;
+  // CTA pair (M = 256) for tall outputs in the 16-bit modes; every CTA then loads ONE half
+  // of the B tile, block by block (PASE_B200_TN_2CTA=0 disables, =2 also enables fp32 modes)
+  static int tn2 = -1;
+  if (tn2 < 0) {
+    const char* e = getenv("PASE_B200_TN_2CTA");
+    tn2 = e ? atoi(e) : 1;
+  }
+  const bool pair = BN == 128 && I >= 256 && tn2 > 0 && (mode >= 2 || tn2 >= 2) && pase_tc_use_2cta();
+  const int b_blocked = !pair && (R % BN) == 0;
   uint64_t bdims[4] = {(uint64_t)eb, (uint64_t)rows_in_group, (uint64_t)(R / eb),
                        (uint64_t)groups};
   uint64_t bstr[3] = {(uint64_t)R * esz, 128, (uint64_t)pitchB * R * esz};
@@ -1590,6 +1843,14 @@ int pase_tc_gemm_tn(const void* Ahi, const void* Alo, long lda, int pitchA, int 
     default: return launch_tn<BNV, 3>(ah, al, bh, bl, a, st);             \
   }
   if (BN == 64) { PASE_TN(64) }
+  if (pair) {
+    switch (mode) {
+      case 0: return launch_tn2<128, 0>(ah, al, bh, bl, a, st);
+      case 1: return launch_tn2<128, 1>(ah, al, bh, bl, a, st);
+      case 2: return launch_tn2<128, 2>(ah, al, bh, bl, a, st);
+      default: return launch_tn2<128, 3>(ah, al, bh, bl, a, st);
+    }
+  }
   PASE_TN(128)
 #undef PASE_TN
 }

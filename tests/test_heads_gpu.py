@@ -66,3 +66,75 @@ def test_spc_worker_runs_and_matches_oracle_math():
     ref = torch.nn.functional.binary_cross_entropy_with_logits(
         yr, torch.cat([torch.ones(3, 1, 1), torch.zeros(3, 1, 1)], 0))
     assert_close(loss, ref, 1e-4, 1e-6, "spc bce")
+
+
+def _workers_plus_cfg():
+    mlp = lambda name, nout: {"num_outputs": nout, "dropout": 0, "hidden_size": 256,
+                              "hidden_layers": 1, "name": name, "context": 1, "r": 7,
+                              "loss": "MSELoss", "skip": False}
+    regr = [{"num_outputs": 1, "dropout": 0, "dropout_time": 0.0, "hidden_layers": 1,
+             "name": "cchunk", "type": "decoder", "hidden_size": 64, "fmaps": [512, 256, 128],
+             "strides": [4, 4, 10], "kwidths": [30, 30, 30], "loss": "L1Loss"}]
+    for name, nout in (("lps", 3075), ("lps_long", 3075), ("fbank", 120), ("fbank_long", 120),
+                       ("gtn", 120), ("gtn_long", 120), ("mfcc", 39), ("mfcc_long", 60),
+                       ("prosody", 12)):
+        regr.append(mlp(name, nout))
+    cls = [{"num_outputs": 1, "dropout": 0, "hidden_size": 256, "hidden_layers": 1, "name": n,
+            "loss": "BCEWithLogitsLoss", "skip": False, "augment": n == "cmi"}
+           for n in ("mi", "cmi")]
+    return {"regr": regr, "cls": cls}
+
+
+@pytest.mark.parametrize("precision", ["3xf16", "3xtf32"])
+def test_workers_plus_full_length_against_oracle(precision):
+    """BASELINE.json configs[2]/[3] model (PASE+.cfg + all 12 workers+ heads) at the real
+    chunk length T=32000 (T'=200), B=4 chunk triplets: every loss and the summed loss against
+    the CPU oracle (fp32 bar), every parameter gradient in relative L2 (the L1-driven decoder
+    path, sign(pred-target), only through its norm)."""
+    import copy
+    from helpers import resolve_cfg, fill_state_dict, rel_l2
+    from pase_b200.pase import pase as native_pase, total_loss
+    from pase_b200.utils import parse_workers
+    from pase_b200 import functional as Fn
+    fe_cfg, wcfg = resolve_cfg("cfg/frontend/PASE+.cfg"), _workers_plus_cfg()
+    B, T, Tq, seed = 4, 32000, 200, 71
+    prev = Fn.PRECISION
+    Fn.set_precision(precision)
+    try:
+        model = native_pase(frontend_cfg=fe_cfg, minions_cfg=parse_workers(copy.deepcopy(wcfg)))
+        sd = fill_state_dict(model.state_dict(), seed)
+        model.load_state_dict(sd)
+        model.frontend.precision = precision
+        model = model.cuda().train()
+        batch = {k: seeded_randn((B, 1, T), seed + 10 + i, 0.5)
+                 for i, k in enumerate(["chunk", "chunk_ctxt", "chunk_rand", "cchunk"])}
+        for i, w in enumerate(wcfg["regr"]):
+            if w["name"] != "cchunk":
+                batch[w["name"]] = seeded_randn((B, w["num_outputs"], Tq), seed + 100 + i)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+                  if v.is_floating_point() and "running" not in k}
+        full = dict(sd)
+        full.update(leaves)
+        _, chunk_r, preds_r, labels_r = O.pase_forward(batch, full, fe_cfg, wcfg, training=True)
+        tot_r, per_r = O.total_loss(preds_r, labels_r, wcfg)
+        tot_r.backward()
+        h, chunk, preds, labels = model({k: v.cuda() for k, v in batch.items()}, 1, "cuda")
+        assert_close(chunk, chunk_r, 1e-3, 1e-5, "chunk")
+        tot, per = total_loss(model, preds, labels)
+        for k, v in per.items():
+            assert_close(v, per_r[k], 2e-4, 1e-6, "loss " + k)
+        assert_close(tot, tot_r, 2e-4, 1e-6, "total")
+        assert tuple(preds["lps"].shape) == (B, 21525, Tq)
+        tot.backward()
+        bad = []
+        for k, p in model.named_parameters():
+            ref = leaves[k].grad
+            if k.startswith("frontend.") and (k.endswith("conv.bias") or k.endswith("W.bias")):
+                continue                                  # analytically zero under train-mode BN
+            r = rel_l2(p.grad.cpu(), ref)
+            lim = 2e-2 if (k.startswith("regression_workers.0.") or "_hz_" in k) else 3e-3
+            if r >= lim:
+                bad.append("%s %.2e" % (k, r))
+        assert not bad, "; ".join(bad[:10])
+    finally:
+        Fn.set_precision(prev)
