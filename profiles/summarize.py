@@ -101,5 +101,44 @@ def full(src, dst):
     print("wrote", dst)
 
 
+def traffic(src, dst, precision=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum of every GEMM launch in an `ncu --set full`
+    capture -> profiles/r02_gemm_traffic.json[precision] (bench.py's roofline.traffic)."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    ti = hdr.index("gpu__time_duration.sum")
+
+    def to_bytes(v, u):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    per, tot, n = {}, 0.0, 0
+    for r in rows[2:]:
+        k = _short(r[ki])
+        if "gemm" not in k:
+            continue
+        b = to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi])
+        e = per.setdefault(k, {"launches": 0, "dram_bytes": 0.0, "time_%s" % units[ti]: 0.0})
+        e["launches"] += 1
+        e["dram_bytes"] += b
+        e["time_%s" % units[ti]] += float(r[ti].replace(",", ""))
+        tot += b
+        n += 1
+    data = json.load(open(dst)) if os.path.exists(dst) else {}
+    data[precision or "default"] = {
+        "source": src, "gemm_launches": n, "dram_bytes_total": tot,
+        "dram_bytes_per_launch": tot / max(n, 1), "per_kernel": per,
+        "how": "ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum "
+               "summed over the GEMM launches captured (whole steps), divided by their count"}
+    json.dump(data, open(dst, "w"), indent=1)
+    print("wrote", dst, precision, "%.1f MB per launch over %d launches" % (tot / max(n, 1) / 1e6, n))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    fn = {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]]
+    fn(*sys.argv[2:])
