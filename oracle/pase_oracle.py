@@ -82,9 +82,10 @@ def sinc_filters(low_hz_, band_hz_, k=251, sr=16000, min_low=50., min_band=50.):
     """(C,1),(C,1) -> (C,1,k) band-pass bank.  modules.py:868-918."""
     half = k // 2
     dev = low_hz_.device
-    n_lin = torch.linspace(0, (k / 2) - 1, steps=half, device=dev)
+    dt = low_hz_.dtype
+    n_lin = torch.linspace(0, (k / 2) - 1, steps=half, device=dev, dtype=dt)
     window = 0.54 - 0.46 * torch.cos(2 * math.pi * n_lin / k)
-    n_ = 2 * math.pi * torch.arange(-(k - 1) / 2.0, 0, device=dev).view(1, -1) / sr
+    n_ = 2 * math.pi * torch.arange(-(k - 1) / 2.0, 0, device=dev, dtype=dt).view(1, -1) / sr
     low = min_low + low_hz_.abs()
     high = torch.clamp(low + min_band + band_hz_.abs(), min_low, sr / 2)
     band = (high - low)[:, 0]
