@@ -65,15 +65,28 @@ KEYS = [
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem wavefronts %"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1/TEX %"),
     ("launch__registers_per_thread", "regs"),
     ("launch__shared_mem_per_block_dynamic", "dyn smem"),
 ]
 
 
-def full(src, dst):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
+def _raw_rows(src):
+    """rows of `ncu --page raw --csv`: from a .ncu-rep, or from a .csv already exported on the
+    GPU box (reports with --import-source are too large to bring back)."""
+    if src.endswith(".csv"):
+        raw = open(src, errors="ignore").read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
+    hi = next(i for i, r in enumerate(rows) if len(r) > 5 and r[0] == "ID")
+    return rows[hi:]
+
+
+def full(src, dst):
+    rows = _raw_rows(src)
     hdr, units = rows[0], rows[1]
     col = {}
     for key, _ in KEYS:
@@ -106,9 +119,7 @@ def traffic(src, dst, precision=None):
     capture -> profiles/r02_gemm_traffic.json[precision] (bench.py's roofline.traffic)."""
     import json
     import os
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = _raw_rows(src)
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
     ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
