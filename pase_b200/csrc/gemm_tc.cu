@@ -1978,7 +1978,7 @@ int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const 
   static int use_win = -1;
   if (use_win < 0) {
     const char* e = getenv("PASE_B200_TC_WINDOW");
-    use_win = e ? atoi(e) : 1;
+    use_win = e ? atoi(e) : 0;
   }
   const int qmax = (K + R - 1) / R;
   const int win_rows = ((BM + qmax - 1 + 7) / 8) * 8;
