@@ -1,10 +1,11 @@
 // Padding, BatchNorm (batch statistics), PReLU and dense-skip pooling kernels.
 // All HBM-bound: channel-last float4 accesses, one pass per tensor.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int RUN = 8;      // consecutive time steps handled by one thread
+constexpr int RUN8 = 8;     // consecutive time steps handled by one thread (RUN template values)
 constexpr int THREADS = 256;
 
 // DF: operand format of the padded waveform (block 0's GEMM operand)
@@ -84,7 +85,7 @@ __device__ __forceinline__ float prelu1(float u, float a) { return u > 0.f ? u :
 //   PASE_FMT_F32 (+ optional tf32-residual twin dst_lo), PASE_FMT_BF16, PASE_FMT_F16X2
 //   (dst = hi, dst_lo = lo').  The dense-skip pool accumulates the value the next layer
 //   reads (i.e. after rounding to bf16 in the bf16 format).
-template <typename YT, int DF>
+template <typename YT, int DF, int RUN>
 __global__ void __launch_bounds__(THREADS)
 bn_prelu_pad_fwd_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
                         const float* __restrict__ scale, const float* __restrict__ shift,
@@ -168,8 +169,8 @@ struct BwdSrc {
 // next layer's input gradient as its dgrad GEMM wrote it).  amax (optional, float[2]):
 // running maxima of |du| and |xhat| (bit-pattern atomicMax), from which pass 2 derives the
 // power-of-two scale of the fp16 gradient operand (3xF16 mode).
-template <typename YT, typename GT>
-__global__ void __launch_bounds__(THREADS)
+template <typename YT, typename GT, int RUN>
+__global__ void __launch_bounds__(THREADS, RUN <= 4 ? 2 : 1)
 bn_prelu_bwd_reduce_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
                            const float* __restrict__ mean, const float* __restrict__ invstd,
                            const float* __restrict__ scale, const float* __restrict__ shift,
@@ -319,8 +320,8 @@ bn_prelu_bwd_reduce_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
 //     |dy| <= max_c |gamma_c invstd_c| (max|du| + |S1_c/M| + max|xhat| |S2_c/M|)
 // (amax from pass 1), every block computes the same scale; block (0,0) publishes
 // scale_out = {1/s, s} for the consuming GEMMs (alpha_dev).
-template <typename YT, int DF>
-__global__ void __launch_bounds__(THREADS)
+template <typename YT, int DF, int RUN>
+__global__ void __launch_bounds__(THREADS, RUN <= 4 ? 3 : 2)
 bn_prelu_bwd_apply_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ gamma, const double* __restrict__ S1,
@@ -619,6 +620,17 @@ __global__ void scale_dev_kernel(float* __restrict__ x, long n, const float* __r
     x[i] *= f;
 }
 
+// time steps per thread of the BatchNorm / PReLU passes: 4 (more resident blocks per SM: the
+// mid-layer launches are latency-bound) or 8; PASE_B200_BN_RUN overrides
+inline int bn_run() {
+  static int r = 0;
+  if (r == 0) {
+    const char* e = getenv("PASE_B200_BN_RUN");
+    r = (e && atoi(e) == 8) ? 8 : 4;
+  }
+  return r;
+}
+
 inline unsigned blocks_for(long total, int threads, int cap_mult = 8) {
   long b = (total + threads - 1) / threads;
   long cap = (long)pase_num_sms() * cap_mult;
@@ -694,14 +706,16 @@ int pase_bn_prelu_pad_fwd(const void* y, int y_bf16, long y_sample_stride, int N
                  "pase_bn_prelu_pad_fwd: bad dst_fmt %d / missing lo", dst_fmt);
   if (pool == nullptr) pool_d = 0;
   const int Tp = T + padL + padR;
+  const int RUN = bn_run();
   const long threads = (long)(C / 4) * ((Tp + RUN - 1) / RUN);
   dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
   cudaStream_t st = (cudaStream_t)stream;
-#define PASE_FWD(YT, DF)                                                                       \
-  bn_prelu_pad_fwd_kernel<YT, DF><<<grid, THREADS, 0, st>>>(                                   \
+#define PASE_FWD_R(YT, DF, RV)                                                                 \
+  bn_prelu_pad_fwd_kernel<YT, DF, RV><<<grid, THREADS, 0, st>>>(                               \
       reinterpret_cast<const YT*>(y), y_sample_stride, T, C, scale, shift, alpha, dst,         \
       dst_sample_stride, dst_row_stride, padL, Tp, pool, pool_sample_stride, pool_row_stride, \
       pool_d, pool_T, dst_lo)
+#define PASE_FWD(YT, DF) do { if (RUN == 8) PASE_FWD_R(YT, DF, 8); else PASE_FWD_R(YT, DF, 4); } while (0)
   if (y_bf16) {
     if (dst_fmt == PASE_FMT_F32) PASE_FWD(__nv_bfloat16, PASE_FMT_F32);
     else if (dst_fmt == PASE_FMT_BF16) PASE_FWD(__nv_bfloat16, PASE_FMT_BF16);
@@ -712,6 +726,7 @@ int pase_bn_prelu_pad_fwd(const void* y, int y_bf16, long y_sample_stride, int N
     else PASE_FWD(float, PASE_FMT_F16X2);
   }
 #undef PASE_FWD
+#undef PASE_FWD_R
   PASE_LAUNCH_CHECK("pase_bn_prelu_pad_fwd");
   return PASE_OK;
 }
@@ -732,20 +747,22 @@ int pase_bn_prelu_bwd_reduce(const void* y, int y_bf16, long y_sample_stride, in
                  "pase_bn_prelu_bwd_reduce: C=%d must be a multiple of 4, <= 4096", C);
   BwdSrc s{srcA, a_sample_stride, a_row_stride, padL, padR, srcB, b_sample_stride, b_row_stride,
            b_shift, pool, pool_sample_stride, pool_row_stride, pool ? pool_d : 0, pool_T};
+  const int RUN = bn_run();
   const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
   long gx = (threads + THREADS - 1) / THREADS;
   if ((THREADS % (C / 4)) == 0) {          // stride keeps the channel quad: cap the grid
-    long cap = (8L * pase_num_sms() + N - 1) / N;
+    long cap = ((RUN == 8 ? 8L : 16L) * pase_num_sms() + N - 1) / N;
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
   }
   dim3 grid((unsigned)gx, N);
   const size_t sm = (3 * C + 2) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define PASE_RED(YT, GT)                                                                     \
-  bn_prelu_bwd_reduce_kernel<YT, GT><<<grid, THREADS, sm, st>>>(                             \
+#define PASE_RED_R(YT, GT, RV)                                                               \
+  bn_prelu_bwd_reduce_kernel<YT, GT, RV><<<grid, THREADS, sm, st>>>(                         \
       reinterpret_cast<const YT*>(y), y_sample_stride, T, C, mean, invstd, scale, shift,     \
       alpha, s, reinterpret_cast<YT*>(dst), dst_sample_stride, S1, S2, dalpha, amax)
+#define PASE_RED(YT, GT) do { if (RUN == 8) PASE_RED_R(YT, GT, 8); else PASE_RED_R(YT, GT, 4); } while (0)
   if (y_bf16) {
     if (a_bf16) PASE_RED(__nv_bfloat16, __nv_bfloat16);
     else PASE_RED(__nv_bfloat16, float);
@@ -754,6 +771,7 @@ int pase_bn_prelu_bwd_reduce(const void* y, int y_bf16, long y_sample_stride, in
     else PASE_RED(float, float);
   }
 #undef PASE_RED
+#undef PASE_RED_R
   PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_reduce");
   return PASE_OK;
 }
@@ -774,25 +792,28 @@ int pase_bn_prelu_bwd_apply(const void* y, int y_bf16, long y_sample_stride, int
                  "and fp32 y/du");
   PASE_CHECK_ARG((dst_fmt == PASE_FMT_BF16) == (y_bf16 != 0),
                  "pase_bn_prelu_bwd_apply: bf16 y/du goes with bf16 dst (and only with it)");
+  const int RUN = bn_run();
   const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
   long gx = (threads + THREADS - 1) / THREADS;
   if ((THREADS % (C / 4)) == 0) {
-    long cap = (8L * pase_num_sms() + N - 1) / N;
+    long cap = ((RUN == 8 ? 8L : 16L) * pase_num_sms() + N - 1) / N;
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
   }
   dim3 grid((unsigned)gx, N);
   const size_t sm = (C + 1) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define PASE_APP(YT, DF)                                                                      \
-  bn_prelu_bwd_apply_kernel<YT, DF><<<grid, THREADS, sm, st>>>(                               \
+#define PASE_APP_R(YT, DF, RV)                                                                \
+  bn_prelu_bwd_apply_kernel<YT, DF, RV><<<grid, THREADS, sm, st>>>(                           \
       reinterpret_cast<const YT*>(y), y_sample_stride, T, C, mean, invstd, gamma, S1, S2,     \
       1.0 / count, reinterpret_cast<const YT*>(du), dst, dst_sample_stride, dbias_acc,        \
       dst_lo, amax, scale_out)
+#define PASE_APP(YT, DF) do { if (RUN == 8) PASE_APP_R(YT, DF, 8); else PASE_APP_R(YT, DF, 4); } while (0)
   if (dst_fmt == PASE_FMT_BF16) PASE_APP(__nv_bfloat16, PASE_FMT_BF16);
   else if (dst_fmt == PASE_FMT_F16X2) PASE_APP(float, PASE_FMT_F16X2);
   else PASE_APP(float, PASE_FMT_F32);
 #undef PASE_APP
+#undef PASE_APP_R
   PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_apply");
   return PASE_OK;
 }

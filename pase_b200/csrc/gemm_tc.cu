@@ -951,238 +951,6 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------ NT window kernel, CTA pair ----
-// Same contract as tc_gemm_nt2_kernel, but the A operand is fetched once per 128-byte column
-// block instead of once per k-block.  With A(m, kk) = F[m + kk/R, kk%R] the k-blocks
-// kk = q*R + cb*BK (q = 0..Q-1) of one column block cb read the SAME columns of F, shifted by
-// q rows: one TMA box of (BM + Q - 1) rows serves all of them, the UMMA descriptor simply
-// starts q rows (q*128 B) further down (K-major SWIZZLE_128B operands may start at any row:
-// the swizzle is a function of absolute shared-memory address bits; measured in round 1).
-// For a k-tap stride-s convolution this divides the activation bytes through TMA / L2 / the
-// shared-memory write port by ~k/s; only the (half) weight tiles stream through a ring of B
-// stages.  Why it pays for the 16-bit modes and did not for TF32 (profiles/r01_history.md): the
-// f16 pipe needs the same operand bytes per instruction in half the time per flop, so the
-// pair kernel sits at the shared-memory port (tensor-core reads 96 B/clk + TMA writes
-// 62 B/clk of 128 B/clk); the window removes two thirds of the writes.
-template <int BN, int MODE>
-struct NTW2Cfg {
-  using MT = ModeT<MODE>;
-  static constexpr int BK = MT::EB;                            // elements per column block
-  static constexpr int BH = BN / 2;
-  static constexpr int B_BYTES = BH * 128;
-  static constexpr int B_STAGE_BYTES = (MT::SPLIT ? 2 : 1) * B_BYTES;   // per CTA
-  static constexpr int NWIN = MT::SPLIT ? 2 : 1;               // hi [, lo] windows per buffer
-  static constexpr int ACC_COLS = MT::NACC * BN;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static constexpr int CPW = (BN / 32 + 3) / 4;
-  static constexpr int EPI_ACTIVE = BN >= 128 ? 16 : 4 * (BN / 32);
-  static_assert(TMEM_COLS <= 512, "TMEM budget");
-};
-
-template <int BN, int MODE, bool OUT16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS_V3, 1)
-tc_gemm_ntw2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
-                    const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-                    const NTArgs a, int win_rows) {
-  using Cfg = NTW2Cfg<BN, MODE>;
-  using MT = ModeT<MODE>;
-  constexpr int BK = Cfg::BK;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  const int stages = a.stages;
-  const int win_bytes = win_rows * 128;                       // one hi (or lo) window
-  const int win_pair = Cfg::NWIN * win_bytes;
-  uint8_t* wins = smem;                                       // 2 window buffers
-  uint8_t* btiles = smem + 2 * win_pair;
-  uint8_t* after = btiles + stages * Cfg::B_STAGE_BYTES;
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(after);
-  uint64_t* b_empty = b_full + MAX_STAGES;
-  uint64_t* w_full = b_empty + MAX_STAGES;
-  uint64_t* w_empty = w_full + 2;
-  uint64_t* acc_full = w_empty + 2;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_out = reinterpret_cast<float*>(after + BAR_BYTES);
-  float* s_stats = s_out + OUT_STAGE_BYTES / 4;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int M = a.M, N = a.N, K = a.K, R = a.R;
-  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + 2 * BM - 1) / (2 * BM);
-  const int total_tiles = n_tiles * m_tiles;
-  const int nkb = K / BK;                                     // K % BK == 0 (host-checked)
-  const int ncb = (R < K ? R : K) / BK;                       // column blocks of a folded row
-  int flush_kb = a.flush_kb;
-  if (flush_kb <= 0 || flush_kb > nkb) flush_kb = nkb;
-  const int nchunks = (nkb + flush_kb - 1) / flush_kb;
-  const bool want_stats = a.colsum != nullptr;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&w_full[b], 1);
-      mbar_init(&w_empty[b], 1);
-      mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 2 * Cfg::EPI_ACTIVE);
-    }
-    fence_barrier_init();
-    tmap_prefetch(&mAhi);
-    tmap_prefetch(&mBhi);
-    if (MT::SPLIT) {
-      tmap_prefetch(&mAlo);
-      tmap_prefetch(&mBlo);
-    }
-  }
-  if (want_stats)
-    for (int i = threadIdx.x; i < 2 * a.stat_cols; i += NTHREADS_V3) s_stats[i] = 0.f;
-  if (warp == 1) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // q-steps of column block cb: kk = q*R + cb*BK < K
-  auto nq_of = [&](int cb) { return (K - cb * BK + R - 1) / R; };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t wi = 0, bi = 0;
-      auto issue_window = [&](int tile, int cb) {
-        const uint32_t w = wi & 1, wph = (wi >> 1) & 1;
-        mbar_wait(&w_empty[w], wph ^ 1, 45);
-        const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
-        uint8_t* dst = wins + w * win_pair;
-        const uint32_t fb = mapa_u32(smem_u32(&w_full[w]), 0);
-        if (leader) mbar_expect_tx(&w_full[w], 2 * win_pair);
-        tma2_load_2d(dst, &mAhi, fb, cb * BK, m0);
-        if (MT::SPLIT) tma2_load_2d(dst + win_bytes, &mAlo, fb, cb * BK, m0);
-        ++wi;
-      };
-      int tile = pair, cb = 0;
-      if (tile < total_tiles) issue_window(tile, 0);
-      while (tile < total_tiles) {
-        const int n0 = (tile % n_tiles) * BN + (int)rank * Cfg::BH;
-        const int nq = nq_of(cb);
-        // successor (tile, cb) whose window is prefetched while this block's last B tiles load
-        int ntile = tile, ncbn = cb + 1;
-        if (ncbn == ncb) { ncbn = 0; ntile = tile + npairs; }
-        const int pre_at = nq > stages ? nq - stages : 0;
-        for (int q = 0; q < nq; ++q, ++bi) {
-          if (q == pre_at && ntile < total_tiles) issue_window(ntile, ncbn);
-          const int s = bi % stages;
-          const uint32_t ph = (bi / stages) & 1;
-          mbar_wait(&b_empty[s], ph ^ 1, 41);
-          uint8_t* st = btiles + s * Cfg::B_STAGE_BYTES;
-          const uint32_t fb = mapa_u32(smem_u32(&b_full[s]), 0);
-          if (leader) mbar_expect_tx(&b_full[s], 2 * Cfg::B_STAGE_BYTES);
-          const int kf = q * R + cb * BK;
-          tma2_load_2d(st, &mBhi, fb, kf, n0);
-          if (MT::SPLIT) tma2_load_2d(st + Cfg::B_BYTES, &mBlo, fb, kf, n0);
-        }
-        tile = ntile;
-        cb = ncbn;
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (leader) {
-      // converged warp, elected issue (see umma_w); M = 256 across the pair
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN, 0, 0, MT::FMT);
-      const uint64_t dconst = desc_hi_bits<2>(16, 1024);
-      const uint32_t wins_u32 = smem_u32(wins), bt_u32 = smem_u32(btiles);
-      const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
-      uint32_t wi = 0, bi = 0, c = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
-        int in_chunk = 0, done_kb = 0;
-        uint32_t b = c & 1;
-        mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1, 44);
-        tc_fence_after();
-        for (int cb = 0; cb < ncb; ++cb, ++wi) {
-          const uint32_t w = wi & 1;
-          mbar_wait(&w_full[w], (wi >> 1) & 1, 46);
-          tc_fence_after();
-          const uint32_t a_hi0 = wins_u32 + w * win_pair;
-          const int nq = nq_of(cb);
-          for (int q = 0; q < nq; ++q, ++bi) {
-            const int s = bi % stages;
-            mbar_wait(&b_full[s], (bi / stages) & 1, 42);
-            tc_fence_after();
-            const uint32_t d_tmem = tm0 + b * Cfg::ACC_COLS;
-            // A starts q rows into the window; k-step of 32 B = +2
-            const uint64_t dah = dconst + ((a_hi0 + q * 128) >> 4);
-            const uint64_t dal = dah + (win_bytes >> 4);
-            const uint64_t dbh = dconst + ((bt_u32 + s * Cfg::B_STAGE_BYTES) >> 4);
-            const uint64_t dbl = dbh + (Cfg::B_BYTES >> 4);
-            issue_kblock<MODE, 2, 4, 2>(d_tmem, BN, dah, dbh, dal, dbl, idesc,
-                                        in_chunk == 0 ? 0u : 1u);
-            umma2_commit_mc_w(&b_empty[s]);
-            ++in_chunk;
-            ++done_kb;
-            if (in_chunk == flush_kb || done_kb == nkb) {
-              umma2_commit_mc_w(&acc_full[b]);          // chunk complete -> epilogue folds it
-              ++c;
-              in_chunk = 0;
-              if (done_kb < nkb) {
-                b = c & 1;
-                mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1, 44);
-                tc_fence_after();
-              }
-            }
-          }
-          umma2_commit_mc_w(&w_empty[w]);               // window free once its MMAs retire
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ---------------- epilogue: identical to tc_gemm_nt2_kernel ----------------
-    const int e = warp - 2;
-    const int q = warp & 3;
-    const int cc0 = e >> 2;
-    if (cc0 < BN / 32) {
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const bool vec_ok = OUT16 ? (((a.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0))
-                                : (((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0));
-      const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
-      float* stg = s_out + e * OUT_STG_FLOATS;
-      const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
-      uint32_t c = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
-        const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
-        const int n0 = (tile % n_tiles) * BN;
-        float sums[Cfg::CPW][32];
-        for (int ch = 0; ch < nchunks; ++ch, ++c) {
-          const uint32_t b = c & 1, aph = (c >> 1) & 1;
-          mbar_wait(&acc_full[b], aph, 43);
-          tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < Cfg::CPW; ++h)
-            fold_chunk<MODE>(lane_addr + b * Cfg::ACC_COLS + (cc0 + 4 * h) * 32, BN, sums[h],
-                             ch == 0);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(acc_empty0 + b * 8);
-        }
-        nt_output<Cfg::CPW, OUT16>(sums, a, alpha, m0, n0, cc0, q, lane, stg, s_stats, vec_ok);
-      }
-    }
-    if (want_stats) flush_stats(a, s_stats);
-    tc_fence_before();
-  }
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
-  }
-}
-
 // ------------------------------------------------------------------ TN kernel ----
 // C[i,j] += alpha * sum_r A[r,i] B[r,j].  A: 4-D tensor (128 B inner, rows-per-group, column
 // blocks, groups); B addressed through the folded-row trick: (r, j) -> row u + j/R of group g,
@@ -1729,40 +1497,6 @@ int launch_nt2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
   return PASE_OK;
 }
 
-template <int BN, int MODE, bool OUT16>
-int launch_ntw2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-                const CUtensorMap& bl, NTArgs a, int win_rows, cudaStream_t st) {
-  using Cfg = NTW2Cfg<BN, MODE>;
-  static bool attr = false;
-  a.stat_cols = a.colsum ? ((a.N + 31) / 32) * 32 : 0;
-  const int win_total = 2 * Cfg::NWIN * win_rows * 128;
-  int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - OUT_STAGE_BYTES - 2 * a.stat_cols * 4 - win_total) /
-               Cfg::B_STAGE_BYTES;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) {
-    pase_set_error("pase_tc_gemm_nt(window): not enough shared memory for the window pipeline");
-    return PASE_ERR_UNSUPPORTED;
-  }
-  a.stages = stages;
-  const int smem = win_total + stages * Cfg::B_STAGE_BYTES + 1024 + BAR_BYTES + OUT_STAGE_BYTES +
-                   2 * a.stat_cols * 4;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_ntw2_kernel<BN, MODE, OUT16>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) {
-      pase_set_error("pase_tc_gemm_nt(window): smem attribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr = true;
-  }
-  const long tiles = (long)((a.N + BN - 1) / BN) * ((a.M + 2 * BM - 1) / (2 * BM));
-  const long max_pairs = pase_num_sms() / 2;
-  const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);
-  tc_gemm_ntw2_kernel<BN, MODE, OUT16><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a, win_rows);
-  PASE_TC_LAUNCH_CHECK("pase_tc_gemm_nt(window)");
-  return PASE_OK;
-}
-
 template <int BN, int MODE>
 int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
               const CUtensorMap& bl, TNArgs a, cudaStream_t st) {
@@ -1968,26 +1702,16 @@ int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const 
   const int BN = N <= 64 ? 64 : ((wide || pair256) ? 256 : 128);
   const int rowb = (BN == 256 && !pair256) ? 64 : 128;
   const int bk = rowb / esz;
-  // split modes: fold the TMEM accumulator into fp32 register sums every K = 128
-  const int flush_kb = split ? (128 / bk > 0 ? 128 / bk : 1) : 0;
+  // split modes: fold the TMEM accumulator into fp32 register sums every K = 128.  The
+  // accumulator rounds toward zero (a bias of ~0.5 ulp per accumulate step): over K <= 512
+  // that stays below 1e-6 relative, so short reductions (sinc layer, block-1 dgrad) keep
+  // one chunk and a third of the epilogue work
+  const int flush_kb = (split && K > 512) ? (128 / bk > 0 ? 128 / bk : 1) : 0;
   CUtensorMap ah, al, bh, bl;
   const bool pair2 = pair256 || (BN == 128 && (N % 128) == 0 && pase_tc_use_2cta());
-  // window kernel (CTA pair, 16-bit modes): A fetched once per column block and reused by
-  // the K/R taps that read it; needs whole k-blocks.  PASE_B200_TC_WINDOW=0 disables,
-  // =2 enables it for the fp32-operand modes too.
-  static int use_win = -1;
-  if (use_win < 0) {
-    const char* e = getenv("PASE_B200_TC_WINDOW");
-    use_win = e ? atoi(e) : 0;
-  }
-  const int qmax = (K + R - 1) / R;
-  const int win_rows = ((BM + qmax - 1 + 7) / 8) * 8;
-  const bool pair128 = BN == 128 && (N % 128) == 0 && pase_tc_use_2cta();
-  const bool window = pair128 && qmax >= 2 && (K % bk) == 0 && win_rows <= 256 &&
-                      use_win > 0 && (mode >= 2 || use_win >= 2);
   uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
   uint64_t astr[1] = {(uint64_t)R * esz};
-  uint32_t abox[2] = {(uint32_t)bk, (uint32_t)(window ? win_rows : BM)};
+  uint32_t abox[2] = {(uint32_t)bk, (uint32_t)BM};
   uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
   uint64_t bstr[1] = {(uint64_t)ldb * esz};
   uint32_t bbox[2] = {(uint32_t)bk, (uint32_t)(pair2 ? BN / 2 : BN)};   // pair: half per CTA
@@ -2024,9 +1748,6 @@ int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const 
 #define PASE_NT1(MODEV, O16, BNV, RB) launch_nt<BNV, MODEV, RB, O16>(ah, al, bh, bl, a, st)
   if (pair256) return c_bf16 ? launch_nt2<256, 2, true>(ah, al, bh, bl, a, st)
                              : launch_nt2<256, 2, false>(ah, al, bh, bl, a, st);
-#define PASE_NTW2(MODEV, O16, BNV) launch_ntw2<BNV, MODEV, O16>(ah, al, bh, bl, a, win_rows, st)
-  if (window) { PASE_NT_MODES(PASE_NTW2, 128) }
-#undef PASE_NTW2
   if (pair2) { PASE_NT_MODES(PASE_NT2, 128) }
   if (BN == 64) { PASE_NT_MODES(PASE_NT1, 64, 128) }
   if (BN == 128) { PASE_NT_MODES(PASE_NT1, 128, 128) }

@@ -9,8 +9,10 @@ run() {
   grep -E "^FAILED|^ERROR|timed out|max err|Error:|mismatch" gpurun_out/$name.log | head -${SHOW:-8} | cut -c1-240
 }
 run ab_gemm 400 tests/test_tc_gemm_gpu.py
-PASE_B200_TC_WINDOW=0 PASE_B200_TN_2CTA=0 run ab_gemm_off 400 tests/test_tc_gemm_gpu.py
-run ab_enc 900 tests/test_encoder_gpu.py -k "golden or full_length or benchmark_shape_against"
+run ab_kern 400 tests/test_kernels_gpu.py
+PASE_B200_BN_RUN=8 run ab_kern8 400 tests/test_kernels_gpu.py
+SHOW=30 run ab_enc 900 tests/test_encoder_gpu.py -s
+run ab_heads 900 tests/test_heads_gpu.py tests/test_flat_adam.py tests/test_graph_gpu.py
 bench() {  # label, env...
   local label=$1; shift
   for p in 3xf16 bf16; do
@@ -25,8 +27,5 @@ except Exception as e:
 PY
   done
 }
-bench all_on X=1
-bench no_window PASE_B200_TC_WINDOW=0
-bench no_tn2 PASE_B200_TN_2CTA=0
-bench none PASE_B200_TC_WINDOW=0 PASE_B200_TN_2CTA=0 PASE_B200_BF16_WIDE=0
-bench win_fp32 PASE_B200_TC_WINDOW=2 PASE_B200_TN_2CTA=2
+bench run4 X=1
+bench run8 PASE_B200_BN_RUN=8
