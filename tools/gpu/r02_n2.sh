@@ -1,0 +1,22 @@
+#!/bin/bash
+# 2 GPUs: NCCL correctness test of the flat all-reduce + pipelined step, then the N=2 bench
+# (overlapped vs not) next to N=1 on the same box
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+timeout 600 python -m pytest tests/test_dp_nccl_gpu.py -q -m gpu -p no:cacheprovider -s > gpurun_out/t_nccl.log 2>&1
+echo "nccl test rc=$? $(grep -E 'passed|failed|skipped' gpurun_out/t_nccl.log | tail -1)"; grep -E "worst|Error|^E " gpurun_out/t_nccl.log | head -10 | cut -c1-240
+show() { python - "$1" "$2" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    print(sys.argv[1], 'n', d['n_gpus'], 'ms/step', round(d['ms_per_step'],3), 'M/s', round(d['value']/1e6,1), 'e2e ms', round(d['e2e']['ms_per_step'],3), d['config'].get('grad_allreduce'))
+except Exception as e:
+    print(sys.argv[1], 'failed', e); print(open(sys.argv[2].replace('.json','.err')).read()[-1200:])
+PY
+}
+timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/n1.json 2> gpurun_out/n1.err; show n1 gpurun_out/n1.json
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/n2.json 2> gpurun_out/n2.err; show n2_overlap gpurun_out/n2.json
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --no-overlap > gpurun_out/n2b.json 2> gpurun_out/n2b.err; show n2_no_overlap gpurun_out/n2b.json
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 --torch-adam > gpurun_out/n2c.json 2> gpurun_out/n2c.err; show n2_round1_path gpurun_out/n2c.json
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/n2ref.json 2> gpurun_out/n2ref.err; tail -c 300 gpurun_out/n2ref.json
