@@ -5,7 +5,6 @@
 
 namespace {
 
-constexpr int RUN8 = 8;     // consecutive time steps handled by one thread (RUN template values)
 constexpr int THREADS = 256;
 
 // DF: operand format of the padded waveform (block 0's GEMM operand)

@@ -65,12 +65,14 @@ def _worker(rank, world, port, out):
     for (ka, pa), (kb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert torch.equal(pa, pb), ka
     start = {k: p.detach().clone() for k, p in ma.named_parameters()}
-    for _ in range(2):
+    for _ in range(3):
         loss_fn(ma(x)).backward()
         oa.reduce_grads()
         oa.step()
+    # 1 eager warm-up step inside the constructor (lazy tables / plans must exist before the
+    # capture) + 2 graph replays = 3 optimizer steps
     pipe = PipelinedDPStep(mb, ob, loss_fn, (B, 1, T), dev, split=split, n_lower=n_lower,
-                           stream=side, resident=True, warmup=0, x_init=x.cpu())
+                           stream=side, resident=True, warmup=1, x_init=x.cpu().pin_memory())
     for _ in range(2):
         pipe.step()
     torch.cuda.synchronize()
