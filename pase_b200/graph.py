@@ -13,7 +13,7 @@ class GraphedEncoderStep(object):
 
     def __init__(self, model, optimizer, loss_fn, shape, device, pre_step=None, post_backward=None,
                  warmup=3, stream=None, resident=False, x_init=None,
-                 capture_error_mode="global", between=None):
+                 capture_error_mode="global", between=None, prefetch=False):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.x_static = torch.zeros(shape, dtype=torch.float32, device=device)
         self.x_host = torch.zeros(shape, dtype=torch.float32).pin_memory()
@@ -28,6 +28,18 @@ class GraphedEncoderStep(object):
         # the same stream between two graph replays.
         self.between = between
         self.resident = resident        # True: input stays in HBM, no H2D / D2H in the graph
+        # prefetch: the H2D copy of the NEXT step's batch (pinned host -> one of two device
+        # staging buffers, on a copy stream) overlaps the current step's compute; the step
+        # itself starts with a device-to-device copy out of the staging buffer.  Same bytes
+        # per step, every copy still inside the caller's timed region -- the usual
+        # double-buffered input pipeline of a training loop.
+        self.prefetch = bool(prefetch) and not resident
+        if self.prefetch:
+            self.stage = [torch.zeros(shape, dtype=torch.float32, device=device) for _ in (0, 1)]
+            self.h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self.copy_stream = torch.cuda.Stream(device=device)
+            self._k = 0
+            self._primed = False
         # capture on the stream the model's autograd nodes already live on: an AccumulateGrad
         # node created on another stream invalidates the capture
         self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
@@ -39,7 +51,7 @@ class GraphedEncoderStep(object):
         self._capture(warmup)
 
     def _part_a(self):
-        if not self.resident:
+        if not self.resident and not self.prefetch:
             self.x_static.copy_(self.x_host, non_blocking=True)
         if self.pre_step is not None:
             self.pre_step()
@@ -91,6 +103,21 @@ class GraphedEncoderStep(object):
         copies it there first."""
         if x_host is not None:
             self.x_host.copy_(x_host)
+        if self.prefetch:
+            k = self._k
+            with torch.cuda.stream(self.stream):
+                if not self._primed:             # first call: nothing was prefetched yet
+                    self.stage[k].copy_(self.x_host, non_blocking=True)
+                    self._primed = True
+                else:
+                    self.stream.wait_event(self.h2d_done[k])
+                self.x_static.copy_(self.stage[k], non_blocking=True)      # D2D, ~2 us
+            # next batch -> the other staging buffer, concurrently with this step's compute
+            # (its previous reader, the step before this one, has completed: step() syncs)
+            with torch.cuda.stream(self.copy_stream):
+                self.stage[1 - k].copy_(self.x_host, non_blocking=True)
+                self.h2d_done[1 - k].record(self.copy_stream)
+            self._k = 1 - k
         self.graph.replay()
         if self.graph_b is not None:
             with torch.cuda.stream(self.stream):
