@@ -21,32 +21,35 @@ __device__ __forceinline__ void block_acc(double v, double* acc) {
   }
 }
 
-__device__ __forceinline__ float ctx_label(const float* __restrict__ label, long row, int col,
-                                           int F, int T, int r) {
-  const int f = col / r, j = col - f * r;
-  const long b = row / T;
-  const int t = (int)(row - b * T);
-  const int tt = t + j - r / 2;
-  return (tt >= 0 && tt < T) ? label[(b * F + f) * T + tt] : 0.f;
-}
+// Thread = one prediction column (f, j fixed: no per-element divisions), block = 256 columns
+// x CTX_RPB rows: pred is read coalesced along the columns, the label window
+// label[b][f][t + j - r/2] walks contiguously in t (L1-resident: every label element serves r
+// predictions).  HBM-bound: 4 B (fwd) / 8 B (bwd) per prediction element.
+constexpr int CTX_RPB = 32;
 
 __global__ void __launch_bounds__(TPB)
 ctx_mse_fwd_kernel(const float* __restrict__ pred, long ldp, const float* __restrict__ label,
                    long rows, int F, int T, int r, double* acc) {
   const int cols = F * r;
-  const long total = rows * cols;
+  const int col = blockIdx.x * TPB + threadIdx.x;
+  const long row0 = (long)blockIdx.y * CTX_RPB;
   float s = 0.f;
-  double sd = 0.0;
-  int cnt = 0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const long row = i / cols;
-    const int col = (int)(i - row * cols);
-    const float d = pred[row * ldp + col] - ctx_label(label, row, col, F, T, r);
-    s = fmaf(d, d, s);
-    if (++cnt == 64) { sd += (double)s; s = 0.f; cnt = 0; }
+  if (col < cols) {
+    const int f = col / r, shift = (col - f * r) - r / 2;
+    long b = row0 / T;
+    int t = (int)(row0 - b * T);
+    const float* p = pred + row0 * ldp + col;
+    const int n = (rows - row0) < CTX_RPB ? (int)(rows - row0) : CTX_RPB;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      const int tt = t + shift;
+      const float lab = (tt >= 0 && tt < T) ? __ldg(label + (b * F + f) * T + tt) : 0.f;
+      const float d = p[(long)i * ldp] - lab;
+      s = fmaf(d, d, s);
+      if (++t == T) { t = 0; ++b; }
+    }
   }
-  block_acc(sd + (double)s, acc);
+  block_acc((double)s, acc);
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -54,14 +57,22 @@ ctx_mse_bwd_kernel(const float* __restrict__ pred, long ldp, const float* __rest
                    long rows, int F, int T, int r, float coef, const float* __restrict__ gscale,
                    float* __restrict__ dpred, long lddp) {
   const int cols = F * r;
-  const long total = rows * cols;
+  const int col = blockIdx.x * TPB + threadIdx.x;
+  if (col >= cols) return;
+  const long row0 = (long)blockIdx.y * CTX_RPB;
   const float k = coef * (gscale ? gscale[0] : 1.f);
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const long row = i / cols;
-    const int col = (int)(i - row * cols);
-    const float d = pred[row * ldp + col] - ctx_label(label, row, col, F, T, r);
-    dpred[row * lddp + col] = k * d;
+  const int f = col / r, shift = (col - f * r) - r / 2;
+  long b = row0 / T;
+  int t = (int)(row0 - b * T);
+  const float* p = pred + row0 * ldp + col;
+  float* dp = dpred + row0 * lddp + col;
+  const int n = (rows - row0) < CTX_RPB ? (int)(rows - row0) : CTX_RPB;
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const int tt = t + shift;
+    const float lab = (tt >= 0 && tt < T) ? __ldg(label + (b * F + f) * T + tt) : 0.f;
+    dp[(long)i * lddp] = k * (p[(long)i * ldp] - lab);
+    if (++t == T) { t = 0; ++b; }
   }
 }
 
@@ -148,7 +159,8 @@ int pase_ctx_mse_fwd(const float* pred, long ldp, const float* label, int B, int
   PASE_CHECK_ARG(pred && label && acc && B > 0 && F > 0 && T > 0 && r >= 1 && (r & 1),
                  "pase_ctx_mse_fwd: bad args (r must be odd, got %d)", r);
   const long rows = (long)B * T;
-  ctx_mse_fwd_kernel<<<nblk(rows * F * r), TPB, 0, (cudaStream_t)stream>>>(pred, ldp, label, rows,
+  const dim3 cgrid((unsigned)((F * r + TPB - 1) / TPB), (unsigned)((rows + CTX_RPB - 1) / CTX_RPB));
+  ctx_mse_fwd_kernel<<<cgrid, TPB, 0, (cudaStream_t)stream>>>(pred, ldp, label, rows,
                                                                           F, T, r, acc);
   PASE_LAUNCH_CHECK("pase_ctx_mse_fwd");
   return PASE_OK;
@@ -159,7 +171,8 @@ int pase_ctx_mse_bwd(const float* pred, long ldp, const float* label, int B, int
   PASE_CHECK_ARG(pred && label && dpred && B > 0 && F > 0 && T > 0 && r >= 1 && (r & 1),
                  "pase_ctx_mse_bwd: bad args");
   const long rows = (long)B * T;
-  ctx_mse_bwd_kernel<<<nblk(rows * F * r), TPB, 0, (cudaStream_t)stream>>>(
+  const dim3 cgrid((unsigned)((F * r + TPB - 1) / TPB), (unsigned)((rows + CTX_RPB - 1) / CTX_RPB));
+  ctx_mse_bwd_kernel<<<cgrid, TPB, 0, (cudaStream_t)stream>>>(
       pred, ldp, label, rows, F, T, r, coef, gscale, dpred, lddp);
   PASE_LAUNCH_CHECK("pase_ctx_mse_bwd");
   return PASE_OK;

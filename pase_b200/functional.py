@@ -189,15 +189,24 @@ class _LinearRows(torch.autograd.Function):
         N, ldx, ldo = ctx.N, ctx.ldx, ctx.ldo
         assert dy.shape == (rows, ldo)
         dev = x.device
-        dyb = torch.empty(rows * ldo + 64, dtype=torch.float32, device=dev)
-        dyb[:rows * ldo].view(rows, ldo).copy_(dy)
-        dyb[rows * ldo:].zero_()
-        dyf = dyb
         mode = _MODES[PRECISION]
+        # the tensor-core weight-gradient kernel reads dY in whole 128-byte column blocks: a dY
+        # whose leading dimension is a multiple of that block (every tensor-core mode pads so)
+        # needs no slack; otherwise copy it into a buffer with 64 zeroed floats behind it
+        blk = _eb(mode) if mode is not None else 4
+        if dy.is_contiguous() and ldo % blk == 0 and dy.data_ptr() % 16 == 0:
+            dyb = dy.reshape(-1)
+            n_dy = rows * ldo
+        else:
+            dyb = torch.empty(rows * ldo + 64, dtype=torch.float32, device=dev)
+            dyb[:rows * ldo].view(rows, ldo).copy_(dy)
+            dyb[rows * ldo:].zero_()
+            n_dy = rows * ldo + 64
+        dyf = dyb
         # dY feeds both backward GEMMs: convert it to the operand format once
         if mode is not None and mode != 0 and tc_shapes_ok(ldo, ldo, ldo) and \
                 ldx % _eb(mode) == 0 and K % _eb(mode) == 0 and ldo % 4 == 0:
-            dyf = to_operand(dyb, rows * ldo + 64, mode, "grad")
+            dyf = to_operand(dyb, n_dy, mode, "grad")
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             wT = torch.empty(K, ldo, dtype=torch.float32, device=dev)

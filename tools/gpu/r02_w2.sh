@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_heads_gpu.py tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/w2_tests.log 2>&1
+echo "heads+kernels rc=$? $(grep -E 'passed|failed' gpurun_out/w2_tests.log | tail -1)"; grep -E "^FAILED|^E  " gpurun_out/w2_tests.log | head -10 | cut -c1-220
+timeout 300 python bench.py --workload workers --steps 5 --warmup 3 2> gpurun_out/w_workers.err | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('workers ms/step', round(d['ms_per_step'],3), 'graph', d['cuda_graph'], d['graph_error'], 'loss', d['loss'])"
