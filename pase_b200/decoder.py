@@ -110,11 +110,12 @@ class _DecoderStackFn(torch.autograd.Function):
                  plan.zeros[:C], plan.ones[:C], plan.ones[:C], plan.zeros[:C], alpha.reshape(-1),
                  src, 0, g.L * C, C, 0, 0, None, 0, 0, 0, None, 0, 0, 0, 0,
                  plan.dyfull[i][g.pad * C:], g.U * g.s * C, S1, S2, dal, None)
-            call("pase_colsum", plan.dyfull[i], C, B * g.U * g.s, C, dbi)
+            # no normalisation in GDeconv1DBlock (mean 0, invstd 1): S1 = sum of du over every
+            # kept position IS the bias gradient -- no separate column-sum pass over dY
             small = torch.empty(4 * C, dtype=torch.float32, device=dev)
             call("pase_cast_d2f", acc, small, 4 * C, 1.0)
             grads[3 * i + 2] = small[2 * C:3 * C].clone().view_as(alpha)
-            grads[3 * i + 1] = small[3 * C:4 * C].clone()
+            grads[3 * i + 1] = small[:C].clone()
             # dY feeds the weight-gradient and the input-gradient GEMM: one operand conversion
             dyop = plan.dyfull[i]
             mode = Fn._MODES[Fn.PRECISION]

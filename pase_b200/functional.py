@@ -175,9 +175,16 @@ class _LinearRows(torch.autograd.Function):
         buf[rows * ldo:].zero_()
         if ldo != N:
             out[:, N:].zero_()
-        gemm_nt(_flat_from(x), ldx, rows * ldx, w2.reshape(-1), K, N * K, out.reshape(-1), ldo,
+        # the input is a GEMM operand twice (A here, B of the weight-gradient GEMM in
+        # backward): convert it to the operand format once and keep it
+        xop = _flat_from(x)
+        mode = _MODES[PRECISION]
+        if mode not in (None, 0) and tc_shapes_ok(ldx, K, K):
+            xop = to_operand(xop, rows * ldx, mode, "act")
+        gemm_nt(xop, ldx, rows * ldx, w2.reshape(-1), K, N * K, out.reshape(-1), ldo,
                 rows, N, K, None if bias is None else bias.detach().reshape(-1))
         ctx.save_for_backward(x, w2)
+        ctx.xop = xop if isinstance(xop, Operand) else None
         ctx.ldx, ctx.N, ctx.has_bias, ctx.wshape, ctx.ldo = ldx, N, bias is not None, \
             weight.shape, ldo
         return out
@@ -216,7 +223,10 @@ class _LinearRows(torch.autograd.Function):
                     rows, K, ldo, None, a_kind="grad")
         if ctx.needs_input_grad[1]:
             dWp = torch.empty(ldo, K, dtype=torch.float32, device=dev)
-            gemm_tn(dyf, ldo, rows * ldo, _flat_from(x), ldx, rows * ldx, dWp.reshape(-1), K,
+            xb = _flat_from(x)
+            if ctx.xop is not None and isinstance(dyf, Operand):
+                xb = ctx.xop                     # same format as the B operand of the TN GEMM
+            gemm_tn(dyf, ldo, rows * ldo, xb, ldx, rows * ldx, dWp.reshape(-1), K,
                     ldo, K, rows)
             dW = dWp[:N].reshape(ctx.wshape)
         dy = dyb[:rows * ldo].view(rows, ldo)
