@@ -59,38 +59,45 @@ def _worker(rank, world, port, out):
     assert torch.allclose(opt.flat_grad, mean, rtol=1e-5, atol=1e-8 + 1e-6 * float(mean.abs().max()))
     assert float((gathered[0] - gathered[1]).abs().max()) > 0      # the shards really differ
 
-    # (2) pipelined graphs == eager, two optimisation steps
-    ma, oa, _ = build(1)
-    mb, ob, n_lower = build(1)
+    # (2) pipelined graphs == eager.  Adam turns ANY gradient into a +-lr step, so parameters
+    # are a poor witness (noise-level gradients flip signs between two runs); the reduced flat
+    # gradient is compared instead, with lr = 0 so that every step sees the same weights.
+    def build0(seed):
+        m, _, n_lower = build(seed)
+        params, n_lower = PipelinedDPStep.order_params(m, split)
+        m.grad_sink = None
+        return m, FlatAdam(params, lr=0.0).bind_encoder(m), n_lower
+    ma, oa, _ = build0(1)
+    mb, ob, n_lower = build0(1)
     for (ka, pa), (kb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert torch.equal(pa, pb), ka
-    start = {k: p.detach().clone() for k, p in ma.named_parameters()}
-    for _ in range(3):
-        loss_fn(ma(x)).backward()
-        oa.reduce_grads()
-        oa.step()
+    loss_fn(ma(x)).backward()
+    oa.reduce_grads()
+    oa.step()
+    ga = oa.flat_grad.clone()
     # 1 eager warm-up step inside the constructor (lazy tables / plans must exist before the
     # capture) + 2 graph replays = 3 optimizer steps
     pipe = PipelinedDPStep(mb, ob, loss_fn, (B, 1, T), dev, split=split, n_lower=n_lower,
                            stream=side, resident=True, warmup=1, x_init=x.cpu().pin_memory())
-    for _ in range(2):
-        pipe.step()
-    torch.cuda.synchronize()
     worst = 0.0
-    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        if k.endswith(("conv.bias", "W.bias")):         # zero-gradient biases: Adam on noise
-            continue
-        moved = float((pa - start[k]).abs().max())
-        diff = float((pa - pb).abs().max())
-        worst = max(worst, diff / max(moved, 1e-12))
-        assert diff <= 2e-2 * moved + 1e-7, (k, diff, moved)
+    for _ in range(2):
+        ob.flat_grad.zero_()                       # a stale buffer must not pass the check
+        pipe.step()
+        torch.cuda.synchronize()
+        gb = ob.flat_grad
+        err = float((ga - gb).abs().max())
+        worst = max(worst, err / float(ga.abs().max()))
+        assert err <= 1e-4 * float(ga.abs().max()), err
+        assert torch.allclose(gb, ga, rtol=2e-2, atol=1e-5 * float(ga.abs().max()))
+    assert float(ob.steps[0]) == 3.0 and float(oa.steps[0]) == 1.0
     # every rank holds the same parameters afterwards
     flat = ob.flat_param.clone()
     both = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(both, flat)
     assert torch.equal(both[0], both[1])
     if rank == 0:
-        open(os.path.join(out, "ok"), "w").write("worst relative update mismatch %.3e\n" % worst)
+        open(os.path.join(out, "ok"), "w").write(
+            "pipelined vs eager reduced gradient: worst |diff| / max|g| = %.3e\n" % worst)
     dist.barrier()
     dist.destroy_process_group()
 
