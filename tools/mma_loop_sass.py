@@ -13,7 +13,7 @@ for f in funcs:
     name = f.split("\n", 1)[0]
     if "tc_gemm" not in name:
         continue
-    m = re.search(r"tc_gemm_\w+?_kernelILi(\d+)ELb(\d)E(?:Li(\d+)E)?", name)
+    m = re.search(r"tc_gemm_\w+?_kernelI((?:L[ib]\d+E)+)", name)
     ins = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", l)]
     ops = [re.sub(r"/\*[0-9a-fx ]+\*/", "", l).strip().rstrip("; ") for l in ins]
     mma = [i for i, o in enumerate(ops) if "UTCHMMA" in o]
@@ -31,5 +31,6 @@ for f in funcs:
         k = o.split()[1] if o.startswith("@") else o.split()[0]
         kinds[k] = kinds.get(k, 0) + 1
     top = sorted(kinds.items(), key=lambda kv: -kv[1])[:8]
-    print(re.search(r"tc_gemm_\w+?_kernel", name).group(0), m.groups(), "mma", len(mma),
+    targs = re.findall(r"L[ib](\d+)E", m.group(1)) if m else []
+    print(re.search(r"tc_gemm_\w+?_kernel", name).group(0), "<%s>" % ",".join(targs), "mma", len(mma),
           "loop instrs", len(body), top)
