@@ -228,7 +228,8 @@ def workers_plus_cfg():
     return {"regr": regr, "cls": cls}
 
 
-def time_workers(dev, precision, B, T=T_CHUNK, steps=5, warmup=3, graph=True, stream=None):
+def time_workers(dev, precision, B, T=T_CHUNK, steps=5, warmup=3, graph=True, stream=None,
+                 fuse=True):
     """BASELINE configs[2]/[3] shape on one GPU: PASE+ encoder on the 3B concatenated chunks +
     all 12 workers+ heads + summed loss, fwd + bwd + ONE flat Adam launch; the whole step
     replayed as one CUDA graph when `graph`.  -> dict (ms/step, chunk-samples/s, ...)."""
@@ -241,6 +242,9 @@ def time_workers(dev, precision, B, T=T_CHUNK, steps=5, warmup=3, graph=True, st
     wcfg = workers_plus_cfg()
     model = pase(frontend_cfg=dict(PASE_PLUS), minions_cfg=parse_workers(wcfg)).to(dev).train()
     model.frontend.precision = precision
+    # fused output layer + contextualised MSE for the MLP regression heads (3xF16): the
+    # (B, F*r, T') predictions -- 551 MB each for the two lps heads -- are never stored
+    model.fuse_regression_loss = (precision == "3xf16") and fuse
     Tq = T // 160
     batch = {k: torch.randn(B, 1, T, device=dev) for k in
              ("chunk", "chunk_ctxt", "chunk_rand", "cchunk")}
@@ -285,6 +289,7 @@ def time_workers(dev, precision, B, T=T_CHUNK, steps=5, warmup=3, graph=True, st
             "config": {"workload": "PASE+.cfg + workers+.cfg (12 workers), B=%d chunk triplets, "
                                    "T=%d" % (B, T),
                        "gemm_precision": precision, "params": nparam,
+                       "fused_regression_heads": bool(model.fuse_regression_loss),
                        "optimizer": "pase_adam_flat, one launch for all 13 parameter groups"},
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
 
@@ -296,7 +301,8 @@ def run_workers(args):
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     print(json.dumps(time_workers(dev, args.precision, args.batch, steps=args.steps,
-                                  warmup=args.warmup, graph=not args.no_graph, stream=side)),
+                                  warmup=args.warmup, graph=not args.no_graph, stream=side,
+                                  fuse=not args.no_fuse_heads)),
           flush=True)
 
 
@@ -741,6 +747,9 @@ def main():
                          "at N=2: 3.49 ms/step vs 3.42 for one all-reduce between two graph "
                          "replays (NVLink moves 31 MB in ~0.05 ms; the extra graph launches, "
                          "events and SM contention cost more), so the plain form is the default")
+    ap.add_argument("--no-fuse-heads", action="store_true",
+                    help="workers workload: materialise the regression predictions (reference "
+                         "protocol) instead of fusing output layer + contextualised MSE")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="e2e: copy the step's batch H2D inside the step instead of prefetching "
                          "the next batch on a copy stream during the current step")

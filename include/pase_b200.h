@@ -108,6 +108,24 @@ int pase_absmax(const float* x, long n, float* amax, void* stream);
 int pase_split_f16(const float* x, void* hi, void* lo, long n, const float* amax,
                    float* scale_out, void* stream);
 
+/* amax[0] = max(amax[0], max_r ||X[r, :cols]||_2)   (Cauchy-Schwarz bound of a GEMM output) */
+int pase_rownorm_max(const float* X, long ld, long rows, int cols, float* amax, void* stream);
+/* scale_out = {1/s, s}: the power of two placing a[0]*a[1] + a[2] + a[3] below 2^14 */
+int pase_bound_scale(const float* a4, float* scale_out, void* stream);
+
+/* ---- fused regression head (MLPMinion output layer + ContextualizedLoss MSE:
+ * minions.py:494-524, losses.py:15-37, GEMM mode 3) ------------------------
+ * residual[m, n] = sum_k A[m,k] B[n,k] + bias[n] - label[b][n/r][t + n%r - r/2]
+ * (m = b*T + t; zero outside [0,T)): never stored as fp32 -- Rhi/Rlo receive the fp16
+ * pair of s * residual ([M x ldr], ldr % 128 == 0, columns >= N zero), the operand of
+ * the two backward GEMMs; loss_acc += sum residual^2; db_acc[n] += sum_m residual[m,n].
+ * scale = device {1/s, s} (pase_bound_scale of the Cauchy-Schwarz bound). */
+int pase_tc_gemm_nt_ctxmse(const void* Ahi, const void* Alo, long a_rows, int R,
+                           const void* Bhi, const void* Blo, long ldb,
+                           void* Rhi, void* Rlo, long ldr, int M, int N, int K,
+                           const float* bias, const float* label, int B, int F, int T, int r,
+                           const float* scale, double* loss_acc, double* db_acc, void* stream);
+
 /* ---- weight re-layout (implicit-GEMM operand preparation) ---------------- */
 /* (Cout,Cin,k) -> Wt[co, j*Cin+ci]                      (forward operand)   */
 int pase_conv_w_to_fwd(const float* W, float* Wt, int Cout, int Cin, int k, void* stream);

@@ -54,6 +54,33 @@ __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict
   }
 }
 
+// amax[0] = max(amax[0], max_r ||X[r, :cols]||_2): one warp per row
+__global__ void rownorm_max_kernel(const float* __restrict__ X, long ld, long rows, int cols,
+                                   float* __restrict__ amax) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  float m = 0.f;
+  for (long r = warp; r < rows; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = X[r * ld + c];
+      s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    m = fmaxf(m, sqrtf(s));
+  }
+  if (lane == 0 && m > 0.f) atomic_max_pos(amax, m);
+}
+
+// scale_out = {1/s, s} for values bounded by a[0]*a[1] + a[2] + a[3]
+__global__ void bound_scale_kernel(const float* __restrict__ a, float* __restrict__ scale_out) {
+  const float bound = fmaf(a[0], a[1], a[2] + a[3]);
+  const float s = f16_grad_scale(bound * 1.0001f);
+  scale_out[0] = 1.f / s;
+  scale_out[1] = s;
+}
+
 inline unsigned cast_blocks(long n) {
   long b = (n / 4 + 255) / 256;
   long cap = (long)pase_num_sms() * 16;
@@ -93,6 +120,23 @@ int pase_split_f16(const float* x, void* hi, void* lo, long n, const float* amax
   split_f16_kernel<<<cast_blocks(n), 256, 0, (cudaStream_t)stream>>>(
       x, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), n, amax, scale_out);
   PASE_LAUNCH_CHECK("pase_split_f16");
+  return PASE_OK;
+}
+
+int pase_rownorm_max(const float* X, long ld, long rows, int cols, float* amax, void* stream) {
+  PASE_CHECK_ARG(X && amax && rows > 0 && cols > 0 && ld >= cols, "pase_rownorm_max: bad args");
+  long blocks = (rows * 32 + 255) / 256;
+  const long cap = (long)pase_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  rownorm_max_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(X, ld, rows, cols, amax);
+  PASE_LAUNCH_CHECK("pase_rownorm_max");
+  return PASE_OK;
+}
+
+int pase_bound_scale(const float* a4, float* scale_out, void* stream) {
+  PASE_CHECK_ARG(a4 && scale_out, "pase_bound_scale: null pointer");
+  bound_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a4, scale_out);
+  PASE_LAUNCH_CHECK("pase_bound_scale");
   return PASE_OK;
 }
 

@@ -397,20 +397,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// bf16 output: the same transpose with rows of 16 bf16 (32 B) -- two passes of 16 columns;
-// after the transpose a lane owns 16 B (8 columns) of a row, 2 lanes cover a 32 B sector.
-__device__ __forceinline__ void store_chunk_bf16(float* stg_f, const float (&v)[32], int lane,
-                                                 __nv_bfloat16* __restrict__ C, long ldc,
-                                                 long orow, int nlim, int nb, bool vec_ok) {
+// 16-bit output (bf16 values, or the fp16 halves of a pair): the same transpose with rows of 16
+// elements (32 B) -- two passes of 16 columns; after the transpose a lane owns 16 B (8 columns)
+// of a row, 2 lanes cover a 32 B sector.  pk[i] = columns 2i, 2i+1 of this lane's row.
+__device__ __forceinline__ void store_chunk_16(float* stg_f, const uint32_t (&pk)[16], int lane,
+                                               uint16_t* __restrict__ C, long ldc, long orow,
+                                               int nlim, int nb, bool vec_ok) {
   uint4* stg = reinterpret_cast<uint4*>(stg_f);          // 64 chunks of 16 B
   const int sw = (lane >> 2) & 1;
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
-    const int c = pass * 16;
-    stg[lane * 2 + (0 ^ sw)] = make_uint4(pack_bf16(v[c + 0], v[c + 1]), pack_bf16(v[c + 2], v[c + 3]),
-                                          pack_bf16(v[c + 4], v[c + 5]), pack_bf16(v[c + 6], v[c + 7]));
-    stg[lane * 2 + (1 ^ sw)] = make_uint4(pack_bf16(v[c + 8], v[c + 9]), pack_bf16(v[c + 10], v[c + 11]),
-                                          pack_bf16(v[c + 12], v[c + 13]), pack_bf16(v[c + 14], v[c + 15]));
+    const int c = pass * 8;
+    stg[lane * 2 + (0 ^ sw)] = make_uint4(pk[c + 0], pk[c + 1], pk[c + 2], pk[c + 3]);
+    stg[lane * 2 + (1 ^ sw)] = make_uint4(pk[c + 4], pk[c + 5], pk[c + 6], pk[c + 7]);
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -418,22 +417,28 @@ __device__ __forceinline__ void store_chunk_bf16(float* stg_f, const float (&v)[
       const uint4 val = stg[r * 2 + (h ^ ((r >> 2) & 1))];
       const long orow_r = __shfl_sync(0xffffffffu, orow, r);
       const int nlim_r = __shfl_sync(0xffffffffu, nlim, r);
-      const int n = nb + c + h * 8;
-      __nv_bfloat16* cp = C + orow_r * ldc + n;
+      const int n = nb + pass * 16 + h * 8;
+      uint16_t* cp = C + orow_r * ldc + n;
       if (n + 7 < nlim_r && vec_ok) {
         *reinterpret_cast<uint4*>(cp) = val;
       } else {
         const uint32_t w[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (n + j < nlim_r) {
-            const uint16_t bits = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
-            *reinterpret_cast<uint16_t*>(cp + j) = bits;
-          }
+          if (n + j < nlim_r) cp[j] = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
       }
     }
     __syncwarp();
   }
+}
+
+__device__ __forceinline__ void store_chunk_bf16(float* stg_f, const float (&v)[32], int lane,
+                                                 __nv_bfloat16* __restrict__ C, long ldc,
+                                                 long orow, int nlim, int nb, bool vec_ok) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  store_chunk_16(stg_f, pk, lane, reinterpret_cast<uint16_t*>(C), ldc, orow, nlim, nb, vec_ok);
 }
 
 // one 64-bit shared-memory descriptor = constant bits | (address >> 4)
@@ -522,7 +527,71 @@ struct NTArgs {
   double* colsum;
   double* colsumsq;
   int accumulate, flush_kb, stages, stat_cols;
+  // contextualised-MSE epilogue (fused regression head, tc_gemm_nt2_kernel<.., CTX = true>):
+  // C / cx_lo receive the fp16 pair of s * (prediction - label window) instead of the
+  // prediction; cx_loss += sum d^2; cx_db[n] += sum_rows d
+  const float* cx_label;           // (B, F, T) fp32
+  int cx_F, cx_T, cx_r, cx_nvalid; // label geometry; columns >= cx_nvalid are padding (zeros)
+  const float* cx_scale;           // device {1/s, s}
+  void* cx_lo;
+  double* cx_loss;
+  double* cx_db;
 };
+
+// Output stage of the fused regression head (losses.py:15-37 + nn.MSELoss fused into the
+// output GEMM of MLPMinion, minions.py:494-524): thread = row (b, t), its 32 columns walk the
+// (feature f, context slot j) pairs; label element = label[b][f][t + j - r/2] (zero outside).
+template <int CPW>
+__device__ __forceinline__ void nt_output_ctx(float (&sums)[CPW][32], const NTArgs& a, float alpha,
+                                              int m0, int n0, int cc0, int q, int lane, float* stg,
+                                              double& loss_acc, bool vec_ok) {
+  const int M = a.M, NV = a.cx_nvalid;
+  const int T = a.cx_T, F = a.cx_F, r = a.cx_r;
+  const int m = m0 + q * 32 + lane;
+  const bool row_ok = m < M;
+  const long b = row_ok ? m / T : 0;
+  const int t = row_ok ? (int)(m - b * T) : 0;
+  const float s = __ldg(a.cx_scale + 1);
+  const float* lab_b = a.cx_label + b * F * T;
+  const long orow = row_ok ? m : 0;
+  const int nlim = row_ok ? a.N : 0;             // padding columns are written (as zeros)
+#pragma unroll
+  for (int h = 0; h < CPW; ++h) {
+    const int nb = n0 + (cc0 + 4 * h) * 32;
+    int f = nb / r, j = nb - f * r;
+    float d2 = 0.f;
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int jn = 0; jn < 32; jn += 2) {
+      float d[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = nb + jn + e;
+        float dd = 0.f;
+        if (row_ok && n < NV) {
+          const float x = fmaf(sums[h][jn + e], alpha, a.bias ? __ldg(a.bias + n) : 0.f);
+          const int tt = t + j - (r >> 1);
+          const float lab = (tt >= 0 && tt < T) ? __ldg(lab_b + (long)f * T + tt) : 0.f;
+          dd = x - lab;
+        }
+        if (++j == r) { j = 0; ++f; }
+        d[e] = dd;
+        sums[h][jn + e] = dd;
+        d2 = fmaf(dd, dd, d2);
+      }
+      __half h0, l0, h1, l1;
+      f16_split(d[0] * s, h0, l0);
+      f16_split(d[1] * s, h1, l1);
+      hi[jn >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[jn >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    loss_acc += (double)d2;
+    store_chunk_16(stg, hi, lane, reinterpret_cast<uint16_t*>(a.C), a.ldc, orow, nlim, nb, vec_ok);
+    store_chunk_16(stg, lo, lane, reinterpret_cast<uint16_t*>(a.cx_lo), a.ldc, orow, nlim, nb, vec_ok);
+    const float s1 = colsum32(sums[h], lane);          // bias gradient: column sums of d
+    if (nb + lane < NV && s1 != 0.f) atomicAdd(a.cx_db + nb + lane, (double)s1);
+  }
+}
 
 // Output stage shared by the 1-CTA and CTA-pair NT kernels: alpha / bias, row map and
 // validity, store (fp32 or bf16), BatchNorm column statistics of the fp32 values.
@@ -783,7 +852,7 @@ struct NT2Cfg {
   static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
 
-template <int BN, int MODE, bool OUT16>
+template <int BN, int MODE, bool OUT16, bool CTX = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS_V3, 1)
 tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                    const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
@@ -925,6 +994,7 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                                 : (((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0));
       const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.f);
       float* stg = s_out + e * OUT_STG_FLOATS;
+      double cx_loss = 0.0;
       const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
       uint32_t c = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
@@ -943,7 +1013,14 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(acc_empty0 + b * 8);
         }
-        nt_output<Cfg::CPW, OUT16>(sums, a, alpha, m0, n0, cc0, q, lane, stg, s_stats, vec_ok);
+        if constexpr (CTX)
+          nt_output_ctx<Cfg::CPW>(sums, a, alpha, m0, n0, cc0, q, lane, stg, cx_loss, vec_ok);
+        else
+          nt_output<Cfg::CPW, OUT16>(sums, a, alpha, m0, n0, cc0, q, lane, stg, s_stats, vec_ok);
+      }
+      if constexpr (CTX) {
+        cx_loss = warp_sum_d(cx_loss);
+        if (lane == 0 && cx_loss != 0.0) atomicAdd(a.cx_loss, cx_loss);
       }
     }
     if (want_stats) flush_stats(a, s_stats);
@@ -1503,6 +1580,31 @@ int launch_nt2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
   return PASE_OK;
 }
 
+// fused regression head: 3xF16 pair kernel with the contextualised-MSE epilogue
+int launch_nt2_ctx(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+                   const CUtensorMap& bl, NTArgs a, cudaStream_t st) {
+  using Cfg = NT2Cfg<128, 3>;
+  static bool attr = false;
+  a.stat_cols = 0;
+  a.stages = pick_stages(Cfg::STAGE_BYTES, 0);
+  const int smem = smem_bytes(a.stages, Cfg::STAGE_BYTES, 0);
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt2_kernel<128, 3, true, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      pase_set_error("pase_tc_gemm_nt_ctxmse: smem attribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr = true;
+  }
+  const long tiles = (long)((a.N + 127) / 128) * ((a.M + 2 * BM - 1) / (2 * BM));
+  const long max_pairs = pase_num_sms() / 2;
+  const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);
+  tc_gemm_nt2_kernel<128, 3, true, true><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_TC_LAUNCH_CHECK("pase_tc_gemm_nt_ctxmse");
+  return PASE_OK;
+}
+
 template <int BN, int MODE>
 int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
               const CUtensorMap& bl, TNArgs a, cudaStream_t st) {
@@ -1738,6 +1840,8 @@ int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const 
   a.rm = RowMap{rows_in, t_valid, rows_out, fold, N / fold};
   a.colsum = colsum; a.colsumsq = colsumsq; a.accumulate = accumulate; a.flush_kb = flush_kb;
   a.stages = 0; a.stat_cols = 0;
+  a.cx_label = nullptr; a.cx_F = a.cx_T = a.cx_r = a.cx_nvalid = 0; a.cx_scale = nullptr;
+  a.cx_lo = nullptr; a.cx_loss = nullptr; a.cx_db = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
 #define PASE_NT_MODES(FN, ...)                                                           \
   switch (mode * 2 + (c_bf16 ? 1 : 0)) {                                                 \
@@ -1768,6 +1872,50 @@ int pase_tc_gemm_nt(const void* Ahi, const void* Alo, long a_rows, int R, const 
 #undef PASE_NT1
 #undef PASE_NT2
 #undef PASE_NT_MODES
+}
+
+// Fused output layer of a regression head (MLPMinion W + ContextualizedLoss MSE,
+// minions.py:494-524, losses.py:15-37): residual = A B^T + bias - ctx(label) is never stored
+// as fp32; the fp16 pair of s * residual (the backward GEMMs' operand), sum residual^2 and
+// the column sums (bias gradient) come out of the GEMM epilogue.  3xF16 operands.
+int pase_tc_gemm_nt_ctxmse(const void* Ahi, const void* Alo, long a_rows, int R, const void* Bhi,
+                           const void* Blo, long ldb, void* Rhi, void* Rlo, long ldr, int M,
+                           int N, int K, const float* bias, const float* label, int B, int F,
+                           int T, int r, const float* scale, double* loss_acc, double* db_acc,
+                           void* stream) {
+  PASE_CHECK_ARG(Ahi && Alo && Bhi && Blo && Rhi && Rlo && label && scale && loss_acc && db_acc,
+                 "pase_tc_gemm_nt_ctxmse: null pointer");
+  PASE_CHECK_ARG(M == B * T && N == F * r && r >= 1 && (r & 1) && K > 0,
+                 "pase_tc_gemm_nt_ctxmse: need M == B*T, N == F*r, odd r (M=%d N=%d)", M, N);
+  PASE_CHECK_ARG(R >= 64 && (R % 64) == 0 && (K % 8) == 0 && (ldb % 8) == 0 && ldb >= K,
+                 "pase_tc_gemm_nt_ctxmse: operand alignment (R=%d K=%d ldb=%ld)", R, K, ldb);
+  PASE_CHECK_ARG((ldr % 128) == 0 && ldr >= N && aligned16(Rhi) && aligned16(Rlo),
+                 "pase_tc_gemm_nt_ctxmse: ldr=%ld must be a multiple of 128 and >= N", ldr);
+  PASE_CHECK_ARG(pase_tc_use_2cta(), "pase_tc_gemm_nt_ctxmse needs the CTA-pair kernels");
+  pase_tc_init_diag();
+  const int mode = 3, esz = 2, bk = 64;
+  CUtensorMap ah, al, bh, bl;
+  uint64_t adims[2] = {(uint64_t)R, (uint64_t)a_rows};
+  uint64_t astr[1] = {(uint64_t)R * esz};
+  uint32_t abox[2] = {(uint32_t)bk, (uint32_t)BM};
+  uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};          // rows >= N: zero-filled by TMA
+  uint64_t bstr[1] = {(uint64_t)ldb * esz};
+  uint32_t bbox[2] = {(uint32_t)bk, 64};
+  int rc;
+  if ((rc = make_map(&ah, Ahi, mode, 2, adims, astr, abox, "ctx A.hi")) != 0) return rc;
+  if ((rc = make_map(&al, Alo, mode, 2, adims, astr, abox, "ctx A.lo")) != 0) return rc;
+  if ((rc = make_map(&bh, Bhi, mode, 2, bdims, bstr, bbox, "ctx B.hi")) != 0) return rc;
+  if ((rc = make_map(&bl, Blo, mode, 2, bdims, bstr, bbox, "ctx B.lo")) != 0) return rc;
+  NTArgs a;
+  a.R = R; a.C = Rhi; a.ldc = ldr; a.M = M; a.N = (int)ldr; a.K = K; a.alpha = 1.f;
+  a.alpha_dev = nullptr; a.bias = bias;
+  a.rm = RowMap{M, M, M, 1, (int)ldr};
+  a.colsum = nullptr; a.colsumsq = nullptr; a.accumulate = 0;
+  a.flush_kb = K > 512 ? 2 : 0;
+  a.stages = 0; a.stat_cols = 0;
+  a.cx_label = label; a.cx_F = F; a.cx_T = T; a.cx_r = r; a.cx_nvalid = N; a.cx_scale = scale;
+  a.cx_lo = Rlo; a.cx_loss = loss_acc; a.cx_db = db_acc;
+  return launch_nt2_ctx(ah, al, bh, bl, a, (cudaStream_t)stream);
 }
 
 // A: groups x [rows_per_group x lda] starting `offA` rows into each group of pitch `pitchA`

@@ -331,6 +331,93 @@ def nct_to_rows(x):
     return _NctToRows.apply(x)
 
 
+class _FusedLinearCtxMSE(torch.autograd.Function):
+    """Output layer of a regression head FUSED with its contextualised MSE (MLPMinion.W +
+    ContextualizedLoss, minions.py:494-524, losses.py:15-37): loss = mean((h W^T + b -
+    ctx_r(label))^2) without ever storing the (rows, F*r) prediction in fp32 -- the GEMM
+    epilogue emits the fp16 pair of the (power-of-two scaled) residual, which IS the operand
+    of the two backward GEMMs, plus sum residual^2 and the bias gradient's column sums.
+    3xF16 precision only (the caller falls back to the unfused path otherwise)."""
+
+    _buffers = {}
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, label, F, r):
+        h, ldh = _rows_ld(h.detach())
+        rows, K = h.shape
+        N = weight.shape[0]
+        dev = h.device
+        label = label.detach().contiguous().float()
+        B, Fl, T = label.shape
+        assert Fl == F and N == F * r and rows == B * T
+        w2 = weight.detach().reshape(N, -1).contiguous()
+        ldr = _ru(N, 128)
+        hop = to_operand(_flat_from(h), rows * ldh, 3, "act")
+        wop = to_operand(w2.reshape(-1), N * K, 3, "weight")
+        # power-of-two scale from the bound |residual| <= max||h_m|| max||W_n|| + max|b| + max|label|
+        am = torch.zeros(4, dtype=torch.float32, device=dev)
+        ops.call("pase_rownorm_max", _flat_from(h), ldh, rows, K, am[0:1])
+        ops.call("pase_rownorm_max", w2.reshape(-1), K, N, K, am[1:2])
+        if bias is not None:
+            ops.call("pase_absmax", bias.detach().reshape(-1), N, am[2:3])
+        ops.call("pase_absmax", label.reshape(-1), label.numel(), am[3:4])
+        scale = torch.empty(2, dtype=torch.float32, device=dev)
+        ops.call("pase_bound_scale", am, scale)
+        # persistent residual buffers (two lps heads of the same shape are alive at once)
+        pool = _FusedLinearCtxMSE._buffers.setdefault((rows, ldr, str(dev)), [])
+        ent = next((e for e in pool if not e["busy"]), None)
+        if ent is None:
+            ent = {"hi": torch.zeros(rows * ldr, dtype=torch.float16, device=dev),
+                   "lo": torch.zeros(rows * ldr, dtype=torch.float16, device=dev), "busy": False}
+            pool.append(ent)
+        ent["busy"] = True                        # released by backward
+        acc = torch.zeros(1 + ldr, dtype=torch.float64, device=dev)
+        ops.call("pase_tc_gemm_nt_ctxmse", hop.hi, hop.lo, rows, ldh, wop.hi, wop.lo, K,
+                 ent["hi"], ent["lo"], ldr, rows, N, K,
+                 None if bias is None else bias.detach().reshape(-1), label.reshape(-1),
+                 B, F, T, r, scale, acc[0:1], acc[1:])
+        ctx.save_for_backward(h, w2, scale, acc)
+        ctx.hop, ctx.ent = hop, ent
+        ctx.dims = (rows, K, N, ldr, ldh, weight.shape, bias is not None)
+        return _loss_scalar(acc[0:1], rows * N)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w2, scale, acc = ctx.saved_tensors
+        rows, K, N, ldr, ldh, wshape, has_bias = ctx.dims
+        ent, dev = ctx.ent, h.device
+        coef = 2.0 / float(rows * N)
+        # d loss / d pred = g * coef * residual; the stored pair is s * residual
+        adev = (g.detach().reshape(1).float() * coef) * scale[0:1]
+        rop = Operand(ent["hi"], ent["lo"], adev)
+        dh = dW = db = None
+        if ctx.needs_input_grad[0]:
+            wT = torch.empty(K, ldr, dtype=torch.float32, device=dev)
+            ops.call("pase_transpose_pad", w2.reshape(-1), K, wT.reshape(-1), ldr, N, K)
+            dh = torch.empty(rows, K, dtype=torch.float32, device=dev)
+            gemm_nt(rop, ldr, rows * ldr, wT.reshape(-1), ldr, K * ldr, dh.reshape(-1), K,
+                    rows, K, ldr, None, a_kind="grad")
+        if ctx.needs_input_grad[1]:
+            dWp = torch.empty(ldr, K, dtype=torch.float32, device=dev)
+            gemm_tn(rop, ldr, rows * ldr, ctx.hop, ldh, rows * ldh, dWp.reshape(-1), K, ldr, K, rows)
+            dW = dWp[:N].reshape(wshape)
+        if has_bias and ctx.needs_input_grad[2]:
+            dbf = torch.empty(ldr, dtype=torch.float32, device=dev)
+            ops.call("pase_cast_d2f", acc[1:], dbf, ldr, coef)
+            db = dbf[:N] * g.detach().float()
+        ent["busy"] = False
+        return dh, dW, db, None, None, None
+
+
+def fused_linear_ctx_mse(h, weight, bias, label, F, r):
+    return _FusedLinearCtxMSE.apply(h, weight, bias, label, F, r)
+
+
+def fused_head_ok(K, ldh):
+    """The fused output layer needs the 3xF16 tensor-core path."""
+    return _MODES[PRECISION] == 3 and ldh % 64 == 0 and K % 64 == 0
+
+
 # ------------------------------------------------------------------ losses ---
 def _loss_scalar(acc, numel):
     return (acc / float(numel)).float().reshape(())

@@ -91,13 +91,38 @@ class MLPMinion(Model):
             h = Fn.prelu_rows(u, blk.act.weight, C)[:, :C]      # drop the leading-dim padding
         return Fn.linear_rows(h, self.W.weight, self.W.bias), h
 
-    def forward(self, x, alpha=1, device=None):
+    def forward(self, x, alpha=1, device=None, label=None):
+        """label (optional, (B, F, T)): fuse the output layer with the worker's contextualised
+        MSE (``pase.fuse_regression_loss``): the returned "prediction" is then a zero-stride
+        placeholder of the reference shape that carries the already-reduced loss
+        (``ContextualizedLoss`` returns it); the (B, F*r, T) prediction is never stored."""
         xin = RowsInput.of(x)
+        if label is not None and not self.skip and self._can_fuse(xin, label):
+            h = xin.rows
+            for blk in self.blocks:
+                C = blk.W.weight.shape[0]
+                h = Fn.prelu_rows(Fn.linear_rows(h, blk.W.weight, blk.W.bias), blk.act.weight, C)[:, :C]
+            F = label.shape[1]
+            loss = Fn.fused_linear_ctx_mse(h, self.W.weight, self.W.bias, label.to(h.device), F,
+                                           int(self.r))
+            pred = torch.zeros(1, device=h.device).expand(xin.B, self.num_outputs, xin.T)
+            pred._pase_fused_loss = loss
+            return pred
         y, h = self.forward_rows(xin.rows)
         pred = rows_to_pred(y, xin.B, xin.T, self.num_outputs)
         if self.skip:
             return pred, rows_to_pred(h, xin.B, xin.T, self.hidden_size)
         return pred
+
+    def _can_fuse(self, xin, label):
+        loss = self.loss
+        if getattr(loss, "kind", None) != "MSELoss" or not self.r or int(self.r) % 2 != 1:
+            return False
+        if label.dim() != 3 or label.shape[1] * int(self.r) != self.num_outputs or \
+                label.shape[0] != xin.B or label.shape[2] != xin.T:
+            return False
+        K = self.W.weight.shape[1]
+        return Fn.fused_head_ok(K, K if self.blocks else xin.rows.stride(0))
 
 
 class SPCMinion(MLPMinion):

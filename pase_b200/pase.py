@@ -27,6 +27,11 @@ class pase(Model):
         self.classification_workers = nn.ModuleList()
         self.regularizer_workers = []
         self.fwd_cchunk = False
+        # opt-in: fuse each MLP regression head's output layer with its contextualised MSE
+        # (the (B, F*r, T) prediction -- 551 MB for the lps heads at B=32 -- is never
+        # stored; preds[name] is then a placeholder carrying the reduced loss).  Off by default:
+        # the trainer's histogram logging (trainer.py:405-413) reads preds[name].
+        self.fuse_regression_loss = False
         for kind, cfg_lst in minions_cfg.items():
             for cfg in cfg_lst:
                 cfg = dict(cfg)
@@ -62,9 +67,13 @@ class pase(Model):
 
         preds, labels = {}, {}
         for worker in self.regression_workers:
-            y = worker(chunk, alpha)
+            lab = x[worker.name].to(device).detach()
+            if self.fuse_regression_loss and hasattr(worker, "_can_fuse"):
+                y = worker(chunk, alpha, label=lab)
+            else:
+                y = worker(chunk, alpha)
             preds[worker.name] = y
-            labels[worker.name] = x[worker.name].to(device).detach()
+            labels[worker.name] = lab
         for worker in self.classification_workers:
             if worker.name in ("spc", "gap"):
                 y, label = worker(chunk, alpha, device=device)

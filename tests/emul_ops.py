@@ -614,3 +614,40 @@ def pase_scatter_copy(table, njobs, total, stream=None):
         _as(d, (rows, cols), (dld, 1)).copy_(_as(s, (rows, cols), (sld, 1)))
         done += rows * cols
     assert done == total
+
+
+def pase_rownorm_max(X, ld, rows, cols, amax):
+    v = _as(X, (rows, cols), (ld, 1)).double().pow(2).sum(1).sqrt().max()
+    amax[0] = max(float(amax[0]), float(v))
+
+
+def pase_bound_scale(a4, scale_out):
+    s = f16_grad_scale((float(a4[0]) * float(a4[1]) + float(a4[2]) + float(a4[3])) * 1.0001)
+    scale_out[0], scale_out[1] = 1.0 / s, s
+
+
+def pase_tc_gemm_nt_ctxmse(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, Rhi, Rlo, ldr, M, N, K, bias, label,
+                           B, F, T, r, scale, loss_acc, db_acc):
+    assert M == B * T and N == F * r and ldr % 128 == 0
+    need = M * R + K
+    A = torch.zeros(need)
+    lim = min(a_rows * R, Ahi.numel(), need)
+    A[:lim] = _operand(Ahi, Alo, 3, lim)
+    Bm = _operand(Bhi, Blo, 3, N * ldb)
+    a = _as(A, (M, K), (R, 1)).double()
+    b = _as(Bm, (N, K), (ldb, 1)).double()
+    pred = a @ b.t()
+    if bias is not None:
+        pred = pred + bias[:N].double()[None, :]
+    d = (pred - _ctx(label, B, F, T, r).double())
+    loss_acc[0] += (d * d).sum()
+    db_acc[:N] += d.sum(0)
+    s = float(scale[1])
+    v = (d * s).float()
+    hi = v.to(torch.float16)
+    out_hi = torch.zeros(M, ldr, dtype=torch.float16)
+    out_lo = torch.zeros(M, ldr, dtype=torch.float16)
+    out_hi[:, :N] = hi
+    out_lo[:, :N] = ((v - hi.float()) * F16_LO_MUL).to(torch.float16)
+    Rhi[:M * ldr] = out_hi.reshape(-1)
+    Rlo[:M * ldr] = out_lo.reshape(-1)

@@ -80,3 +80,32 @@ def test_state_dict_keys_match_reference_layout():
             assert k.split("/", 1)[1] in keys, k
     assert "regression_workers.0.blocks.0.deconv.weight" in keys
     assert "classification_workers.1.minion.W.bias" in keys
+
+
+def test_fused_regression_heads_equal_unfused(emulated):
+    """pase.fuse_regression_loss: same losses, same total, same gradients as the unfused heads
+    (3xF16 GEMM mode; emulated kernels)."""
+    from pase_b200 import functional as Fn
+    assert Fn.PRECISION == "3xf16"
+    res = {}
+    for fused in (False, True):
+        gold, meta, model, batch = build_case("pase_plus_workers_3200")
+        model.fuse_regression_loss = fused
+        random.seed(meta["seed"])
+        h, chunk, preds, labels = model(batch, 1, "cpu")
+        tot, losses = total_loss(model, preds, labels)
+        tot.backward()
+        res[fused] = (float(tot), {k: float(v) for k, v in losses.items()},
+                      {k: p.grad.clone() for k, p in model.named_parameters()}, preds)
+    (ta, la, ga, _), (tb, lb, gb, pb) = res[False], res[True]
+    assert abs(ta - tb) <= 1e-5 * abs(ta)
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 2e-5 * max(abs(la[k]), 1e-6), k
+    for k in ga:
+        if k.startswith("frontend.") and k.endswith(("conv.bias", "W.bias")):
+            continue                      # analytically zero under train-mode BN: noise only
+        scale = float(ga[k].abs().max())
+        assert float((ga[k] - gb[k]).abs().max()) <= 2e-4 * scale + 1e-9, k
+    # fused predictions are placeholders of the reference shape
+    assert tuple(pb["lps"].shape) == tuple(res[False][3]["lps"].shape)
+    assert pb["lps"].stride() == (0, 0, 0)

@@ -140,3 +140,72 @@ def test_workers_plus_full_length_against_oracle(precision):
         assert not bad, "; ".join(bad[:10])
     finally:
         Fn.set_precision(prev)
+
+
+def test_fused_regression_heads_gpu():
+    """pase.fuse_regression_loss on the GPU (3xF16): the contextualised-MSE epilogue of the
+    output GEMM gives the same losses and gradients as the unfused heads at T=32000, and the
+    fused GEMM kernel matches its spec (tests/emul_ops.py) on a ragged shape."""
+    import copy
+    import emul_ops
+    from pase_b200 import _lib
+    from helpers import resolve_cfg, fill_state_dict, rel_l2
+    from pase_b200.pase import pase as native_pase, total_loss
+    from pase_b200.utils import parse_workers
+    from pase_b200 import functional as Fn
+    # --- kernel vs spec: B=3, T=50, F=11, r=7 (N=77 -> ldr=128), K=128
+    B, T, F, r, K = 3, 50, 11, 7, 128
+    M, N, ldr = B * T, F * r, 128
+    g = torch.Generator().manual_seed(5)
+    h = torch.randn(M * K, generator=g)
+    W = torch.randn(N * K, generator=g) * 0.1
+    bias, label = torch.randn(N, generator=g), torch.randn(B * F * T, generator=g)
+    def pair(x):
+        hi = x.to(torch.float16)
+        return hi, ((x - hi.float()) * 2048.0).to(torch.float16)
+    (hh, hl), (wh, wl) = pair(h), pair(W)
+    scale = torch.tensor([1.0 / 64.0, 64.0])
+    args = [hh, hl, M, K, wh, wl, K, torch.zeros(M * ldr, dtype=torch.float16),
+            torch.zeros(M * ldr, dtype=torch.float16), ldr, M, N, K, bias, label, B, F, T, r, scale,
+            torch.zeros(1, dtype=torch.float64), torch.zeros(ldr, dtype=torch.float64)]
+    cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    emul_ops.call("pase_tc_gemm_nt_ctxmse", *cpu)
+    _lib.call("pase_tc_gemm_nt_ctxmse", *dev)
+    torch.cuda.synchronize()
+    vc = cpu[7].float() + cpu[8].float() / 2048.0
+    vd = dev[7].cpu().float() + dev[8].cpu().float() / 2048.0
+    assert float((vc - vd).abs().max()) <= 4e-6 * float(vc.abs().max())
+    assert abs(float(cpu[20]) - float(dev[20].cpu())) <= 1e-5 * float(cpu[20])
+    assert float((cpu[21] - dev[21].cpu()).abs().max()) <= 1e-5 * float(cpu[21].abs().max())
+    # --- whole model, fused vs unfused
+    fe_cfg, wcfg = resolve_cfg("cfg/frontend/PASE+.cfg"), _workers_plus_cfg()
+    Bm, Tm, Tq, seed = 2, 32000, 200, 73
+    prev = Fn.PRECISION
+    Fn.set_precision("3xf16")
+    try:
+        res = {}
+        for fused in (False, True):
+            model = native_pase(frontend_cfg=fe_cfg, minions_cfg=parse_workers(copy.deepcopy(wcfg)))
+            model.load_state_dict(fill_state_dict(model.state_dict(), seed))
+            model = model.cuda().train()
+            model.fuse_regression_loss = fused
+            batch = {k: seeded_randn((Bm, 1, Tm), seed + 10 + i, 0.5).cuda()
+                     for i, k in enumerate(["chunk", "chunk_ctxt", "chunk_rand", "cchunk"])}
+            for i, w in enumerate(wcfg["regr"]):
+                if w["name"] != "cchunk":
+                    batch[w["name"]] = seeded_randn((Bm, w["num_outputs"], Tq), seed + 100 + i).cuda()
+            hh_, chunk, preds, labels = model(batch, 1, "cuda")
+            tot, per = total_loss(model, preds, labels)
+            tot.backward()
+            res[fused] = (float(tot), {k: float(v) for k, v in per.items()},
+                          {k: p.grad.detach().cpu() for k, p in model.named_parameters()})
+        (ta, la, ga), (tb, lb, gb) = res[False], res[True]
+        assert abs(ta - tb) <= 2e-5 * abs(ta)
+        for k in la:
+            assert abs(la[k] - lb[k]) <= 5e-5 * max(abs(la[k]), 1e-6), k
+        for k in ga:
+            if k.startswith("regression_workers") and not k.startswith("regression_workers.0."):
+                assert rel_l2(gb[k], ga[k]) < 1e-4, k       # the fused heads themselves
+    finally:
+        Fn.set_precision(prev)
