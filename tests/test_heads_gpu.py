@@ -206,6 +206,13 @@ def test_fused_regression_heads_gpu():
             assert abs(la[k] - lb[k]) <= 5e-5 * max(abs(la[k]), 1e-6), k
         for k in ga:
             if k.startswith("regression_workers") and not k.startswith("regression_workers.0."):
-                assert rel_l2(gb[k], ga[k]) < 1e-4, k       # the fused heads themselves
+                # the fused heads themselves.  The two models' encoder outputs differ by ~4e-7
+                # (order of the BatchNorm statistics' atomics), which now and then flips ONE
+                # hidden PReLU gate of a head (|u| ~ 1e-7): the hidden layer's weight / bias
+                # gradients then move by ~(1-alpha) dh x^T / |dW| = 2e-4..1e-3 (measured; the
+                # same spread shows between two unfused runs).  Output-layer gradients have no
+                # gate between them and the loss.
+                lim = 5e-3 if ".blocks." in k and ".W." in k else 2e-5
+                assert rel_l2(gb[k], ga[k]) < lim, (k, rel_l2(gb[k], ga[k]))
     finally:
         Fn.set_precision(prev)
