@@ -207,7 +207,8 @@ int pase_bn_prelu_pad_fwd(const void* y, int y_bf16, long y_sample_stride, int N
                           float* pool, long pool_sample_stride, long pool_row_stride,
                           int pool_d, int pool_T, void* stream);
 /* backward, pass 1: g = sum of gradient sources (srcA: fp32 or bf16 as its dgrad GEMM
- * wrote it; srcB / pool: fp32); du = PReLU'(u) g written to dst (same type as y);
+ * wrote it; srcB / pool: fp32); du = PReLU'(u) g written to dst (same type as y; NULL:
+ * not stored, see pase_bn_prelu_bwd_apply_src);
  * accumulates S1=sum du, S2=sum du*xhat, dalpha (double[C] each).  amax (float[2],
  * optional, caller-zeroed): max|du|, max|xhat| for the fp16-pair gradient scale. */
 int pase_bn_prelu_bwd_reduce(const void* y, int y_bf16, long y_sample_stride, int N, int T, int C,
@@ -231,6 +232,23 @@ int pase_bn_prelu_bwd_apply(const void* y, int y_bf16, long y_sample_stride, int
                             const void* du, void* dst, void* dst_lo, int dst_fmt,
                             long dst_sample_stride, double* dbias_acc,
                             const float* amax, float* scale_out, void* stream);
+/* backward, pass 2 WITHOUT a stored du: du = PReLU'(u) g is recomputed from the gradient
+ * sources (arguments as in pass 1, which is then called with dst = NULL and writes only its
+ * sums): one write and one read of the layer's activation size less per block. */
+int pase_bn_prelu_bwd_apply_src(const void* y, int y_bf16, long y_sample_stride, int N, int T,
+                                int C, const float* mean, const float* invstd,
+                                const float* gamma, const float* scale, const float* shift,
+                                const float* alpha, const double* S1, const double* S2,
+                                double count,
+                                const void* srcA, int a_bf16, long a_sample_stride,
+                                long a_row_stride, int padL, int padR,
+                                const float* srcB, long b_sample_stride, long b_row_stride,
+                                int b_shift,
+                                const float* pool, long pool_sample_stride, long pool_row_stride,
+                                int pool_d, int pool_T,
+                                void* dst, void* dst_lo, int dst_fmt, long dst_sample_stride,
+                                double* dbias_acc, const float* amax, float* scale_out,
+                                void* stream);
 /* plain per-channel PReLU on (rows,C) (MLPBlock / GDeconv1DBlock act) */
 int pase_prelu_fwd(const float* u, float* h, const float* alpha, long rows, int C,
                    long ldu, long ldh, void* stream);

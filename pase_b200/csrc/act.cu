@@ -1,6 +1,7 @@
 // Padding, BatchNorm (batch statistics), PReLU and dense-skip pooling kernels.
 // All HBM-bound: channel-last float4 accesses, one pass per tensor.
 #include "common.cuh"
+#include "bn_stream.cuh"
 #include <cstdlib>
 
 namespace {
@@ -158,11 +159,61 @@ bn_prelu_pad_fwd_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
 }
 
 // ---- backward pass 1: du + reductions ----
-struct BwdSrc {
-  const void* A; long a_ss, a_rs; int padL, padR;
-  const float* B; long b_ss, b_rs; int b_shift;
-  const float* P; long p_ss, p_rs; int pool_d, pool_T;
-};
+// (BwdSrc: bn_stream.cuh)
+
+// The gradient reaching this block's output for one run of RUN time steps (t0 ..) of the
+// channel quad at c: source A (the next layer's padded input gradient, reflect halo folded
+// back at the two sequence ends), the optional shifted source B (QRNN) and the broadcast of
+// the mean-pooled dense-skip gradient.  Straight-line loads first (no branch between a load
+// and the next one, so all DRAM requests of the run are in flight together).
+template <typename GT, int RUN>
+__device__ __forceinline__ void load_grad_run(const BwdSrc& s, int n, int T, long t0, int nvalid,
+                                              int c, float4 (&gs)[RUN]) {
+  const GT* an = reinterpret_cast<const GT*>(s.A) + (long)n * s.a_ss + c;
+#pragma unroll
+  for (int i = 0; i < RUN; ++i) {
+    const int t = (int)t0 + (i < nvalid ? i : 0);
+    gs[i] = ld4t(an + (long)(t + s.padL) * s.a_rs);
+  }
+  if (s.P != nullptr && s.pool_d > 0) {       // mean-pooled dense-skip gradient (broadcast)
+    const int pool_len = s.pool_T * s.pool_d;
+    const float inv_d = 1.f / (float)s.pool_d;
+    const float* pn = s.P + (long)n * s.p_ss + c;
+    float4 pv[RUN];
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      const int t = (int)t0 + (i < nvalid ? i : 0);
+      const int tw = t < pool_len ? t / s.pool_d : 0;
+      pv[i] = ld4(pn + (long)tw * s.p_rs);
+    }
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      const int t = (int)t0 + i;
+      const float w = (t < pool_len) ? inv_d : 0.f;
+      gs[i].x += pv[i].x * w; gs[i].y += pv[i].y * w;
+      gs[i].z += pv[i].z * w; gs[i].w += pv[i].w * w;
+    }
+  }
+  // rare: reflect-pad fold-back at the two sequence ends, second shifted source (QRNN)
+  const bool edge = (s.padL > 0 && t0 <= s.padL) || (s.padR > 0 && t0 + RUN >= T - 1 - s.padR);
+  if (edge || s.B != nullptr) {
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      if (i >= nvalid) break;
+      const int t = (int)t0 + i;
+      float4 g = gs[i];
+      auto add4 = [&](float4 v) { g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w; };
+      if (s.padL > 0 && t >= 1 && t <= s.padL) add4(ld4t(an + (long)(s.padL - t) * s.a_rs));
+      if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
+        add4(ld4t(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs));
+      if (s.B) {
+        const int tb = t + s.b_shift;
+        if (tb >= 0 && tb < T) add4(ld4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c));
+      }
+      gs[i] = g;
+    }
+  }
+}
 
 // YT: storage type of y and of du (dst); GT: storage type of the gradient source A (the
 // next layer's input gradient as its dgrad GEMM wrote it).  amax (optional, float[2]):
@@ -192,58 +243,17 @@ bn_prelu_bwd_reduce_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
   const float4 sc = ld4(scale + c), sh = ld4(shift + c), al = ld4(alpha + c);
   const float4 mu = ld4(mean + c), is = ld4(invstd + c);
   const YT* yn = y + (long)n * y_ss;
-  YT* dn = dst + (long)n * d_ss;
-  const int pool_len = s.pool_d > 0 ? s.pool_T * s.pool_d : 0;
-  const float inv_d = s.pool_d > 0 ? 1.f / (float)s.pool_d : 0.f;
+  YT* dn = dst ? dst + (long)n * d_ss : nullptr;
   for (long idx = idx0; idx < nthreads; idx += (long)gridDim.x * blockDim.x) {
     const long t0 = (idx / C4) * RUN;
     const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
     float4 gs[RUN], ys[RUN];
-    // phase 1: straight-line loads of the whole run (no branch between a load and the next
-    // one, so all DRAM requests of the run are in flight together)
-    const GT* an = reinterpret_cast<const GT*>(s.A) + (long)n * s.a_ss + c;
 #pragma unroll
     for (int i = 0; i < RUN; ++i) {
       const int t = (int)t0 + (i < nvalid ? i : 0);
-      gs[i] = ld4t(an + (long)(t + s.padL) * s.a_rs);
       ys[i] = ld4t(yn + (long)t * C + c);
     }
-    if (s.P != nullptr) {                       // mean-pooled dense-skip gradient (broadcast)
-      const float* pn = s.P + (long)n * s.p_ss + c;
-      float4 pv[RUN];
-#pragma unroll
-      for (int i = 0; i < RUN; ++i) {
-        const int t = (int)t0 + (i < nvalid ? i : 0);
-        const int tw = t < pool_len ? t / s.pool_d : 0;
-        pv[i] = ld4(pn + (long)tw * s.p_rs);
-      }
-#pragma unroll
-      for (int i = 0; i < RUN; ++i) {
-        const int t = (int)t0 + i;
-        const float w = (t < pool_len) ? inv_d : 0.f;
-        gs[i].x += pv[i].x * w; gs[i].y += pv[i].y * w;
-        gs[i].z += pv[i].z * w; gs[i].w += pv[i].w * w;
-      }
-    }
-    // rare: reflect-pad fold-back at the two sequence ends, second shifted source (QRNN)
-    const bool edge = (s.padL > 0 && t0 <= s.padL) || (s.padR > 0 && t0 + RUN >= T - 1 - s.padR);
-    if (edge || s.B != nullptr) {
-#pragma unroll
-      for (int i = 0; i < RUN; ++i) {
-        if (i >= nvalid) break;
-        const int t = (int)t0 + i;
-        float4 g = gs[i];
-        auto add4 = [&](float4 v) { g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w; };
-        if (s.padL > 0 && t >= 1 && t <= s.padL) add4(ld4t(an + (long)(s.padL - t) * s.a_rs));
-        if (s.padR > 0 && t <= T - 2 && t >= T - 1 - s.padR)
-          add4(ld4t(an + (long)(s.padL + 2 * (T - 1) - t) * s.a_rs));
-        if (s.B) {
-          const int tb = t + s.b_shift;
-          if (tb >= 0 && tb < T) add4(ld4(s.B + (long)n * s.b_ss + (long)tb * s.b_rs + c));
-        }
-        gs[i] = g;
-      }
-    }
+    load_grad_run<GT, RUN>(s, n, T, t0, nvalid, c, gs);
     const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
     const float alv[4] = {al.x, al.y, al.z, al.w};
     const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
@@ -266,7 +276,7 @@ bn_prelu_bwd_reduce_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
         mx_du = fmaxf(mx_du, fabsf(du[k]));
         mx_xh = fmaxf(mx_xh, fabsf(xh));
       }
-      st4t(dn + (long)t * C + c, make_float4(du[0], du[1], du[2], du[3]));
+      if (dn != nullptr) st4t(dn + (long)t * C + c, make_float4(du[0], du[1], du[2], du[3]));
     }
   }
   // lanes that own the same channel quad (C/4 < 32, power of two) combine before the
@@ -390,6 +400,116 @@ bn_prelu_bwd_apply_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
         for (int k = 0; k < 4; ++k) {
           const float xh = (vv[k] - muv[k]) * isv[k];
           o[k] = gi[k] * (dd[k] - m1[k] - xh * m2[k]);
+          acc[k] += o[k];
+        }
+        const long off = (long)n * d_ss + (long)t * C + c;
+        if constexpr (DF == PASE_FMT_F32) {
+          st4(reinterpret_cast<float*>(dst_v) + off, make_float4(o[0], o[1], o[2], o[3]));
+          if (dst_lo_v != nullptr)
+            st4(reinterpret_cast<float*>(dst_lo_v) + off,
+                make_float4(tf32_residual(o[0]), tf32_residual(o[1]), tf32_residual(o[2]),
+                            tf32_residual(o[3])));
+        } else if constexpr (DF == PASE_FMT_BF16) {
+          st4t(reinterpret_cast<__nv_bfloat16*>(dst_v) + off, make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+          st4_f16x2(reinterpret_cast<__half*>(dst_v) + off,
+                    reinterpret_cast<__half*>(dst_lo_v) + off,
+                    make_float4(o[0] * gs_scale, o[1] * gs_scale, o[2] * gs_scale,
+                                o[3] * gs_scale));
+        }
+      }
+    }
+    if (dbias) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&red[c + k], acc[k]);
+    }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, (double)red[i]);
+  }
+}
+
+// Backward pass 2 without a stored du: du = PReLU'(u) g is recomputed from the gradient
+// sources (same arithmetic as pass 1, so the sums S1 / S2 it is centred with are exactly its
+// own) -- pass 1 then writes nothing but its 3C sums, and the du tensor (one write + one read
+// of the layer's activation size) disappears from the step.
+template <typename YT, typename GT, int DF, int RUN>
+__global__ void __launch_bounds__(THREADS, 1)
+bn_prelu_bwd_apply_src_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
+                              const float* __restrict__ mean, const float* __restrict__ invstd,
+                              const float* __restrict__ gamma, const float* __restrict__ scale,
+                              const float* __restrict__ shift, const float* __restrict__ alpha,
+                              const double* __restrict__ S1, const double* __restrict__ S2,
+                              double inv_count, BwdSrc s, void* dst_v, long d_ss,
+                              double* __restrict__ dbias, void* dst_lo_v,
+                              const float* __restrict__ amax, float* __restrict__ scale_out) {
+  extern __shared__ float red[];      // [C] + [1]
+  for (int i = threadIdx.x; i < C + 1; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float gs_scale = 1.f;
+  if constexpr (DF == PASE_FMT_F16X2) {
+    const float mdu = amax[0], mxh = amax[1];
+    float b = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      const float gi = fabsf((gamma ? gamma[i] : 1.f) * invstd[i]);
+      const float m1 = fabsf((float)(S1[i] * inv_count)), m2 = fabsf((float)(S2[i] * inv_count));
+      b = fmaxf(b, gi * (mdu + m1 + mxh * m2));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, off));
+    if ((threadIdx.x & 31) == 0) atomic_max_pos(&red[C], b);
+    __syncthreads();
+    gs_scale = f16_grad_scale(red[C] * 1.0001f);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      scale_out[0] = 1.f / gs_scale;
+      scale_out[1] = gs_scale;
+    }
+  }
+  const int C4 = C >> 2;
+  const int n = blockIdx.y;
+  const long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nthreads = (long)C4 * ((T + RUN - 1) / RUN);
+  const int q = (int)(idx0 % C4);
+  const int c = q * 4;
+  float acc[4] = {0, 0, 0, 0};
+  if (idx0 < nthreads) {
+    float m1[4], m2[4], gi[4], muv[4], isv[4], scv[4], shv[4], alv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      m1[k] = (float)(S1[c + k] * inv_count);
+      m2[k] = (float)(S2[c + k] * inv_count);
+      muv[k] = mean[c + k];
+      isv[k] = invstd[c + k];
+      gi[k] = (gamma ? gamma[c + k] : 1.f) * isv[k];
+      scv[k] = scale[c + k];
+      shv[k] = shift[c + k];
+      alv[k] = alpha[c + k];
+    }
+    const YT* yn = y + (long)n * y_ss;
+    for (long idx = idx0; idx < nthreads; idx += (long)gridDim.x * blockDim.x) {
+      const long t0 = (idx / C4) * RUN;
+      const int nvalid = (T - (int)t0) < RUN ? (T - (int)t0) : RUN;
+      float4 vs[RUN], gs[RUN];
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
+        const int t = (int)t0 + (i < nvalid ? i : 0);
+        vs[i] = ld4t(yn + (long)t * C + c);
+      }
+      load_grad_run<GT, RUN>(s, n, T, t0, nvalid, c, gs);
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
+        if (i >= nvalid) break;
+        const int t = (int)t0 + i;
+        const float vv[4] = {vs[i].x, vs[i].y, vs[i].z, vs[i].w};
+        const float gg[4] = {gs[i].x, gs[i].y, gs[i].z, gs[i].w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float u = fmaf(vv[k], scv[k], shv[k]);
+          const float du = u > 0.f ? gg[k] : alv[k] * gg[k];
+          const float xh = (vv[k] - muv[k]) * isv[k];
+          o[k] = gi[k] * (du - m1[k] - xh * m2[k]);
           acc[k] += o[k];
         }
         const long off = (long)n * d_ss + (long)t * C + c;
@@ -740,13 +860,20 @@ int pase_bn_prelu_bwd_reduce(const void* y, int y_bf16, long y_sample_stride, in
                              long pool_sample_stride, long pool_row_stride, int pool_d,
                              int pool_T, void* dst, long dst_sample_stride, double* S1,
                              double* S2, double* dalpha, float* amax, void* stream) {
-  PASE_CHECK_ARG(y && mean && invstd && scale && shift && alpha && dst && S1 && S2 && dalpha &&
-                     srcA,
-                 "pase_bn_prelu_bwd_reduce: null pointer (srcA is mandatory)");
+  PASE_CHECK_ARG(y && mean && invstd && scale && shift && alpha && S1 && S2 && dalpha && srcA,
+                 "pase_bn_prelu_bwd_reduce: null pointer (srcA is mandatory; dst may be NULL: "
+                 "sums only, see pase_bn_prelu_bwd_apply_src)");
   PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 4096,
                  "pase_bn_prelu_bwd_reduce: C=%d must be a multiple of 4, <= 4096", C);
   BwdSrc s{srcA, a_sample_stride, a_row_stride, padL, padR, srcB, b_sample_stride, b_row_stride,
            b_shift, pool, pool_sample_stride, pool_row_stride, pool ? pool_d : 0, pool_T};
+  if (dst == nullptr) {                    // sums only: persistent staged kernel when it fits
+    BnStreamArgs sa{};
+    sa.y = y; sa.y_bf16 = y_bf16; sa.y_ss = y_sample_stride; sa.N = N; sa.T = T; sa.C = C;
+    sa.mean = mean; sa.invstd = invstd; sa.scale = scale; sa.shift = shift; sa.alpha = alpha;
+    sa.s = s; sa.a_bf16 = a_bf16; sa.S1 = S1; sa.S2 = S2; sa.dalpha = dalpha; sa.amax = amax;
+    if (pase_bn_stream_ok(sa)) return pase_bn_stream_reduce(sa, (cudaStream_t)stream);
+  }
   const int RUN = bn_run();
   const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
   long gx = (threads + THREADS - 1) / THREADS;
@@ -815,6 +942,72 @@ int pase_bn_prelu_bwd_apply(const void* y, int y_bf16, long y_sample_stride, int
 #undef PASE_APP
 #undef PASE_APP_R
   PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_apply");
+  return PASE_OK;
+}
+
+int pase_bn_prelu_bwd_apply_src(const void* y, int y_bf16, long y_sample_stride, int N, int T,
+                                int C, const float* mean, const float* invstd,
+                                const float* gamma, const float* scale, const float* shift,
+                                const float* alpha, const double* S1, const double* S2,
+                                double count, const void* srcA, int a_bf16, long a_sample_stride,
+                                long a_row_stride, int padL, int padR, const float* srcB,
+                                long b_sample_stride, long b_row_stride, int b_shift,
+                                const float* pool, long pool_sample_stride, long pool_row_stride,
+                                int pool_d, int pool_T, void* dst, void* dst_lo, int dst_fmt,
+                                long dst_sample_stride, double* dbias_acc, const float* amax,
+                                float* scale_out, void* stream) {
+  PASE_CHECK_ARG(y && mean && invstd && scale && shift && alpha && S1 && S2 && srcA && dst,
+                 "pase_bn_prelu_bwd_apply_src: null pointer");
+  PASE_CHECK_ARG(N > 0 && T > 0 && C > 0 && (C % 4) == 0 && C <= 8192,
+                 "pase_bn_prelu_bwd_apply_src: bad C=%d", C);
+  PASE_CHECK_ARG(dst_fmt >= 0 && dst_fmt <= 2, "pase_bn_prelu_bwd_apply_src: bad dst_fmt %d",
+                 dst_fmt);
+  PASE_CHECK_ARG(dst_fmt != PASE_FMT_F16X2 || (dst_lo && amax && scale_out && !y_bf16),
+                 "pase_bn_prelu_bwd_apply_src: the fp16-pair format needs dst_lo, amax, "
+                 "scale_out and fp32 y");
+  PASE_CHECK_ARG((dst_fmt == PASE_FMT_BF16) == (y_bf16 != 0),
+                 "pase_bn_prelu_bwd_apply_src: bf16 y goes with bf16 dst (and only with it)");
+  PASE_CHECK_ARG(!a_bf16 || y_bf16, "pase_bn_prelu_bwd_apply_src: bf16 srcA needs bf16 y");
+  BwdSrc s{srcA, a_sample_stride, a_row_stride, padL, padR, srcB, b_sample_stride, b_row_stride,
+           b_shift, pool, pool_sample_stride, pool_row_stride, pool ? pool_d : 0, pool_T};
+  {
+    BnStreamArgs sa{};
+    sa.y = y; sa.y_bf16 = y_bf16; sa.y_ss = y_sample_stride; sa.N = N; sa.T = T; sa.C = C;
+    sa.mean = mean; sa.invstd = invstd; sa.gamma = gamma; sa.scale = scale; sa.shift = shift;
+    sa.alpha = alpha; sa.s = s; sa.a_bf16 = a_bf16; sa.S1in = S1; sa.S2in = S2;
+    sa.inv_count = 1.0 / count; sa.dst = dst; sa.dst_lo = dst_lo; sa.dst_fmt = dst_fmt;
+    sa.d_ss = dst_sample_stride; sa.dbias = dbias_acc; sa.amax = const_cast<float*>(amax); sa.scale_out = scale_out;
+    if (pase_bn_stream_ok(sa) && (dst_sample_stride % 8) == 0 && aligned16(dst) &&
+        (dst_lo == nullptr || aligned16(dst_lo)))
+      return pase_bn_stream_apply(sa, (cudaStream_t)stream);
+  }
+  const int RUN = bn_run();
+  const long threads = (long)(C / 4) * ((T + RUN - 1) / RUN);
+  long gx = (threads + THREADS - 1) / THREADS;
+  if ((THREADS % (C / 4)) == 0) {
+    long cap = ((RUN == 8 ? 8L : 16L) * pase_num_sms() + N - 1) / N;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+  }
+  dim3 grid((unsigned)gx, N);
+  const size_t sm = (C + 1) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PASE_APS_R(YT, GT, DF, RV)                                                             \
+  bn_prelu_bwd_apply_src_kernel<YT, GT, DF, RV><<<grid, THREADS, sm, st>>>(                    \
+      reinterpret_cast<const YT*>(y), y_sample_stride, T, C, mean, invstd, gamma, scale, shift, \
+      alpha, S1, S2, 1.0 / count, s, dst, dst_sample_stride, dbias_acc, dst_lo, amax, scale_out)
+#define PASE_APS(YT, GT, DF) do { if (RUN == 8) PASE_APS_R(YT, GT, DF, 8); else PASE_APS_R(YT, GT, DF, 4); } while (0)
+  if (dst_fmt == PASE_FMT_BF16) {
+    if (a_bf16) PASE_APS(__nv_bfloat16, __nv_bfloat16, PASE_FMT_BF16);
+    else PASE_APS(__nv_bfloat16, float, PASE_FMT_BF16);
+  } else if (dst_fmt == PASE_FMT_F16X2) {
+    PASE_APS(float, float, PASE_FMT_F16X2);
+  } else {
+    PASE_APS(float, float, PASE_FMT_F32);
+  }
+#undef PASE_APS
+#undef PASE_APS_R
+  PASE_LAUNCH_CHECK("pase_bn_prelu_bwd_apply_src");
   return PASE_OK;
 }
 

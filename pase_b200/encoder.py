@@ -185,7 +185,6 @@ class EncoderPlan(object):
         self.apad, self.apad_lo, self.y, self.bn = [], [], [], []
         self.Wt, self.dWt, self.Wd, self.dyz, self.dyz_lo, self.dxpad = [], [], [], [], [], []
         self.gscale = []
-        du_max = 0
         for g in G:
             n_apad = N * g.apad_floats + g.K + 64
             self.apad.append(zo(n_apad))
@@ -209,10 +208,6 @@ class EncoderPlan(object):
             self.dyz_lo.append(zlo(n_dyz))
             self._ops[("dyz", g.idx)] = Operand(self.dyz[-1], self.dyz_lo[-1],
                                                 None if gs is None else gs, kind="grad")
-            du_max = max(du_max, n_dyz)
-        # 3xF16: du lives in an fp32 scratch between the two BatchNorm backward passes (the
-        # fp16 pair is written by pass 2 once the power-of-two scale is known)
-        self.du_scratch = e(du_max) if mode == 3 else None
         rows = N * self.Tq
         self.rows = rows
         if self.rnn:
@@ -696,24 +691,24 @@ def encoder_backward_steps(plan, mod, params, gout, gntc, training, sink=None, s
         d_ss = g.Ty * C if g.sinc else g.Pd * C
         dst = plan.dyz[l][doff:]
         dst_lo = None if plan.dyz_lo[l] is None else plan.dyz_lo[l][doff:]
-        # du: in place in the dy buffer (same type as y), except 3xF16 (fp32 scratch)
-        du = plan.du_scratch[doff:] if plan.mode == 3 else dst
         amax = None if plan.amax is None else plan.amax[2 * l:2 * l + 2]
         o = plan.bs_off[l]
         S1, S2, dal, dbi = sb[o:o + C], sb[o + C:o + 2 * C], sb[o + 2 * C:o + 3 * C], \
             sb[o + 3 * C:o + 4 * C]
+        # pass 1 writes only its sums; pass 2 recomputes du = PReLU'(u) g from the same
+        # gradient sources (no du tensor: one activation-sized write + read less per block)
+        src = (s["A"], s["a_bf16"], s["a_ss"], s["a_rs"], s["padL"], s["padR"],
+               s["B"], s["b_ss"], s["b_rs"], s["b_shift"], pool, Tq * Kc, Kc, pd, Tq)
         call("pase_bn_prelu_bwd_reduce", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
-             scale, shift, P(pre + "act.weight"),
-             s["A"], s["a_bf16"], s["a_ss"], s["a_rs"], s["padL"], s["padR"],
-             s["B"], s["b_ss"], s["b_rs"], s["b_shift"],
-             pool, Tq * Kc, Kc, pd, Tq, du, d_ss, S1, S2, dal, amax)
+             scale, shift, P(pre + "act.weight"), *src, None, d_ss, S1, S2, dal, amax)
         if training:
             a1, a2 = S1, S2
         else:
             a1, a2 = zeros[:C], zeros[C:2 * C]
-        call("pase_bn_prelu_bwd_apply", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
-             P(pre + "norm.weight"), a1, a2, float(N * g.T_out), du, dst, dst_lo, fmt, d_ss,
-             None if g.sinc else dbi, amax, plan.gscale[l])
+        call("pase_bn_prelu_bwd_apply_src", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
+             P(pre + "norm.weight"), scale, shift, P(pre + "act.weight"), a1, a2,
+             float(N * g.T_out), *src, dst, dst_lo, fmt, d_ss, None if g.sinc else dbi, amax,
+             plan.gscale[l])
         if g.sinc:
             plan.tn(("dyz", l), plan.dyz[l], g.Nn, g.rows_out, 0, False, ("apad", l), plan.apad[l],
                     g.lda, g.P, False, plan.dWt[l], g.K, g.Nn, g.K, N, g.rows_out, 1.0, 0)

@@ -247,11 +247,8 @@ def pase_bn_prelu_pad_fwd(y, y_bf16, y_ss, N, T, C, scale, shift, alpha, dst, ds
         pv += seen[:, padL:padL + L].reshape(N, pool_T, pool_d, C).mean(2)
 
 
-def pase_bn_prelu_bwd_reduce(y, y_bf16, y_ss, N, T, C, mean, invstd, scale, shift, alpha,
-                             srcA, a_bf16, a_ss, a_rs, padL, padR, srcB, b_ss, b_rs, b_shift,
-                             pool, p_ss, p_rs, pool_d, pool_T, dst, d_ss, S1, S2, dalpha, amax):
-    assert (y.dtype == torch.bfloat16) == bool(y_bf16) and dst.dtype == y.dtype
-    yv = _as(y, (N, T, C), (y_ss, C, 1)).float()
+def _bwd_grad_sources(N, T, C, srcA, a_bf16, a_ss, a_rs, padL, padR, srcB, b_ss, b_rs, b_shift,
+                      pool, p_ss, p_rs, pool_d, pool_T):
     g = torch.zeros(N, T, C)
     if srcA is not None:
         assert (srcA.dtype == torch.bfloat16) == bool(a_bf16)
@@ -269,6 +266,16 @@ def pase_bn_prelu_bwd_reduce(y, y_bf16, y_ss, N, T, C, mean, invstd, scale, shif
         L = pool_T * pool_d
         pv = _as(pool, (N, pool_T, C), (p_ss, p_rs, 1))
         g[:, :L] += (pv / pool_d).repeat_interleave(pool_d, dim=1)
+    return g
+
+
+def pase_bn_prelu_bwd_reduce(y, y_bf16, y_ss, N, T, C, mean, invstd, scale, shift, alpha,
+                             srcA, a_bf16, a_ss, a_rs, padL, padR, srcB, b_ss, b_rs, b_shift,
+                             pool, p_ss, p_rs, pool_d, pool_T, dst, d_ss, S1, S2, dalpha, amax):
+    assert (y.dtype == torch.bfloat16) == bool(y_bf16) and (dst is None or dst.dtype == y.dtype)
+    yv = _as(y, (N, T, C), (y_ss, C, 1)).float()
+    g = _bwd_grad_sources(N, T, C, srcA, a_bf16, a_ss, a_rs, padL, padR, srcB, b_ss, b_rs,
+                          b_shift, pool, p_ss, p_rs, pool_d, pool_T)
     u = yv * scale[:C] + shift[:C]
     pos = u > 0
     du = torch.where(pos, g, alpha[:C] * g)
@@ -279,14 +286,30 @@ def pase_bn_prelu_bwd_reduce(y, y_bf16, y_ss, N, T, C, mean, invstd, scale, shif
     if amax is not None:
         amax[0] = max(float(amax[0]), float(du.abs().max()))
         amax[1] = max(float(amax[1]), float(xh.abs().max()))
-    _as(dst, (N, T, C), (d_ss, C, 1)).copy_(du.to(dst.dtype))
+    if dst is not None:
+        _as(dst, (N, T, C), (d_ss, C, 1)).copy_(du.to(dst.dtype))
+
+
+def pase_bn_prelu_bwd_apply_src(y, y_bf16, y_ss, N, T, C, mean, invstd, gamma, scale, shift, alpha,
+                                S1, S2, count, srcA, a_bf16, a_ss, a_rs, padL, padR, srcB, b_ss,
+                                b_rs, b_shift, pool, p_ss, p_rs, pool_d, pool_T, dst, dst_lo,
+                                dst_fmt, d_ss, dbias, amax, scale_out):
+    assert (y.dtype == torch.bfloat16) == bool(y_bf16)
+    yv = _as(y, (N, T, C), (y_ss, C, 1)).float()
+    g = _bwd_grad_sources(N, T, C, srcA, a_bf16, a_ss, a_rs, padL, padR, srcB, b_ss, b_rs,
+                          b_shift, pool, p_ss, p_rs, pool_d, pool_T)
+    u = yv * scale[:C] + shift[:C]
+    du = torch.where(u > 0, g, alpha[:C] * g)
+    pase_bn_prelu_bwd_apply(y, y_bf16, y_ss, N, T, C, mean, invstd, gamma, S1, S2, count,
+                            du.reshape(-1), dst, dst_lo, dst_fmt, d_ss, dbias, amax,
+                            scale_out, _du_ss=T * C)
 
 
 def pase_bn_prelu_bwd_apply(y, y_bf16, y_ss, N, T, C, mean, invstd, gamma, S1, S2, count, du,
-                            dst, dst_lo, dst_fmt, d_ss, dbias, amax, scale_out):
-    assert (y.dtype == torch.bfloat16) == bool(y_bf16) and du.dtype == y.dtype
+                            dst, dst_lo, dst_fmt, d_ss, dbias, amax, scale_out, _du_ss=None):
+    assert (y.dtype == torch.bfloat16) == bool(y_bf16) and (du.dtype == y.dtype or _du_ss)
     yv = _as(y, (N, T, C), (y_ss, C, 1)).float()
-    dv = _as(du, (N, T, C), (d_ss, C, 1)).float()
+    dv = _as(du, (N, T, C), (d_ss if _du_ss is None else _du_ss, C, 1)).float()
     xh = (yv - mean[:C]) * invstd[:C]
     gi = (gamma[:C] if gamma is not None else 1.0) * invstd[:C]
     m1, m2 = (S1[:C] / count).float(), (S2[:C] / count).float()

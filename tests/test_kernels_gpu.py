@@ -241,6 +241,71 @@ def test_bn_prelu_bwd(N, T, C, padL, padR, pool_d, useB):
     assert float((vd / s - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("N,T,C,padL,padR,pool_d,useB,fmt", [
+    (2, 203, 64, 4, 5, 16, False, 0), (3, 77, 48, 0, 0, 0, True, 0), (2, 40, 512, 9, 10, 2, False, 2),
+    (2, 1603, 128, 5, 5, 8, False, 2), (3, 331, 256, 4, 5, 0, True, 2), (2, 203, 64, 4, 5, 16, False, 1),
+    (2, 77, 64, 0, 0, 0, True, 1)])
+def test_bn_prelu_bwd_no_du(N, T, C, padL, padR, pool_d, useB, fmt):
+    """Sums-only pass 1 (dst = NULL) + pass 2 that recomputes du from the gradient sources
+    (pase_bn_prelu_bwd_apply_src) against the spec, in the fp32 / fp16-pair / bf16 formats."""
+    bf = fmt == 1
+    Tp = T + padL + padR
+    ydt = torch.bfloat16 if bf else torch.float32
+    y = R(N * T * C, seed=24).to(ydt)
+    mean, invstd = R(C, seed=25, scale=0.1), R(C, seed=26).abs() + 0.5
+    scale, shift, alpha = R(C, seed=27), R(C, seed=28), R(C, seed=29, scale=0.3)
+    a_bf = bf and not useB                 # the last block's source is fp32 in every mode
+    srcA = R(N * Tp * C, seed=30).to(torch.bfloat16 if a_bf else torch.float32)
+    srcB = R(N * T * 2 * C, seed=31) if useB else None
+    pool_T = T // pool_d if pool_d else 0
+    pool = R(N * max(pool_T, 1) * C, seed=32) if pool_d else None
+    S1, S2, dal = (torch.zeros(C, dtype=torch.float64) for _ in range(3))
+    amax = torch.zeros(2)
+    src = [srcA, int(a_bf), Tp * C, C, padL, padR, srcB, T * 2 * C, 2 * C, 1, pool,
+           max(pool_T, 1) * C, C, pool_d, pool_T]
+    cpu, dev = run_both("pase_bn_prelu_bwd_reduce", [
+        y, int(bf), T * C, N, T, C, mean, invstd, scale, shift, alpha] + src +
+        [None, T * C, S1, S2, dal, amax], rtol=2e-4, atol=2e-5)
+    s1, s2, am = cpu[28], cpu[29], cpu[31]
+    gamma = R(C, seed=33)
+    odt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[fmt]
+    hi = torch.zeros(N * T * C, dtype=odt)
+    lo = torch.zeros(N * T * C, dtype=odt) if fmt == 2 else None
+    sc = torch.zeros(2)
+    args = [y, int(bf), T * C, N, T, C, mean, invstd, gamma, scale, shift, alpha, s1, s2,
+            float(N * T)] + src + [hi, lo, fmt, T * C, torch.zeros(C, dtype=torch.float64),
+                                   am if fmt == 2 else None, sc if fmt == 2 else None]
+    cpu2 = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    dev2 = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    emul_ops.call("pase_bn_prelu_bwd_apply_src", *cpu2)
+    _lib.call("pase_bn_prelu_bwd_apply_src", *dev2)
+    torch.cuda.synchronize()
+    i_hi, i_lo, i_db, i_sc = 30, 31, 34, 36
+    if fmt == 2:
+        assert torch.equal(cpu2[i_sc], dev2[i_sc].cpu())
+        vc = cpu2[i_hi].float() + cpu2[i_lo].float() / 2048.0
+        vd = dev2[i_hi].cpu().float() + dev2[i_lo].cpu().float() / 2048.0
+        assert float(vd.abs().max()) <= 16384.0
+        tol = 2e-5
+    else:
+        vc, vd = cpu2[i_hi].float(), dev2[i_hi].cpu().float()
+        tol = 2.0 ** -7 if bf else 2e-5
+    assert float((vc - vd).abs().max()) <= tol * float(vc.abs().max())
+    db_c, db_d = cpu2[i_db], dev2[i_db].cpu()
+    assert float((db_c - db_d).abs().max()) <= 1e-4 * float(db_c.abs().max()) + 1e-6
+    if not bf:
+        # identical to the two-pass form with a stored du
+        du = torch.zeros(N * T * C)
+        emul_ops.call("pase_bn_prelu_bwd_reduce", y, 0, T * C, N, T, C, mean, invstd, scale, shift,
+                      alpha, *src, du, T * C, torch.zeros(C, dtype=torch.float64),
+                      torch.zeros(C, dtype=torch.float64), torch.zeros(C, dtype=torch.float64), None)
+        ref = torch.zeros(N * T * C)
+        emul_ops.call("pase_bn_prelu_bwd_apply", y, 0, T * C, N, T, C, mean, invstd, gamma, s1, s2,
+                      float(N * T), du, ref, None, 0, T * C, None, None, None)
+        s = float(cpu2[i_sc][1]) if fmt == 2 else 1.0
+        assert float((vd / s - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
 def test_bn_prelu_bwd_bf16():
     """bf16 storage of y, the gradient source, du and dy (in place)."""
     N, T, C, padL, padR, pool_d = 2, 203, 64, 4, 5, 16

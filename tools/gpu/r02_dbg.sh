@@ -1,4 +1,6 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-.}"
-timeout 600 python tools/gpu/debug_fused2.py 1 60 2>&1 | tail -12
-timeout 600 python tools/gpu/debug_fused2.py 0 60 2>&1 | tail -12
+mkdir -p gpurun_out
+timeout 600 python tools/gpu/kineto_step.py 3xf16 graph > gpurun_out/kineto_3xf16.md 2> gpurun_out/kineto_err.log; echo rc=$?
+tail -5 gpurun_out/kineto_err.log
+head -30 gpurun_out/kineto_3xf16.md
