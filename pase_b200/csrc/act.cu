@@ -13,6 +13,7 @@ template <int DF>
 __global__ void reflect_pad_wave_kernel(const float* __restrict__ x, void* __restrict__ dst_v,
                                         void* __restrict__ dst_lo_v, int T, int padL, int Tp,
                                         long pitch) {
+  pdl_wait();
   const int n = blockIdx.y;
   for (int tau = blockIdx.x * blockDim.x + threadIdx.x; tau < Tp; tau += gridDim.x * blockDim.x) {
     const float v = x[(long)n * T + reflect_idx(tau - padL, T)];
@@ -37,6 +38,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colsum,
                                    const float* __restrict__ beta, float* running_mean,
                                    float* running_var, float momentum, float eps, float* mean,
                                    float* invstd, float* scale, float* shift) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
@@ -92,6 +94,7 @@ bn_prelu_pad_fwd_kernel(const YT* __restrict__ y, long y_ss, int T, int C,
                         const float* __restrict__ alpha, void* __restrict__ dst_v, long d_ss,
                         long d_rs, int padL, int Tp, float* __restrict__ pool, long p_ss,
                         long p_rs, int pool_d, int pool_T, void* __restrict__ dst_lo_v) {
+  pdl_wait();
   const int C4 = C >> 2;
   const int n = blockIdx.y;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -586,6 +589,7 @@ prelu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dh,
 // out[c] (+)= sum_r X[r*ld + c]
 __global__ void __launch_bounds__(THREADS)
 colsum_kernel(const float* __restrict__ X, long ld, long rows, int C, double* __restrict__ acc) {
+  pdl_wait();
   extern __shared__ float red[];      // [C]
   for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
@@ -607,6 +611,7 @@ colsum_kernel(const float* __restrict__ X, long ld, long rows, int C, double* __
 
 __global__ void cast_d2f_kernel(const double* __restrict__ src, float* __restrict__ dst, int n,
                                 float scale) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (float)(src[i] * (double)scale);
 }
@@ -615,6 +620,7 @@ __global__ void cast_d2f_kernel(const double* __restrict__ src, float* __restric
 __global__ void out_affine_nct_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                                       const float* __restrict__ shift, float* __restrict__ out,
                                       float* __restrict__ out_ntc, int T, int C) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -640,6 +646,7 @@ __global__ void out_bwd_reduce_kernel(const float* __restrict__ dout,
                                       const float* __restrict__ invstd, int T, int C,
                                       float* __restrict__ g_ntc, double* __restrict__ S1,
                                       double* __restrict__ S2) {
+  pdl_wait();
   __shared__ float tile[32][33];
   __shared__ float r1[32], r2[32];
   const int n = blockIdx.z;
@@ -680,6 +687,7 @@ __global__ void out_bwd_apply_kernel(float* __restrict__ g, const float* __restr
                                      const float* __restrict__ scale,
                                      const double* __restrict__ S1, const double* __restrict__ S2,
                                      double inv_count, int use_stats, long rows, int C) {
+  pdl_wait();
   const long total = rows * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
@@ -775,11 +783,11 @@ int pase_reflect_pad_wave(const float* x, void* dst, void* dst_lo, int dst_fmt, 
   dim3 grid(blocks_for(Tp, 256, 4), N);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_fmt == PASE_FMT_F32)
-    reflect_pad_wave_kernel<PASE_FMT_F32><<<grid, 256, 0, st>>>(x, dst, dst_lo, T, padL, Tp, pitch);
+    PASE_LAUNCH((reflect_pad_wave_kernel<PASE_FMT_F32>), grid, 256, 0, st, x, dst, dst_lo, T, padL, Tp, pitch);
   else if (dst_fmt == PASE_FMT_BF16)
-    reflect_pad_wave_kernel<PASE_FMT_BF16><<<grid, 256, 0, st>>>(x, dst, dst_lo, T, padL, Tp, pitch);
+    PASE_LAUNCH((reflect_pad_wave_kernel<PASE_FMT_BF16>), grid, 256, 0, st, x, dst, dst_lo, T, padL, Tp, pitch);
   else
-    reflect_pad_wave_kernel<PASE_FMT_F16X2><<<grid, 256, 0, st>>>(x, dst, dst_lo, T, padL, Tp, pitch);
+    PASE_LAUNCH((reflect_pad_wave_kernel<PASE_FMT_F16X2>), grid, 256, 0, st, x, dst, dst_lo, T, padL, Tp, pitch);
   PASE_LAUNCH_CHECK("pase_reflect_pad_wave");
   return PASE_OK;
 }
@@ -792,7 +800,7 @@ int pase_bn_finalize(const double* colsum, const double* colsumsq, int C, int fo
                  "pase_bn_finalize: bad args");
   PASE_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr),
                  "pase_bn_finalize: running stats must be given together");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  PASE_LAUNCH((bn_finalize_kernel), (C + 127) / 128, 128, 0, (cudaStream_t)stream, 
       colsum, colsumsq, C, fold, count, gamma, beta, running_mean, running_var, momentum, eps,
       mean, invstd, scale, shift);
   PASE_LAUNCH_CHECK("pase_bn_finalize");
@@ -831,7 +839,7 @@ int pase_bn_prelu_pad_fwd(const void* y, int y_bf16, long y_sample_stride, int N
   dim3 grid((unsigned)((threads + THREADS - 1) / THREADS), N);
   cudaStream_t st = (cudaStream_t)stream;
 #define PASE_FWD_R(YT, DF, RV)                                                                 \
-  bn_prelu_pad_fwd_kernel<YT, DF, RV><<<grid, THREADS, 0, st>>>(                               \
+  PASE_LAUNCH((bn_prelu_pad_fwd_kernel<YT, DF, RV>), grid, THREADS, 0, st,                                \
       reinterpret_cast<const YT*>(y), y_sample_stride, T, C, scale, shift, alpha, dst,         \
       dst_sample_stride, dst_row_stride, padL, Tp, pool, pool_sample_stride, pool_row_stride, \
       pool_d, pool_T, dst_lo)
@@ -1046,7 +1054,7 @@ int pase_colsum(const float* X, long ld, long rows, int C, double* acc, void* st
     long cap = (long)pase_num_sms() * 4;
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
-    colsum_kernel<<<(unsigned)nb, THREADS, Cp * sizeof(float), (cudaStream_t)stream>>>(
+    PASE_LAUNCH((colsum_kernel), (unsigned)nb, THREADS, Cp * sizeof(float), (cudaStream_t)stream, 
         X + c0, ld, rows, Cp, acc + c0);
     PASE_LAUNCH_CHECK("pase_colsum");
   }
@@ -1055,7 +1063,7 @@ int pase_colsum(const float* X, long ld, long rows, int C, double* acc, void* st
 
 int pase_cast_d2f(const double* src, float* dst, int n, float scale, void* stream) {
   PASE_CHECK_ARG(src && dst && n > 0, "pase_cast_d2f: bad args");
-  cast_d2f_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, dst, n, scale);
+  PASE_LAUNCH((cast_d2f_kernel), (n + 255) / 256, 256, 0, (cudaStream_t)stream, src, dst, n, scale);
   PASE_LAUNCH_CHECK("pase_cast_d2f");
   return PASE_OK;
 }
@@ -1065,7 +1073,7 @@ int pase_out_affine_nct(const float* y, const float* scale, const float* shift, 
   PASE_CHECK_ARG(y && scale && shift && out && N > 0 && T > 0 && C > 0,
                  "pase_out_affine_nct: bad args");
   dim3 grid((T + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  out_affine_nct_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(y, scale, shift, out, out_ntc, T,
+  PASE_LAUNCH((out_affine_nct_kernel), grid, block, 0, (cudaStream_t)stream, y, scale, shift, out, out_ntc, T,
                                                                   C);
   PASE_LAUNCH_CHECK("pase_out_affine_nct");
   return PASE_OK;
@@ -1077,7 +1085,7 @@ int pase_out_bwd_reduce(const float* dout, const float* dout_ntc, const float* y
   PASE_CHECK_ARG((dout || dout_ntc) && y && mean && invstd && g_ntc && S1 && S2,
                  "pase_out_bwd_reduce: null pointer");
   dim3 grid((T + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  out_bwd_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dout, dout_ntc, y, mean, invstd,
+  PASE_LAUNCH((out_bwd_reduce_kernel), grid, block, 0, (cudaStream_t)stream, dout, dout_ntc, y, mean, invstd,
                                                                   T, C, g_ntc, S1, S2);
   PASE_LAUNCH_CHECK("pase_out_bwd_reduce");
   return PASE_OK;
@@ -1088,7 +1096,7 @@ int pase_out_bwd_apply(float* g, const float* y, const float* mean, const float*
                        int use_stats, long rows, int C, void* stream) {
   PASE_CHECK_ARG(g && y && mean && invstd && scale && S1 && S2 && rows > 0 && C > 0,
                  "pase_out_bwd_apply: bad args");
-  out_bwd_apply_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
+  PASE_LAUNCH((out_bwd_apply_kernel), blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream, 
       g, y, mean, invstd, scale, S1, S2, 1.0 / count, use_stats, rows, C);
   PASE_LAUNCH_CHECK("pase_out_bwd_apply");
   return PASE_OK;

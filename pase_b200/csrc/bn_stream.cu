@@ -109,6 +109,7 @@ bn_bwd_stream_kernel(const BnStreamArgs a, const Geo g) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();
   // prologue: fill the ring
   const long first = blockIdx.x, stride = gridDim.x;
   if (tid == 0) {
@@ -337,7 +338,7 @@ int launch_cfg(const BnStreamArgs& a, cudaStream_t st) {
   }
   long grid = 2L * pase_num_sms();
   if (grid > g.total) grid = g.total;
-  kern<<<(unsigned)grid, THREADS, smem, st>>>(a, g);
+  PASE_LAUNCH(kern, (unsigned)grid, THREADS, smem, st, a, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     pase_set_error("bn_stream: launch failed: %s", cudaGetErrorString(e));

@@ -18,6 +18,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 }
 
 __global__ void absmax_kernel(const float* __restrict__ x, long n, float* __restrict__ amax) {
+  pdl_wait();
   float m = 0.f;
   const long stride = (long)gridDim.x * blockDim.x * 4;
   for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -38,6 +39,7 @@ __global__ void absmax_kernel(const float* __restrict__ x, long n, float* __rest
 __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi,
                                  __half* __restrict__ lo, long n, const float* __restrict__ amax,
                                  float* __restrict__ scale_out) {
+  pdl_wait();
   const float s = amax ? f16_grad_scale(amax[0] * 1.0001f) : 1.f;
   if (scale_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     scale_out[0] = 1.f / s;
@@ -104,7 +106,7 @@ int pase_cast_bf16(const float* x, void* dst, long n, void* stream) {
 
 int pase_absmax(const float* x, long n, float* amax, void* stream) {
   PASE_CHECK_ARG(x && amax && n > 0 && aligned16(x), "pase_absmax: bad args / alignment");
-  absmax_kernel<<<cast_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n, amax);
+  PASE_LAUNCH((absmax_kernel), cast_blocks(n), 256, 0, (cudaStream_t)stream, x, n, amax);
   PASE_LAUNCH_CHECK("pase_absmax");
   return PASE_OK;
 }
@@ -117,7 +119,7 @@ int pase_split_f16(const float* x, void* hi, void* lo, long n, const float* amax
                  "pase_split_f16: bad args / alignment");
   PASE_CHECK_ARG(amax == nullptr || scale_out != nullptr,
                  "pase_split_f16: a scaled split needs scale_out");
-  split_f16_kernel<<<cast_blocks(n), 256, 0, (cudaStream_t)stream>>>(
+  PASE_LAUNCH((split_f16_kernel), cast_blocks(n), 256, 0, (cudaStream_t)stream, 
       x, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), n, amax, scale_out);
   PASE_LAUNCH_CHECK("pase_split_f16");
   return PASE_OK;

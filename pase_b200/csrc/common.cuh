@@ -5,6 +5,8 @@
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 #include "../../include/pase_b200.h"
 
 void pase_set_error(const char* fmt, ...);
@@ -35,6 +37,49 @@ static inline int pase_num_sms() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+// ---- programmatic dependent launch (PDL) ----
+// Kernels launched through PASE_LAUNCH may be scheduled while the previous kernel of the stream
+// is still draining (graph capture turns this into a programmatic edge): launch latency, block
+// distribution and the kernel's own prologue overlap the predecessor's tail.  Contract: such a
+// kernel executes pdl_wait() before its first access to global memory (the wait returns once
+// every prerequisite grid has completed and flushed).
+// MEASURED (profiles/r02_history.md): inside the CUDA-graph replay of the encoder step the
+// attribute buys nothing (3.255 vs 3.258 ms with the implicit trigger at block exit) and the
+// early trigger below costs 1.5 % (the dependents' resident, waiting blocks get in the way of
+// the running kernel), so it is OFF unless PASE_B200_PDL=1; with the attribute off pdl_wait()
+// is a no-op.
+static inline bool pase_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PASE_B200_PDL");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pase_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block,
+                                          size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pase_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#define PASE_LAUNCH(kern, grid, block, smem, st, ...) \
+  pase_launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(st), __VA_ARGS__)
+// wait for the prerequisite grids, then let the NEXT kernel of the stream start its own
+// launch / prologue (it waits for this grid's completion in turn)
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

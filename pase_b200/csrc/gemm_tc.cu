@@ -715,6 +715,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -911,6 +912,7 @@ tc_gemm_nt2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
   cluster_sync_all();            // barriers of both CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -1120,6 +1122,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   if (nch <= 0) {                      // uniform across the CTA
     __syncthreads();
     if (warp == WARP_MMA) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -1316,6 +1319,7 @@ tc_gemm_tn2_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   // this CTA's half of the B tile: columns [j0 + rank*BH, +BH)
   const int jb = j0 + (int)rank * Cfg::BH;
   const int jq = jb / R, jc = jb % R;
@@ -1546,7 +1550,7 @@ int launch_nt(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   }
   const long tiles = (long)((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM);
   const int grid = (int)(tiles < pase_num_sms() ? tiles : pase_num_sms());
-  tc_gemm_nt_kernel<BN, MODE, ROWB, OUT16><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_LAUNCH((tc_gemm_nt_kernel<BN, MODE, ROWB, OUT16>), grid, NTHREADS_V3, smem, st, ah, al, bh, bl, a);
   PASE_TC_LAUNCH_CHECK("pase_tc_gemm_nt");
   return PASE_OK;
 }
@@ -1575,7 +1579,7 @@ int launch_nt2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
   const long tiles = (long)((a.N + BN - 1) / BN) * ((a.M + 2 * BM - 1) / (2 * BM));
   const long max_pairs = pase_num_sms() / 2;
   const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);   // cluster dims (2,1,1)
-  tc_gemm_nt2_kernel<BN, MODE, OUT16><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_LAUNCH((tc_gemm_nt2_kernel<BN, MODE, OUT16>), grid, NTHREADS_V3, smem, st, ah, al, bh, bl, a);
   PASE_TC_LAUNCH_CHECK("pase_tc_gemm_nt(2cta)");
   return PASE_OK;
 }
@@ -1600,7 +1604,7 @@ int launch_nt2_ctx(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorM
   const long tiles = (long)((a.N + 127) / 128) * ((a.M + 2 * BM - 1) / (2 * BM));
   const long max_pairs = pase_num_sms() / 2;
   const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);
-  tc_gemm_nt2_kernel<128, 3, true, true><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_LAUNCH((tc_gemm_nt2_kernel<128, 3, true, true>), grid, NTHREADS_V3, smem, st, ah, al, bh, bl, a);
   PASE_TC_LAUNCH_CHECK("pase_tc_gemm_nt_ctxmse");
   return PASE_OK;
 }
@@ -1656,7 +1660,7 @@ int launch_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   splits = (total + cps - 1) / cps;
   a.chunks_per_split = (int)cps;
   dim3 grid(tj, ti, (unsigned)splits);
-  tc_gemm_tn_kernel<BN, MODE><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_LAUNCH((tc_gemm_tn_kernel<BN, MODE>), grid, NTHREADS_V3, smem, st, ah, al, bh, bl, a);
   PASE_TC_LAUNCH_CHECK("pase_tc_gemm_tn");
   return PASE_OK;
 }
@@ -1701,7 +1705,7 @@ int launch_tn2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
   splits = (total + cps - 1) / cps;
   a.chunks_per_split = (int)cps;
   dim3 grid(2 * tj, ti, (unsigned)splits);               // cluster (2,1,1) along x
-  tc_gemm_tn2_kernel<BN, MODE><<<grid, NTHREADS_V3, smem, st>>>(ah, al, bh, bl, a);
+  PASE_LAUNCH((tc_gemm_tn2_kernel<BN, MODE>), grid, NTHREADS_V3, smem, st, ah, al, bh, bl, a);
   PASE_TC_LAUNCH_CHECK("pase_tc_gemm_tn(2cta)");
   return PASE_OK;
 }

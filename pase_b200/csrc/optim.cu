@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, long n, const AdamSeg* __restrict__ segs, int nseg,
                  const float* __restrict__ steps, float grad_scale) {
+  pdl_wait();
   __shared__ AdamSeg ss[SEG_MAX];
   __shared__ float c1[SEG_MAX], c2[SEG_MAX];       // lr / bias1, 1 / sqrt(bias2)
   for (int i = threadIdx.x; i < nseg; i += blockDim.x) {
@@ -90,7 +91,7 @@ int pase_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_a
   const long cap = (long)pase_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+  PASE_LAUNCH((adam_flat_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, 
       param, grad, exp_avg, exp_avg_sq, n, reinterpret_cast<const AdamSeg*>(seg_table), nseg, steps,
       grad_scale);
   PASE_LAUNCH_CHECK("pase_adam_flat");

@@ -100,6 +100,7 @@ __global__ void deconv_w_to_bwd_kernel(const float* __restrict__ W, float* __res
 // dst (cols x ldd) = src^T, src (rows x cols, ld lds); pads columns [rows, ldd) with 0
 __global__ void transpose_pad_kernel(const float* __restrict__ src, long lds,
                                      float* __restrict__ dst, long ldd, int rows, int cols) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -128,6 +129,7 @@ __global__ void sinc_make_kernel(const float* __restrict__ low_hz, const float* 
                                  const float* __restrict__ n_, const float* __restrict__ win,
                                  float* __restrict__ filt, float* __restrict__ Wp, int C, int k,
                                  int fold, int Kv, float min_low, float min_band, float sr) {
+  pdl_wait();
   extern __shared__ float f[];       // [k]
   const int co = blockIdx.x;
   const int half = k / 2;
@@ -158,6 +160,7 @@ __global__ void sinc_grad_kernel(const float* __restrict__ dWp, const float* __r
                                  const float* __restrict__ win, float* __restrict__ dlow,
                                  float* __restrict__ dband, int C, int k, int fold, int Kv,
                                  float min_low, float min_band, float sr) {
+  pdl_wait();
   __shared__ double r_hi[32], r_lo[32];
   const int co = blockIdx.x;
   const int half = k / 2;
@@ -239,6 +242,7 @@ __device__ __forceinline__ void w_store(float* dst, void* hi, void* lo, long e, 
 
 __global__ void conv_w_batch_kernel(const long* __restrict__ table, int njobs, long total, int op,
                                     float* __restrict__ dst_base, int fmt) {
+  pdl_wait();
   __shared__ long jt[WJOB_MAX * WJOB];
   for (int i = threadIdx.x; i < njobs * WJOB; i += blockDim.x) jt[i] = table[i];
   __syncthreads();
@@ -289,6 +293,7 @@ constexpr int WB_SMEM_FLOATS = 12000;          // 46.9 KB (+ the static job row 
 
 __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int njobs, int op,
                                           float* __restrict__ dst_base, int fmt) {
+  pdl_wait();
   extern __shared__ float tile[];
   __shared__ long J[WJOB];
   if (threadIdx.x == 0) {
@@ -350,6 +355,7 @@ __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int nj
 constexpr int SC_MAX = 128;
 
 __global__ void scatter_copy_kernel(const long* __restrict__ table, int njobs) {
+  pdl_wait();
   __shared__ long jt[SC_MAX * 6];
   __shared__ long pre[SC_MAX + 1];
   for (int i = threadIdx.x; i < njobs * 6; i += blockDim.x) jt[i] = table[i];
@@ -383,7 +389,7 @@ extern "C" {
 int pase_scatter_copy(const long* table, int njobs, long total, void* stream) {
   PASE_CHECK_ARG(table && njobs > 0 && njobs <= SC_MAX && total > 0,
                  "pase_scatter_copy: bad args (njobs=%d, at most %d)", njobs, SC_MAX);
-  scatter_copy_kernel<<<nblk(total), 256, 0, (cudaStream_t)stream>>>(table, njobs);
+  PASE_LAUNCH((scatter_copy_kernel), nblk(total), 256, 0, (cudaStream_t)stream, table, njobs);
   PASE_LAUNCH_CHECK("pase_scatter_copy");
   return PASE_OK;
 }
@@ -417,12 +423,11 @@ int pase_conv_w_batch(const long* table, int njobs, long total, int op, float* d
     // tiled: `total` thread blocks, 48 KB of shared memory (the caller guarantees that a
     // slab fits: (Cin+1)*k resp. 32*(8*k+1) floats <= 12000, Cout % 32 == 0, Cin % 8 == 0)
     PASE_CHECK_ARG(total < (1L << 31), "pase_conv_w_batch: too many blocks");
-    conv_w_batch_tiled_kernel<<<(unsigned)total, 256, WB_SMEM_FLOATS * sizeof(float),
-                                (cudaStream_t)stream>>>(table, njobs, op, dst_base, fmt);
+    PASE_LAUNCH((conv_w_batch_tiled_kernel), (unsigned)total, 256, WB_SMEM_FLOATS * sizeof(float), (cudaStream_t)stream, table, njobs, op, dst_base, fmt);
     PASE_LAUNCH_CHECK("pase_conv_w_batch");
     return PASE_OK;
   }
-  conv_w_batch_kernel<<<nblk(total), 256, 0, (cudaStream_t)stream>>>(table, njobs, total, op,
+  PASE_LAUNCH((conv_w_batch_kernel), nblk(total), 256, 0, (cudaStream_t)stream, table, njobs, total, op,
                                                                     dst_base, fmt);
   PASE_LAUNCH_CHECK("pase_conv_w_batch");
   return PASE_OK;
@@ -471,7 +476,7 @@ int pase_transpose_pad(const float* src, long lds, float* dst, long ldd, int row
   PASE_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ldd >= rows && lds >= cols,
                  "pase_transpose_pad: bad args");
   dim3 grid((unsigned)((ldd + 31) / 32), (cols + 31) / 32), block(32, 8);
-  transpose_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols);
+  PASE_LAUNCH((transpose_pad_kernel), grid, block, 0, (cudaStream_t)stream, src, lds, dst, ldd, rows, cols);
   PASE_LAUNCH_CHECK("pase_transpose_pad");
   return PASE_OK;
 }
@@ -482,7 +487,7 @@ int pase_sinc_make(const float* low_hz, const float* band_hz, const float* n_, c
   PASE_CHECK_ARG(low_hz && band_hz && n_ && window_ && Wp, "pase_sinc_make: null pointer");
   PASE_CHECK_ARG(C > 0 && (k & 1) && fold >= 1 && Kv >= k + fold - 1,
                  "pase_sinc_make: need odd k and Kv >= k+fold-1 (k=%d fold=%d Kv=%d)", k, fold, Kv);
-  sinc_make_kernel<<<C, 128, k * sizeof(float), (cudaStream_t)stream>>>(
+  PASE_LAUNCH((sinc_make_kernel), C, 128, k * sizeof(float), (cudaStream_t)stream, 
       low_hz, band_hz, n_, window_, filt, Wp, C, k, fold, Kv, min_low, min_band, sr);
   PASE_LAUNCH_CHECK("pase_sinc_make");
   return PASE_OK;
@@ -494,7 +499,7 @@ int pase_sinc_grad(const float* dWp, const float* low_hz, const float* band_hz, 
   PASE_CHECK_ARG(dWp && low_hz && band_hz && n_ && window_ && dlow && dband,
                  "pase_sinc_grad: null pointer");
   PASE_CHECK_ARG(C > 0 && (k & 1) && fold >= 1 && Kv >= k + fold - 1, "pase_sinc_grad: bad shape");
-  sinc_grad_kernel<<<C, 128, 0, (cudaStream_t)stream>>>(dWp, low_hz, band_hz, n_, window_, dlow,
+  PASE_LAUNCH((sinc_grad_kernel), C, 128, 0, (cudaStream_t)stream, dWp, low_hz, band_hz, n_, window_, dlow,
                                                         dband, C, k, fold, Kv, min_low, min_band,
                                                         sr);
   PASE_LAUNCH_CHECK("pase_sinc_grad");

@@ -14,6 +14,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 __global__ void __launch_bounds__(128)
 qrnn_scan_fwd_kernel(const float* __restrict__ Y, float* __restrict__ h, long ldh,
                      float* __restrict__ Cst, int T, int H) {
+  pdl_wait();
   const int n = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= H) return;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(128)
 qrnn_scan_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ Cst,
                      const float* __restrict__ dh, long lddh, float* __restrict__ dY, int T,
                      int H) {
+  pdl_wait();
   const int n = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= H) return;
@@ -107,7 +109,7 @@ int pase_qrnn_scan_fwd(const float* Y, float* h, long ldh, float* Cst, int N, in
   PASE_CHECK_ARG(Y && h && Cst && N > 0 && T > 0 && H > 0 && ldh >= H,
                  "pase_qrnn_scan_fwd: bad args");
   dim3 grid((H + 127) / 128, N);
-  qrnn_scan_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Y, h, ldh, Cst, T, H);
+  PASE_LAUNCH((qrnn_scan_fwd_kernel), grid, 128, 0, (cudaStream_t)stream, Y, h, ldh, Cst, T, H);
   PASE_LAUNCH_CHECK("pase_qrnn_scan_fwd");
   return PASE_OK;
 }
@@ -117,7 +119,7 @@ int pase_qrnn_scan_bwd(const float* Y, const float* Cst, const float* dh, long l
   PASE_CHECK_ARG(Y && Cst && dh && dY && N > 0 && T > 0 && H > 0 && lddh >= H,
                  "pase_qrnn_scan_bwd: bad args");
   dim3 grid((H + 127) / 128, N);
-  qrnn_scan_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Y, Cst, dh, lddh, dY, T, H);
+  PASE_LAUNCH((qrnn_scan_bwd_kernel), grid, 128, 0, (cudaStream_t)stream, Y, Cst, dh, lddh, dY, T, H);
   PASE_LAUNCH_CHECK("pase_qrnn_scan_bwd");
   return PASE_OK;
 }
