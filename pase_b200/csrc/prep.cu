@@ -296,10 +296,18 @@ __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int nj
   pdl_wait();
   extern __shared__ float tile[];
   __shared__ long J[WJOB];
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // job lookup by one warp: every lane tests one job's first block (one round of loads
+    // instead of a serial walk of dependent global reads by thread 0)
+    const int lane = threadIdx.x;
     int j = 0;
-    while (j + 1 < njobs && (long)blockIdx.x >= table[(j + 1) * WJOB + 11]) ++j;
-    for (int i = 0; i < WJOB; ++i) J[i] = table[j * WJOB + i];
+    for (int base = 0; base < njobs; base += 32) {
+      const int jj = base + lane;
+      const bool le = jj < njobs && table[jj * WJOB + 11] <= (long)blockIdx.x;
+      const unsigned m = __ballot_sync(0xffffffffu, le);
+      if (m) j = base + 31 - __clz(m);
+    }
+    if (lane < WJOB) J[lane] = table[j * WJOB + lane];
   }
   __syncthreads();
   const float* src = reinterpret_cast<const float*>(J[0]);

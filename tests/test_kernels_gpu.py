@@ -382,8 +382,11 @@ def test_output_norm_kernels():
     run_both("pase_ntc_to_nct", [R(N * T * 104, seed=46), 104, torch.zeros(N * C * T), N, C, T])
 
 
-def test_qrnn_scan():
-    N, T, H = 3, 23, 96
+@pytest.mark.parametrize("N,T,H", [(3, 23, 96), (2, 200, 512), (2, 16, 40), (1, 300, 64),
+                                   (1, 500, 32), (1, 700, 32), (2, 1, 33)])
+def test_qrnn_scan(N, T, H):
+    """T <= 512: time-segmented scans (16-step segments, 16 / 24 / 32 segments per block);
+    longer: the sequential kernels."""
     Y = R(N * T * 3 * H, seed=47)
     ldh = H + 32
     cpu, _ = run_both("pase_qrnn_scan_fwd", [Y, torch.zeros(N * T * ldh), ldh, torch.zeros(N * T * H),
