@@ -316,31 +316,70 @@ __global__ void conv_w_batch_tiled_kernel(const long* __restrict__ table, int nj
   void* lo = reinterpret_cast<void*>(J[3]);
   const int Cout = (int)J[4], Cin = (int)J[5], k = (int)J[6], sd = (int)J[7], taps = (int)J[8];
   const int b = (int)((long)blockIdx.x - J[11]);
+  // (index pairs are advanced incrementally: the integer divisions by the runtime Cin / k
+  // of a per-element e % Cin, e / Cin made these loops instruction-bound -- 35 us per launch
+  // for 31 MB)
+  const int nt = blockDim.x;
   if (op == 3) {                       // Wt[co][j][ci] = W[co][ci][j]
     const int n = Cin * k;
     const float* w = src + (long)b * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = w[i];
+    for (int i = threadIdx.x; i < n; i += nt) tile[i] = w[i];
     __syncthreads();
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      const int ci = e % Cin, jj = e / Cin;
+    int ci = threadIdx.x % Cin, jj = threadIdx.x / Cin;
+    const int dci = nt % Cin, djj = nt / Cin;
+    for (int e = threadIdx.x; e < n; e += nt) {
       w_store(dst, hi, lo, (long)b * n + e, tile[ci * k + jj], fmt);
+      ci += dci;
+      jj += djj;
+      if (ci >= Cin) {
+        ci -= Cin;
+        ++jj;
+      }
     }
   } else if (op == 5) {                // dW[co][ci][j] = dWt[co][j][ci]
     const int n = Cin * k, pitch = Cin + 1;
     const float* w = src + (long)b * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[(i / Cin) * pitch + (i % Cin)] = w[i];
+    {
+      int ci = threadIdx.x % Cin, jj = threadIdx.x / Cin;
+      const int dci = nt % Cin, djj = nt / Cin;
+      for (int i = threadIdx.x; i < n; i += nt) {
+        tile[jj * pitch + ci] = w[i];
+        ci += dci;
+        jj += djj;
+        if (ci >= Cin) {
+          ci -= Cin;
+          ++jj;
+        }
+      }
+    }
     __syncthreads();
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      const int jj = e % k, ci = e / k;
+    int jj = threadIdx.x % k, ci = threadIdx.x / k;
+    const int djj = nt % k, dci = nt / k;
+    for (int e = threadIdx.x; e < n; e += nt) {
       dst[(long)b * n + e] = tile[jj * pitch + ci];
+      jj += djj;
+      ci += dci;
+      if (jj >= k) {
+        jj -= k;
+        ++ci;
+      }
     }
   } else {                             // Wd[p][ci][v][co] = W[co][ci][sd*(taps-1-v)+p] | 0
     const int nci = Cin / WB_CI;
     const int co0 = (b / nci) * 32, ci0 = (b % nci) * WB_CI;
     const int seg = WB_CI * k, pitch = seg + 1;
-    for (int i = threadIdx.x; i < 32 * seg; i += blockDim.x) {
-      const int col = i / seg, r = i % seg;
-      tile[col * pitch + r] = src[((long)(co0 + col) * Cin + ci0) * k + r];
+    {
+      int col = threadIdx.x / seg, r = threadIdx.x % seg;
+      const int dcol = nt / seg, dr = nt % seg;
+      for (int i = threadIdx.x; i < 32 * seg; i += nt) {
+        tile[col * pitch + r] = src[((long)(co0 + col) * Cin + ci0) * k + r];
+        col += dcol;
+        r += dr;
+        if (r >= seg) {
+          r -= seg;
+          ++col;
+        }
+      }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;

@@ -16,6 +16,7 @@ projection (mean-pool commutes with a bias-free 1x1 conv, frontend.py:182,
 skips and the QRNN output are concatenated so W + all skips are one GEMM.
 """
 import math
+import os
 import torch
 
 from . import ops
@@ -699,13 +700,25 @@ def encoder_backward_steps(plan, mod, params, gout, gntc, training, sink=None, s
         # gradient sources (no du tensor: one activation-sized write + read less per block)
         src = (s["A"], s["a_bf16"], s["a_ss"], s["a_rs"], s["padL"], s["padR"],
                s["B"], s["b_ss"], s["b_rs"], s["b_shift"], pool, Tq * Kc, Kc, pd, Tq)
-        call("pase_bn_prelu_bwd_reduce", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
-             scale, shift, P(pre + "act.weight"), *src, None, d_ss, S1, S2, dal, amax)
+        if os.environ.get("PASE_B200_BN_DU") == "1":      # debug: two passes with a stored du
+            du = torch.empty(N * d_ss + 64, dtype=plan.y[l].dtype, device=plan.y[l].device)
+            call("pase_bn_prelu_bwd_reduce", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
+                 scale, shift, P(pre + "act.weight"), *src, du, d_ss, S1, S2, dal, amax)
+            call("pase_bn_prelu_bwd_apply", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
+                 P(pre + "norm.weight"), S1 if training else zeros[:C],
+                 S2 if training else zeros[C:2 * C], float(N * g.T_out), du, dst, dst_lo, fmt, d_ss,
+                 None if g.sinc else dbi, amax, plan.gscale[l])
+            _bn_du_debug = True
+        else:
+            _bn_du_debug = False
+            call("pase_bn_prelu_bwd_reduce", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
+                 scale, shift, P(pre + "act.weight"), *src, None, d_ss, S1, S2, dal, amax)
         if training:
             a1, a2 = S1, S2
         else:
             a1, a2 = zeros[:C], zeros[C:2 * C]
-        call("pase_bn_prelu_bwd_apply_src", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
+        if not _bn_du_debug:
+          call("pase_bn_prelu_bwd_apply_src", plan.y[l], ybf, g.Ty * C, N, g.T_out, C, mean, invstd,
              P(pre + "norm.weight"), scale, shift, P(pre + "act.weight"), a1, a2,
              float(N * g.T_out), *src, dst, dst_lo, fmt, d_ss, None if g.sinc else dbi, amax,
              plan.gscale[l])

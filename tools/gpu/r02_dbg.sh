@@ -1,6 +1,5 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-.}"
-mkdir -p gpurun_out
-timeout 600 python tools/gpu/kineto_step.py 3xf16 graph > gpurun_out/kineto_3xf16.md 2> gpurun_out/kineto_err.log; echo rc=$?
-tail -5 gpurun_out/kineto_err.log
-head -30 gpurun_out/kineto_3xf16.md
+timeout 300 python tools/gpu/debug_4001.py 2>&1 | tail -22
+PASE_B200_BN_STREAM=0 timeout 300 python tools/gpu/debug_4001.py 2>&1 | tail -22
+PASE_B200_BN_DU=1 timeout 300 python tools/gpu/debug_4001.py 2>&1 | tail -22
