@@ -16,7 +16,5 @@ except Exception as e:
 PY
 }
 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/n1.json 2> gpurun_out/n1.err; show n1 gpurun_out/n1.json
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/n2.json 2> gpurun_out/n2.err; show n2_default gpurun_out/n2.json
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --overlap > gpurun_out/n2b.json 2> gpurun_out/n2b.err; show n2_overlap gpurun_out/n2b.json
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 --torch-adam > gpurun_out/n2c.json 2> gpurun_out/n2c.err; show n2_round1_path gpurun_out/n2c.json
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/n2ref.json 2> gpurun_out/n2ref.err; tail -c 300 gpurun_out/n2ref.json
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/n2.json 2> gpurun_out/n2.err; show n2_default gpurun_out/n2.json
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline --no-extras --overlap > gpurun_out/n2b.json 2> gpurun_out/n2b.err; show n2_overlap gpurun_out/n2b.json
