@@ -442,6 +442,7 @@ def run_native(args):
     # buffer, ATen fused Adam) for A/B comparison.
     from pase_b200.optim import FlatAdam
     red = None
+    peer = False
     if args.torch_adam:
         red = FlatGradAllReducer(params, attach=False) if world > 1 else None
         opt = torch.optim.Adam(params, lr=1e-4, fused=True)
@@ -453,7 +454,17 @@ def run_native(args):
             # hidden behind the backward of blocks 2..0 (pase_b200/graph.py::PipelinedDPStep)
             from pase_b200.graph import PipelinedDPStep
             params, n_lower = PipelinedDPStep.order_params(model, DP_SPLIT)
-        opt = FlatAdam(params, lr=1e-4).bind_encoder(model)
+        if world > 1 and args.dp == "peer" and not args.overlap:
+            # data parallelism fused into the update: peer-mapped flat buffers, ONE kernel does
+            # the gradient mean over this rank's shard, Adam and the parameter all-gather over
+            # NVLink (pase_adam_flat_dp) -- no collective call, the step stays one CUDA graph
+            try:
+                opt = FlatAdam(params, lr=1e-4, peer_dp=True).bind_encoder(model)
+                peer = True
+            except Exception as exc:          # noqa: BLE001 -- every rank fails together
+                sys.stderr.write("bench: peer-mapped DP unavailable (%s); NCCL all-reduce\n" % (exc,))
+        if not peer:
+            opt = FlatAdam(params, lr=1e-4).bind_encoder(model)
         grad_bytes = opt.n * 4 if world > 1 else 0
 
     def zero_grads():
@@ -515,7 +526,7 @@ def run_native(args):
     gopt = gres = gs = None
     # N>1: two captured halves ([fwd, bwd, pack gradients] and [Adam]) with the NCCL
     # all-reduce of the flat gradient buffer issued eagerly between the two replays
-    if world > 1:
+    if world > 1 and not (not args.torch_adam and peer):
         gkw = dict(post_backward=red.pack, between=red.reduce) if red is not None else \
             dict(between=opt.reduce_grads)
     else:
@@ -645,12 +656,17 @@ def run_native(args):
                        "cuda_graph": value_graphed,
                        "l2": "no flush: per-step working set (~1.7 GB activations) >> 126 MB L2",
                        "optimizer": "torch fused Adam" if args.torch_adam else
-                       "pase_adam_flat (one launch, gradients written in place)",
+                       ("pase_adam_flat_dp (one launch, moments sharded over the ranks)"
+                        if peer else "pase_adam_flat (one launch, gradients written in place)"),
                        "grad_allreduce": None if world == 1 else (
                            "one flat buffer; upper bucket overlapped with backward of blocks "
                            "%d..0 (side stream), lower bucket after" % (DP_SPLIT - 1)
                            if (args.overlap and not args.torch_adam) else
-                           "one flat buffer between two graph replays"),
+                           ("fused into the update kernel over peer memory (pase_adam_flat_dp: "
+                            "mean of the peers' gradient shards + Adam + parameter all-gather "
+                            "over NVLink, no collective call, one CUDA graph per step)"
+                            if (not args.torch_adam and peer) else
+                            "one ncclAllReduce(avg) of the flat buffer between two graph replays")),
                        "grad_allreduce_bytes": grad_bytes},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "cuda_graph": graphed, "input_prefetch": bool(graphed and not args.no_prefetch),
@@ -741,6 +757,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
+                    help="N>1 gradient exchange: 'peer' = fused into the update kernel over "
+                         "CUDA-IPC peer memory (pase_adam_flat_dp: reduce-scatter + Adam + "
+                         "all-gather, one CUDA graph per step, no collective call); 'nccl' = one "
+                         "ncclAllReduce(avg) of the flat buffer between two graph replays")
     ap.add_argument("--overlap", action="store_true",
                     help="N>1: hide the all-reduce of the large gradient bucket behind the tail "
                          "of backward (PipelinedDPStep, three graphs + side stream).  Measured "

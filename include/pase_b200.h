@@ -320,6 +320,25 @@ int pase_scale_dev(float* x, long n, const float* dev_scalar, float host_coef, v
 int pase_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n,
                    const long* seg_table, int nseg, const float* steps, float grad_scale,
                    void* stream);
+/* Data parallelism fused into the update (replaces ncclAllReduce + the update above, see
+ * SURVEY.md 8e): every rank's flat gradient / parameter / flag buffers are peer-mapped
+ * (param_peers / grad_peers / flag_peers: DEVICE arrays of `world` pointers; flags: int[2*world]
+ * per rank, zero-initialised).  One launch per rank and step: cross-GPU barrier, mean of the
+ * peers' gradients over this rank's 1/world shard read through NVLink, Adam on the local
+ * (exp_avg, exp_avg_sq) shard, new parameters stored into every rank's buffer, barrier.
+ * epoch / done: zero-initialised device scalars owned by the optimizer.  n % 4 == 0. */
+int pase_adam_flat_dp(void* const* param_peers, void* const* grad_peers,
+                      void* const* flag_peers, float* exp_avg, float* exp_avg_sq, long n,
+                      const long* seg_table, int nseg, const float* steps, int world, int rank,
+                      int* epoch, int* done, void* stream);
+/* peer-mapped buffers for pase_adam_flat_dp (CUDA IPC; same node, one process per GPU):
+ * alloc: zeroed cudaMalloc buffer on the current device + its 64-byte IPC handle;
+ * open: map a peer's buffer (handle received out of band) into the current device's address
+ * space with peer access; close / free: the inverse operations. */
+int pase_dp_alloc(long bytes, void** ptr_out, void* handle_out64);
+int pase_dp_open(const void* handle64, void** ptr_out);
+int pase_dp_close(void* ptr);
+int pase_dp_free(void* ptr);
 
 #ifdef __cplusplus
 }

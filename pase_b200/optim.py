@@ -27,7 +27,14 @@ def _ru4(n):
 
 class FlatAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 grad_buffer=None, grad_scale=1.0):
+                 grad_buffer=None, grad_scale=1.0, peer_dp=False, group=None):
+        """peer_dp=True (torch.distributed initialised, one process per GPU of ONE node): the
+        flat parameter / gradient buffers are CUDA-IPC peer-mapped across the ranks and
+        ``step()`` becomes ``pase_adam_flat_dp`` -- gradient averaging (reduce-scatter),
+        the Adam update of this rank's 1/world shard and the parameter all-gather in ONE
+        kernel over NVLink, no collective call (``reduce_grads()`` turns into a no-op).  The
+        Adam moments are then sharded: ``consolidate_state()`` (collective) before
+        ``state_dict()``."""
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         plist = [p for g in self.param_groups for p in g["params"]]
@@ -46,13 +53,33 @@ class FlatAdam(torch.optim.Optimizer):
             self._ranges.append((start, off))
         self.n = off
         f32 = dict(dtype=torch.float32, device=dev)
-        self.flat_param = torch.zeros(self.n, **f32)
+        self._peer = None
+        if peer_dp:
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("FlatAdam(peer_dp=True) needs an initialised process group")
+            if grad_buffer is not None:
+                raise ValueError("FlatAdam: peer_dp allocates its own gradient buffer")
+            world = dist.get_world_size(group)
+            if world > 1:
+                from .peer import PeerAlloc, PeerGroup
+                allocs = {"param": PeerAlloc(self.n, torch.float32, dev),
+                          "grad": PeerAlloc(self.n, torch.float32, dev),
+                          "flag": PeerAlloc(2 * world, torch.int32, dev)}
+                self._peer = PeerGroup(allocs, group)
+                self._peer_sync = torch.zeros(2, dtype=torch.int32, device=dev)   # epoch, done
+                self._group = group
+        if self._peer is not None:
+            self.flat_param = self._peer.allocs["param"].tensor
+            self.flat_grad = self._peer.allocs["grad"].tensor
+        else:
+            self.flat_param = torch.zeros(self.n, **f32)
+            if grad_buffer is not None and grad_buffer.numel() != self.n:
+                raise ValueError("FlatAdam: grad_buffer has %d elements, layout needs %d"
+                                 % (grad_buffer.numel(), self.n))
+            self.flat_grad = grad_buffer if grad_buffer is not None else torch.zeros(self.n, **f32)
         self.exp_avg = torch.zeros(self.n, **f32)
         self.exp_avg_sq = torch.zeros(self.n, **f32)
-        if grad_buffer is not None and grad_buffer.numel() != self.n:
-            raise ValueError("FlatAdam: grad_buffer has %d elements, layout needs %d"
-                             % (grad_buffer.numel(), self.n))
-        self.flat_grad = grad_buffer if grad_buffer is not None else torch.zeros(self.n, **f32)
         self.grad_scale = float(grad_scale)
         self._plist = plist
         self._pviews, self._gviews = [], []
@@ -122,6 +149,8 @@ class FlatAdam(torch.optim.Optimizer):
     def reduce_grads(self, group=None):
         """Data parallelism: ONE all-reduce (average) of the flat gradient buffer."""
         import torch.distributed as dist
+        if self._peer is not None:
+            return self.flat_grad            # averaged inside step() (pase_adam_flat_dp)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             self.pack_grads()
             if dist.get_backend(group) == "nccl":
@@ -154,9 +183,37 @@ class FlatAdam(torch.optim.Optimizer):
                 loss = closure()
         self.pack_grads()
         self.steps += 1.0
+        if self._peer is not None:
+            pg = self._peer
+            ops.call("pase_adam_flat_dp", pg.table("param"), pg.table("grad"), pg.table("flag"),
+                     self.exp_avg, self.exp_avg_sq, self.n, self._segments(),
+                     len(self.param_groups), self.steps, pg.world, pg.rank,
+                     self._peer_sync[0:1], self._peer_sync[1:2])
+            return loss
         ops.call("pase_adam_flat", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
                  self.n, self._segments(), len(self.param_groups), self.steps, self.grad_scale)
         return loss
+
+    def shard_range(self):
+        """[lo, hi) of the flat index space whose Adam moments this rank maintains."""
+        if self._peer is None:
+            return 0, self.n
+        per = ((self.n + 3) // 4 + self._peer.world - 1) // self._peer.world
+        return min(per * self._peer.rank * 4, self.n), min(per * (self._peer.rank + 1) * 4, self.n)
+
+    def consolidate_state(self):
+        """peer_dp: gather every rank's shard of (exp_avg, exp_avg_sq) so that ``state_dict()``
+        is complete on every rank.  Collective -- call it on all ranks before checkpointing."""
+        if self._peer is None:
+            return
+        import torch.distributed as dist
+        per = ((self.n + 3) // 4 + self._peer.world - 1) // self._peer.world * 4
+        for buf in (self.exp_avg, self.exp_avg_sq):
+            pad = torch.zeros(per * self._peer.world, dtype=buf.dtype, device=buf.device)
+            pad[:self.n] = buf
+            lo = per * self._peer.rank
+            dist.all_gather_into_tensor(pad, pad[lo:lo + per].clone(), group=self._group)
+            buf.copy_(pad[:self.n])
 
     # ---- torch.optim.Adam-compatible persistence ----------------------------------------
     def state_dict(self):
