@@ -249,9 +249,10 @@ int pase_adam_flat_dp(void* const* param_peers, void* const* grad_peers,
            reinterpret_cast<unsigned*>(done)};
   const long shard4 = ((n + 3) / 4 + world - 1) / world;
   long blocks = (shard4 + 255) / 256;
-  // every block spins in barrier A and the last one in barrier B: the grid must be
-  // co-resident with whatever else runs, so keep it to one wave
-  const long cap = (long)pase_num_sms() * 4;
+  // one wave of 8 x 256 threads per SM: every thread has its remote loads (NVLink latency
+  // ~3 us) in flight at once instead of walking a long grid-stride loop.  (Blocks wait for
+  // the PEERS in barrier A, never for each other, so more waves would also be correct.)
+  const long cap = (long)pase_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adam_flat_dp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
