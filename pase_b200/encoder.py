@@ -184,8 +184,7 @@ class EncoderPlan(object):
         self.pool_d = [max(g.T_out // self.Tq, 1) for g in G[:-1]]
 
         self.apad, self.apad_lo, self.y, self.bn = [], [], [], []
-        self.Wt, self.dWt, self.Wd, self.dyz, self.dyz_lo, self.dxpad = [], [], [], [], [], []
-        self.gscale = []
+        self.Wt = []
         for g in G:
             n_apad = N * g.apad_floats + g.K + 64
             self.apad.append(zo(n_apad))
@@ -194,6 +193,59 @@ class EncoderPlan(object):
             self.y.append(torch.empty(int(N * g.rows_out * g.Nn), **yd))
             self.bn.append(torch.zeros(4, g.Cout, **f32))       # mean, invstd, scale, shift
             self.Wt.append(e(g.Nn * g.K))
+        rows = N * self.Tq
+        self.rows = rows
+        if self.rnn:
+            Cq, H = self.Clast, self.H
+            n_xq = N * (self.Tq + 1) * Cq + 2 * Cq + 64
+            self.xq, self.xq_lo = zo(n_xq), zlo(n_xq)
+            self._ops["xq"] = Operand(self.xq, self.xq_lo)
+            self.Yg, self.Cst = e(rows * 3 * H), e(rows * H)
+            self.Wq = e(3 * H * 2 * Cq)
+        self.cat = z(rows * self.Kc)
+        self.Wcat = e(self.emb * self.Kc)
+        self.yout = e(rows * self.emb)
+        self.bn_out = torch.zeros(4, self.emb, **f32)
+        self.bn_out[1].fill_(1.0)
+        self.bn_out[2].fill_(1.0)
+
+        # double-precision accumulators: forward batch statistics ...
+        self.fs_off, n = [], 0
+        for g in G:
+            self.fs_off.append(n)
+            n += 2 * g.Nn
+        self.fs_out = n
+        n += 2 * self.emb
+        self.stats_f = torch.zeros(n, **f64)
+        self.zeros64 = torch.zeros(max(2 * max(g.Cout for g in G), 2 * self.emb), **f64)
+        # everything only the backward pass touches is allocated on first use
+        # (`ensure_backward`): inference / feature extraction at a new (N, T) -- the main
+        # downstream use, one plan per utterance length -- costs the forward buffers only
+        self.backward_ready = False
+        self.dWt = self.Wd = self.dyz = self.dyz_lo = self.dxpad = self.gscale = None
+        self.dYg = self.dsrc = self.WqT = self.dWq = None
+        self.dcat = self.WcatT = self.dWcat = self.g = None
+        self.stats_b = self.grad_vec = self.amax = None
+        self.generation = 0
+
+    def ensure_backward(self):
+        """Allocate the backward-only buffers (input / output gradients in operand format,
+        weight-gradient and dgrad-weight layouts, fp64 reduction accumulators).  Called by
+        WaveFe.encode before a forward that will be differentiated, i.e. during the eager
+        warm-up steps and never inside a CUDA-graph capture."""
+        if self.backward_ready:
+            return
+        G, N, mode, device = self.geoms, self.N, self.mode, self.device
+        f32 = dict(dtype=torch.float32, device=device)
+        f64 = dict(dtype=torch.float64, device=device)
+        opd = dict(dtype=self.op_dtype, device=device)
+        yd = dict(dtype=torch.bfloat16 if mode == 2 else torch.float32, device=device)
+        z = lambda n: torch.zeros(int(n), **f32)
+        e = lambda n: torch.empty(int(n), **f32)
+        zo = lambda n: torch.zeros(int(n), **opd)
+        zlo = lambda n: torch.zeros(int(n), **opd) if self.split_mode else None
+        self.dWt, self.Wd, self.dyz, self.dyz_lo, self.dxpad, self.gscale = [], [], [], [], [], []
+        for g in G:
             self.dWt.append(e(g.Nn * g.K))
             gs = torch.ones(2, **f32) if mode == 3 else None
             self.gscale.append(gs)
@@ -209,39 +261,18 @@ class EncoderPlan(object):
             self.dyz_lo.append(zlo(n_dyz))
             self._ops[("dyz", g.idx)] = Operand(self.dyz[-1], self.dyz_lo[-1],
                                                 None if gs is None else gs, kind="grad")
-        rows = N * self.Tq
-        self.rows = rows
+        rows = self.rows
         if self.rnn:
             Cq, H = self.Clast, self.H
-            n_xq = N * (self.Tq + 1) * Cq + 2 * Cq + 64
-            self.xq, self.xq_lo = zo(n_xq), zlo(n_xq)
-            self._ops["xq"] = Operand(self.xq, self.xq_lo)
-            self.Yg, self.Cst, self.dYg = e(rows * 3 * H), e(rows * H), z(rows * 3 * H + 64)
+            self.dYg = z(rows * 3 * H + 64)
             self.dsrc = e(rows * 2 * Cq)
-            self.Wq = e(3 * H * 2 * Cq)
             self.WqT = e(2 * Cq * 3 * H)
             self.dWq = e(3 * H * 2 * Cq)
-        self.cat = z(rows * self.Kc)
         self.dcat = e(rows * self.Kc)
-        self.Wcat = e(self.emb * self.Kc)
         self.WcatT = e(self.Kc * self.emb)
         self.dWcat = e(self.emb * self.Kc)
-        self.yout = e(rows * self.emb)
         self.g = torch.zeros(rows * self.emb + 64, **f32)     # +slack: TC wgrad reads whole blocks
-        self.bn_out = torch.zeros(4, self.emb, **f32)
-        self.bn_out[1].fill_(1.0)
-        self.bn_out[2].fill_(1.0)
-
-        # double-precision accumulators: forward batch statistics ...
-        self.fs_off, n = [], 0
-        for g in G:
-            self.fs_off.append(n)
-            n += 2 * g.Nn
-        self.fs_out = n
-        n += 2 * self.emb
-        self.stats_f = torch.zeros(n, **f64)
-        # ... and backward reductions: per block S1,S2,dalpha,dbias; output S1,S2;
-        # qrnn bias; W bias.
+        # backward reductions: per block S1,S2,dalpha,dbias; output S1,S2; qrnn bias; W bias
         self.bs_off, n = [], 0
         for g in G:
             self.bs_off.append(n)
@@ -254,10 +285,9 @@ class EncoderPlan(object):
         n += self.emb
         self.stats_b = torch.zeros(n, **f64)
         self.grad_vec = torch.zeros(n, **f32)
-        self.zeros64 = torch.zeros(max(2 * max(g.Cout for g in G), 2 * self.emb), **f64)
         # running maxima for the 3xF16 gradient scales: 2 floats per use, zeroed per backward
         self.amax = torch.zeros(2 * (self.nblk + 4), **f32) if mode == 3 else None
-        self.generation = 0
+        self.backward_ready = True
 
     # -- GEMM operands -----------------------------------------------------------------
     def operand(self, name, buf, fresh=True, kind="act"):
@@ -586,6 +616,7 @@ def encoder_backward_steps(plan, mod, params, gout, gntc, training, sink=None, s
     conv weight gradients by the batched re-layout, the sinc cut-offs by pase_sinc_grad,
     everything else by one batched strided copy -- and {} is returned: no per-parameter
     clones, no autograd accumulation kernels, no packing before the all-reduce."""
+    plan.ensure_backward()
     call = ops.call
     cfg, G, N = plan.cfg, plan.geoms, plan.N
     Tq, Kc, rows, emb = plan.Tq, plan.Kc, plan.rows, plan.emb
@@ -835,6 +866,7 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mod, plan, training, names, *tensors):
         params = dict(zip(names, tensors))
+        plan.ensure_backward()
         out, out_ntc = encoder_forward(plan, mod, x, params, training, True)
         ctx.mod, ctx.plan, ctx.training, ctx.names = mod, plan, training, names
         ctx.generation = plan.generation

@@ -217,6 +217,7 @@ class WaveFe(Model):
             raise RuntimeError("WaveFe parameters live on %s but the input is on %s"
                                % (tensors[0].device, x.device))
         if torch.is_grad_enabled() and any(p.requires_grad for p in tensors):
+            plan.ensure_backward()
             return _enc._EncoderFn.apply(x, self, plan, self.training, names, *tensors)
         with torch.no_grad():
             return _enc.encoder_forward(plan, self, x, dict(named), self.training, False)

@@ -222,3 +222,25 @@ def test_gradient_sink_equals_autograd_path(emulated):
         for (k, a), (_, b) in zip(ref.named_parameters(), nat.named_parameters()):
             if it == 0 or not k.endswith(("conv.bias", "W.bias")):
                 assert torch.allclose(a, b, rtol=1e-5, atol=2e-6), k
+
+
+def test_forward_only_plan_allocates_no_backward_buffers(emulated):
+    """Inference at a new (N, T) builds the forward buffers only (feature extraction over
+    per-utterance lengths); the first differentiated forward adds the backward set."""
+    gold, meta = load_golden("enc_pasep_train_3200")
+    cfg = resolve_cfg(meta["cfg"])
+    model = WaveFe(**cfg)
+    model.precision = "3xf16"
+    model.load_state_dict(fill_state_dict(model.state_dict(), meta["seed"]))
+    model.train(True)
+    x = seeded_randn((meta["N"], 1, meta["T"]), meta["seed"] + 1, 0.5)
+    with torch.no_grad():
+        y0, _ = run_encoder_cpu(model, x)
+    plan = model._plan(x.shape[0], x.shape[2], x.device)
+    assert not plan.backward_ready and plan.dyz is None and plan.stats_b is None
+    fwd_bytes = plan.nbytes()
+    y, _ = run_encoder_cpu(model, x)
+    assert plan.backward_ready and plan.nbytes() > 1.5 * fwd_bytes
+    assert_close(y, gold["y"], 1e-4, 1e-5, "after the lazy allocation")
+    y.square().mean().backward()
+    assert all(p.grad is not None for p in model.parameters())
