@@ -409,6 +409,37 @@ def time_encoder_config(dev, stream, precision, B, T, steps=10):
             "value": B * T / (ms * 1e-3), "unit": "samples/s", "plan_gb": mem}
 
 
+def time_lps_targets(dev, B=B_PER_GPU, T=T_CHUNK, reps=10):
+    """the lps + lps_long regression targets of one step computed ON the GPU
+    from the chunks already resident there (pase_b200/targets.py), next to the reference's way
+    (torch.stft + librosa-style deltas per chunk on the host, then an H2D copy of the labels)."""
+    import time
+    from pase_b200.targets import LPS
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import targets_oracle as TO
+    wav = torch.randn(B, 1, T, device=dev) * 0.3
+    tr = [LPS(win=400, name="lps"), LPS(win=512, name="lps_long")]
+    for t in tr:
+        t(wav)
+    ms = _event_time(lambda: [t(wav) for t in tr], reps)
+    w0 = wav[0, 0].cpu()
+    t0 = time.perf_counter()
+    n_cpu = 2
+    for _ in range(n_cpu):
+        TO.lps(w0, 2048, 160, 400, 2)
+        TO.lps(w0, 2048, 160, 512, 2)
+    cpu_ms_chunk = (time.perf_counter() - t0) / n_cpu * 1e3
+    nbytes = 2 * B * 3075 * (T // 160) * 4
+    return {"config": "N1: lps + lps_long regression targets of one step on the GPU, B=%d, "
+                      "T=%d (2 x (B, 3075, %d) fp32)" % (B, T, T // 160),
+            "ms_per_step": ms, "launches": 6,
+            "label_bytes_not_copied_h2d": nbytes,
+            "cpu_reference_ms_per_chunk": cpu_ms_chunk,
+            "cpu_reference_ms_per_step_one_core": cpu_ms_chunk * B,
+            "note": "reference path = oracle/targets_oracle.py (torch.stft + savgol deltas) per "
+                    "chunk on one host core, as a DataLoader worker runs it"}
+
+
 # ------------------------------------------------------------------ GPU arm ---
 def run_native(args):
     import torch.distributed as dist
@@ -735,6 +766,10 @@ def run_native(args):
                 others.append(w)
             except Exception as exc:
                 others.append({"config": "workers+ full step", "error": repr(exc)[:300]})
+            try:
+                others.append(time_lps_targets(dev))
+            except Exception as exc:
+                others.append({"config": "on-device lps targets", "error": repr(exc)[:300]})
             line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu(4, 3, 1, budget_s=30.0)

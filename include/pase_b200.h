@@ -340,6 +340,21 @@ int pase_dp_open(const void* handle64, void** ptr_out);
 int pase_dp_close(void* ptr);
 int pase_dp_free(void* ptr);
 
+/* ---- on-device regression targets (pase/transforms.py:439-487 LPS, 183-202 ZNorm) ---- */
+/* frames matrix of the STFT as an fp16 (hi, lo') pair GEMM operand: row (n, j), column m =
+ * x[n][reflect(j*hop + start0 + m)] for m < win (the samples the rectangular window keeps;
+ * start0 = (n_fft - win)/2 - n_fft/2), zero for win <= m < lda. */
+int pase_frame_wave(const float* x, int N, int T, int hop, int win, int start0, int frames,
+                    void* hi, void* lo, int lda, void* stream);
+/* C (N*frames, ldc): columns (2k, 2k+1) = (re, im) of bin k.  out (N, (1+der_order)*nbins,
+ * frames): 10 log10(|X|^2 + 1e-19), then its Savitzky-Golay derivatives of order 1..der_order
+ * along time (fir: der_order rows of `width` correlation taps; edge frames use the nearest
+ * full window = scipy/librosa mode 'interp' with polyorder == deriv), optionally
+ * (v - mean[f]) / std[f] per feature row. */
+int pase_lps_post(const float* C, long ldc, int N, int frames, int nbins, int der_order,
+                  int width, const float* fir, const float* mean, const float* stdv, float* out,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -674,3 +674,31 @@ def pase_tc_gemm_nt_ctxmse(Ahi, Alo, a_rows, R, Bhi, Blo, ldb, Rhi, Rlo, ldr, M,
     out_lo[:, :N] = ((v - hi.float()) * F16_LO_MUL).to(torch.float16)
     Rhi[:M * ldr] = out_hi.reshape(-1)
     Rlo[:M * ldr] = out_lo.reshape(-1)
+
+
+def pase_frame_wave(x, N, T, hop, win, start0, frames, hi, lo, lda):
+    idx = (torch.arange(frames)[:, None] * hop + start0 + torch.arange(win)[None, :])
+    idx = _reflect(idx, T)
+    A = torch.zeros(N, frames, lda)
+    A[:, :, :win] = x[:N * T].view(N, T)[:, idx]
+    h = A.to(torch.float16)
+    hi[:N * frames * lda] = h.reshape(-1)
+    lo[:N * frames * lda] = ((A - h.float()) * F16_LO_MUL).to(torch.float16).reshape(-1)
+
+
+def pase_lps_post(C, ldc, N, frames, nbins, der_order, width, fir, mean, stdv, out):
+    spec = _as(C, (N, frames, ldc), (frames * ldc, ldc, 1))
+    re, im = spec[:, :, 0:2 * nbins:2], spec[:, :, 1:2 * nbins:2]
+    mag = torch.sqrt(re * re + im * im)
+    X = (10.0 * torch.log10(mag * mag + 1e-19)).permute(0, 2, 1)          # (N, nbins, frames)
+    feats = [X]
+    half = width // 2
+    for d in range(1, der_order + 1):
+        taps = fir[(d - 1) * width:d * width]
+        c = torch.arange(frames).clamp(half, frames - 1 - half)
+        win = c[:, None] - half + torch.arange(width)[None, :]               # (frames, width)
+        feats.append((X[:, :, win] * taps).sum(-1))
+    Y = torch.cat(feats, 1)
+    if mean is not None:
+        Y = (Y - mean[:Y.shape[1], None]) / stdv[:Y.shape[1], None]
+    out[:Y.numel()] = Y.reshape(-1)
