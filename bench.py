@@ -282,7 +282,21 @@ def time_workers(dev, precision, B, T=T_CHUNK, steps=5, warmup=3, graph=True, st
             torch.cuda.synchronize()
     ms = _event_time(fn, steps)
     nparam = sum(p.numel() for p in model.parameters())
+    # algorithmic FLOPs of the step as the reference computes it (per step at
+    # B=32: encoder on the 3B = 96 chunks 2438 GFLOP, 9 MLP heads 487, cchunk decoder 1409),
+    # scaled with B; counted once per product whatever the GEMM mode issues
+    gflop = (2438.0 + 487.0 + 1409.0) * B / 32.0 * (T / float(T_CHUNK))
+    pk = load_peaks()
+    peak = pk["tf_sustained"]
+    ach = gflop / ms                      # GFLOP / ms = TFLOP/s
+    roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "traffic": None,
+            "algorithmic_gflop_per_step": gflop,
+            "note": "FLOPs as the reference computes the step (SURVEY.md 8d), counted once per "
+                    "product; peak = sustained bf16 tensor rate (" + pk["src"] + "); "
+                    "per-kernel times of this step: profiles/r02_timeline_workers.md"}
     return {"metric": "waveform-samples/sec PASE+ encoder(3B chunks)+workers+ heads fwd+bwd+adam",
+            "roofline": roof,
             "value": B * T / (ms * 1e-3), "unit": "chunk-samples/s", "ms_per_step": ms,
             "n_gpus": 1, "cuda_graph": graphed, "graph_error": why,
             "loss": float(loss_dev),
