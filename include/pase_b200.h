@@ -232,7 +232,8 @@ int pase_bn_prelu_bwd_apply(const void* y, int y_bf16, long y_sample_stride, int
                             const void* du, void* dst, void* dst_lo, int dst_fmt,
                             long dst_sample_stride, double* dbias_acc,
                             const float* amax, float* scale_out, void* stream);
-/* backward, pass 2 WITHOUT a stored du: du = PReLU'(u) g is recomputed from the gradient
+/* backward of FeBlock's norm -> act (pase/models/modules.py:1072-1075, autograd of
+ * BatchNorm1d + PReLU), pass 2 WITHOUT a stored du: du = PReLU'(u) g is recomputed from the gradient
  * sources (arguments as in pass 1, which is then called with dst = NULL and writes only its
  * sums): one write and one read of the layer's activation size less per block. */
 int pase_bn_prelu_bwd_apply_src(const void* y, int y_bf16, long y_sample_stride, int N, int T,
@@ -320,8 +321,9 @@ int pase_scale_dev(float* x, long n, const float* dev_scalar, float host_coef, v
 int pase_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n,
                    const long* seg_table, int nseg, const float* steps, float grad_scale,
                    void* stream);
-/* Data parallelism fused into the update (replaces ncclAllReduce + the update above, see
- * SURVEY.md 8e): every rank's flat gradient / parameter / flag buffers are peer-mapped
+/* Data parallelism fused into the update (the reference is single-GPU: its per-worker Adam
+ * instances, trainer.py:86-143 / worker_scheduler.py:66-73, have no exchange step; this
+ * replaces ncclAllReduce + the update above): every rank's flat gradient / parameter / flag buffers are peer-mapped
  * (param_peers / grad_peers / flag_peers: DEVICE arrays of `world` pointers; flags: int[2*world]
  * per rank, zero-initialised).  One launch per rank and step: cross-GPU barrier, mean of the
  * peers' gradients over this rank's 1/world shard read through NVLink, Adam on the local
