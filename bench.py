@@ -694,6 +694,9 @@ def run_native(args):
                       "3xf16": "f32 (3xF16 split on tcgen05, fp32 accumulate: fp32-equivalent "
                                "products)", "tf32": "tf32", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
+            "parity": "oracle pinned to goldens of the unmodified reference (tests/golden); the "
+                      "QRNN layer follows SURVEY.md A.2 (torchqrnn is un-vendored and unpinned "
+                      "upstream: parity for that layer is unpinned)",
             "config": {"workload": "PASE+.cfg encoder fwd+bwd+adam, B=32/GPU, T=32000, fp32, "
                                    "train-mode BN, no workers (BASELINE configs[1])",
                        "global_batch": B_PER_GPU * world, "seq_len": T_CHUNK,
