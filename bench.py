@@ -423,6 +423,30 @@ def time_encoder_config(dev, stream, precision, B, T, steps=10):
             "value": B * T / (ms * 1e-3), "unit": "samples/s", "plan_gb": mem}
 
 
+def gemm_time_in_replay(step_fn, gemm_flop_per_step, peak_tflops, reps=3):
+    """Sum of the tcgen05 GEMM kernels' device durations inside `reps` replays of the captured
+    step, from torch.profiler's CUDA activity records (same method as tools/gpu/kineto_step.py,
+    profiles/r02_timeline_*.md)."""
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            step_fn()
+        torch.cuda.synchronize()
+    us, n = 0.0, 0
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA and "tc_gemm" in e.name:
+            us += e.time_range.end - e.time_range.start
+            n += 1
+    if n == 0:
+        raise RuntimeError("no GEMM kernel records")
+    ms = us / 1e3 / reps
+    ach = gemm_flop_per_step / (ms * 1e-3) / 1e12
+    return {"gemm_ms_per_step": ms, "gemm_launches_per_step": n // reps, "achieved": ach,
+            "unit": "TFLOP/s", "frac": ach / peak_tflops,
+            "how": "torch.profiler CUDA activity records of %d graph replays" % reps}
+
+
 def time_lps_targets(dev, B=B_PER_GPU, T=T_CHUNK, reps=10):
     """the lps + lps_long regression targets of one step computed ON the GPU
     from the chunks already resident there (pase_b200/targets.py), next to the reference's way
@@ -749,7 +773,7 @@ def run_native(args):
         }
         if world == 1 and not args.no_extras:
             # everything below is measured AFTER the timed regions of the headline numbers
-            gres = gs = None                # release the captured graphs' memory pools
+            gs = None                       # release the e2e graph's memory pool
             torch.cuda.empty_cache()
             pk = measure_matmul_peaks(dev)
             line["peaks_measured_here"] = pk
@@ -788,6 +812,17 @@ def run_native(args):
             except Exception as exc:
                 others.append({"config": "on-device lps targets", "error": repr(exc)[:300]})
             line["other_configs"] = others
+            if value_graphed and gres is not None:
+                # LAST (profiling must not touch any timed number): the GEMM launches' device
+                # time INSIDE the graph replay that `value` times (CUPTI activity records through
+                # torch.profiler: no per-launch events, no launch gaps, warm caches), next to
+                # the event-bracketed figure of `roofline.achieved`
+                try:
+                    line["roofline"]["in_replay"] = gemm_time_in_replay(
+                        lambda: gres.step(), gemm_flop, peaks["tf_sustained"])
+                except Exception as exc:                  # never lose the headline line
+                    line["roofline"]["in_replay"] = {"error": repr(exc)[:200]}
+            gres = None
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu(4, 3, 1, budget_s=30.0)
             line["cpu_baseline"] = {
